@@ -1,0 +1,179 @@
+/* tcr_b200.h — C ABI of the B200-native TC-ResNet hot path (libtcr_b200.so).
+ *
+ * The reference (hyperconnect/TC-ResNet) has no FFI: its "plugin API" is Python-level and the
+ * arithmetic runs inside TensorFlow 1.13's Session.run.  This header is the boundary a maintainer
+ * binds with ctypes; each entry point names the reference interface whose
+ * arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in signatures.
+ *   - every function returns an int status (TCR_OK == 0); tcr_last_error() gives the message of the
+ *     last failure on the calling thread.  Functions never throw and never exit.
+ *   - the CALLER owns every tensor buffer (device pointers, fp32, row-major) and the stream;
+ *     the library owns only the opaque handle and its private workspace.
+ *   - one handle per (GPU, stream); a handle is not thread-safe, distinct handles are independent.
+ *   - all activations are (N, T, C) row-major with C fastest (== the reference's NHWC [N,T,1,C]);
+ *     conv weights are HWIO [k,1,C_in,C_out] exactly as TF stores them, so flat parameter buffers
+ *     can be filled from / dumped to reference checkpoints by name (tcr_param_table).
+ */
+#ifndef TCR_B200_H_
+#define TCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCR_ABI_VERSION 1
+
+enum {
+  TCR_OK = 0,
+  TCR_ERR_INVALID = 1,      /* bad argument / unsupported configuration */
+  TCR_ERR_CUDA = 2,         /* CUDA runtime or launch failure */
+  TCR_ERR_UNSUPPORTED = 3,
+  TCR_ERR_COMM = 4          /* NCCL failure or libnccl not loadable */
+};
+
+enum { TCR_MODEL_TCRESNET8 = 8, TCR_MODEL_TCRESNET14 = 14 };
+enum { TCR_FEATURE_MFCC = 0, TCR_FEATURE_LOG_MEL = 1 };
+
+typedef struct tcr_handle tcr_handle;
+typedef void* tcr_stream;   /* cudaStream_t */
+
+/* Everything that fixes shapes.  Mirrors the flags the reference threads through `args`:
+ * datasets/audio_data_wrapper.py:61-110 (sample_rate, clip_duration_ms, window_size_ms,
+ * window_stride_ms, num_mel_bins, num_mfccs, lower/upper_edge_hertz), factory/base.py:13-35
+ * (num_classes, preprocess_method), factory/audio_nets.py:366-370 (width_multiplier,
+ * dropout_keep_prob), audio_nets/tc_resnet.py:102-123 (BN decay 0.997, eps 0.001). */
+typedef struct tcr_config {
+  int32_t model;                  /* TCR_MODEL_TCRESNET8 | TCR_MODEL_TCRESNET14 (audio_nets/tc_resnet.py:57,65) */
+  float   width_multiplier;       /* channels = int(c * width_multiplier); every count must be a multiple of 4 */
+  int32_t num_classes;            /* 12 */
+  int32_t sample_rate;            /* 16000 */
+  int32_t clip_samples;           /* int(sample_rate * clip_duration_ms / 1000) = 16000 */
+  int32_t window_size_samples;    /* int(sample_rate * window_size_ms / 1000): 640 (T=49) or 480 (T=98) */
+  int32_t window_stride_samples;  /* 320 or 160 */
+  int32_t num_mel_bins;           /* 64 */
+  int32_t num_mfccs;              /* 40 */
+  float   lower_edge_hertz;       /* 80 */
+  float   upper_edge_hertz;       /* 7600 */
+  int32_t feature_kind;           /* TCR_FEATURE_MFCC (power + DCT) | TCR_FEATURE_LOG_MEL (magnitude, no DCT) */
+  int32_t max_batch;              /* workspace is sized for this many utterances per call */
+  float   bn_decay;               /* 0.997 */
+  float   bn_epsilon;             /* 0.001 */
+  float   dropout_keep_prob;      /* 0.5 (1.0 disables dropout) */
+  float   label_smoothing;        /* 0.0 */
+  int32_t device;                 /* CUDA device ordinal */
+} tcr_config;
+
+typedef struct tcr_info {
+  int32_t abi_version;
+  int32_t frames;          /* T  = 1 + (clip - window) / stride */
+  int32_t features;        /* F  = num_mfccs or num_mel_bins */
+  int32_t fft_length;      /* next pow2 >= window */
+  int32_t num_conv_layers; /* conv0 + per block (down?) + 2 */
+  int32_t num_blocks;
+  int32_t last_channels;
+  int32_t last_frames;
+  int64_t num_trainable;   /* floats in the flat `params`, `slots`, `grads` buffers */
+  int64_t num_moving;      /* floats in the flat BN moving-statistics buffer */
+  int64_t forward_flops_per_utt;   /* 2 FLOP per MAC, network only */
+  int64_t workspace_bytes;
+} tcr_info;
+
+enum { TCR_KIND_WEIGHT = 0, TCR_KIND_BETA = 1, TCR_KIND_GAMMA = 2, TCR_KIND_MOVING_MEAN = 3, TCR_KIND_MOVING_VAR = 4 };
+
+/* One row per TF variable.  `name` is the reference's variable name (e.g.
+ * "TCResNet8/block0/conv0_0/BatchNorm/gamma"); trainables come first in
+ * tf.trainable_variables() order (offsets into params/slots/grads), then the moving statistics
+ * (offsets into the moving buffer).  Replaces the by-name access of common/model_loader.py:87-165
+ * and the injection hook helper/trainer.py:145-154. */
+typedef struct tcr_param_desc {
+  char    name[96];
+  int32_t kind;
+  int32_t rank;
+  int32_t shape[4];
+  int64_t offset;
+  int64_t numel;
+} tcr_param_desc;
+
+/* Arguments of one training step == one `session.run(train_op)` of helper/trainer.py:312-321. */
+typedef struct tcr_step_args {
+  const float* input;        /* wav [n, clip_samples] in [-1,1], or features [n,T,F] if input_is_features */
+  int32_t      input_is_features;
+  const float* onehot;       /* [n, num_classes] fp32 (datasets/audio_data_wrapper.py:113-118) */
+  int32_t      n;            /* utterances on THIS rank */
+  float*       params;       /* flat trainables, updated in place */
+  float*       slots;        /* flat momentum accumulators (`<var>/Momentum`), updated in place */
+  float*       moving;       /* flat BN moving mean/variance, updated in place */
+  float        learning_rate;
+  float        momentum;     /* 0.9 */
+  float        weight_decay; /* 0.001 */
+  uint64_t     dropout_seed; /* counter-based RNG seed; ignored when dropout_mask != NULL or keep_prob == 1 */
+  const float* dropout_mask; /* optional injected {0,1} mask [n, last_channels] (parity runs) */
+  float*       losses;       /* optional device [2]: total_loss, model_loss (factory/audio_nets.py:161-183) */
+  float*       logits;       /* optional device [n, num_classes] */
+  float*       probs;        /* optional device [n, num_classes] softmax (output/softmax) */
+  float*       grads;        /* optional device [num_trainable]: gradient of total_loss actually applied */
+  int32_t      apply_update; /* 1: momentum update + BN moving update; 0: gradients only */
+} tcr_step_args;
+
+int         tcr_abi_version(void);
+const char* tcr_last_error(void);
+
+/* Fills *cfg with the BASELINE shape: TCResNet8-1.0, 16 kHz 1 s clips, 40 ms / 20 ms windows (T=49). */
+int tcr_config_default(tcr_config* cfg);
+
+/* Builds the layer plan, constant tables (Hann window, FFT twiddles, banded mel weights, DCT) and
+ * the device workspace.  Replaces graph construction in AudioNetModel.build
+ * (factory/audio_nets.py:41-60) and tc_resnet (audio_nets/tc_resnet.py:6-54). */
+int tcr_create(const tcr_config* cfg, tcr_handle** out);
+int tcr_destroy(tcr_handle* h);
+int tcr_get_info(const tcr_handle* h, tcr_info* out);
+int tcr_param_table(const tcr_handle* h, const tcr_param_desc** descs, int32_t* count);
+
+/* Xavier-uniform weights, gamma=1, beta=0, moving mean/var = 0/1, slots = 0
+ * (TCResNet_arg_scope, audio_nets/tc_resnet.py:102-123).  Host-side RNG (not TF's), written with
+ * cudaMemcpyAsync on `stream`.  Any of params/slots/moving may be NULL. */
+int tcr_init_variables(tcr_handle* h, float* params, float* slots, float* moving, uint64_t seed, tcr_stream stream);
+
+/* Front-end only: wav [n, clip_samples] -> features [n, T, F].
+ * Replaces MFCCPreprocessor._preprocess / LogMelSpectrogramPreprocessor._preprocess
+ * (datasets/preprocessors.py:64-96, 162-170, 183-194). */
+int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream);
+
+/* Forward pass.  is_training == 0: evaluate_audio.py path (BN moving statistics, dropout identity;
+ * helper/base.py:52-125).  is_training == 1: the training graph's forward (batch statistics, dropout)
+ * as run by the trainer's in-loop evaluation (helper/trainer.py:436-460); `moving` is not updated.
+ * onehot/losses may be NULL; when both are given losses[0..1] = total_loss, model_loss. */
+int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, const float* params,
+                const float* moving, int32_t n, int32_t is_training, uint64_t dropout_seed,
+                const float* dropout_mask, const float* onehot, float weight_decay,
+                float* logits, float* probs, float* losses, tcr_stream stream);
+
+/* Forward + backward + SGD-momentum + BN moving-average update (helper/trainer.py:171-222,
+ * slim.learning.create_train_op).  With a communicator attached (tcr_comm_init) gradients are
+ * averaged over ranks with one ncclAllReduce before the update. */
+int tcr_train_step(tcr_handle* h, const tcr_step_args* args, tcr_stream stream);
+
+/* Debug / parity inspection: device pointer of a named workspace tensor after the last call, e.g.
+ * "features", "y:conv0", "y:block0/conv0_0", "out:block1", "g:block0/down", "grads".
+ * Returns TCR_ERR_INVALID for unknown names. */
+int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr, int64_t* numel);
+
+/* Data-parallel plumbing (no reference counterpart: const.py:7 hard-wires one device).  The unique id
+ * (128 bytes, ncclUniqueId) is created on rank 0 and distributed by the host (torch.distributed). */
+int tcr_comm_unique_id(void* id128);
+int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int32_t world_size);
+int tcr_comm_destroy(tcr_handle* h);
+
+/* Measured fp32 FMA peak of the device the handle lives on (TFLOP/s), used as the compute-roofline
+ * denominator by bench.py.  Launches a register-resident FMA loop and times it with CUDA events. */
+int tcr_measure_fp32_peak(tcr_handle* h, double* tflops, tcr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TCR_B200_H_ */

@@ -1,0 +1,530 @@
+// tcr_api.cu — C ABI of libtcr_b200 (include/tcr_b200.h): handle, constant tables, layer plan,
+// workspace and the per-call launch sequences.  No torch types; the caller owns tensors and the stream.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+
+#include "tcr_net.h"
+#include "tcr_plan.h"
+
+using namespace tcr;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define TCR_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return fail(TCR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int tcr_abi_version(void) { return TCR_ABI_VERSION; }
+extern "C" const char* tcr_last_error(void) { return g_err; }
+
+extern "C" int tcr_config_default(tcr_config* cfg) {
+  if (!cfg) return fail(TCR_ERR_INVALID, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->model = TCR_MODEL_TCRESNET8;
+  cfg->width_multiplier = 1.0f;
+  cfg->num_classes = 12;
+  cfg->sample_rate = 16000;
+  cfg->clip_samples = 16000;
+  cfg->window_size_samples = 640;
+  cfg->window_stride_samples = 320;
+  cfg->num_mel_bins = 64;
+  cfg->num_mfccs = 40;
+  cfg->lower_edge_hertz = 80.0f;
+  cfg->upper_edge_hertz = 7600.0f;
+  cfg->feature_kind = TCR_FEATURE_MFCC;
+  cfg->max_batch = 512;
+  cfg->bn_decay = 0.997f;
+  cfg->bn_epsilon = 0.001f;
+  cfg->dropout_keep_prob = 0.5f;
+  cfg->label_smoothing = 0.0f;
+  cfg->device = 0;
+  return TCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device allocation helpers
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int dev_alloc(tcr_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (cudaMalloc(&q, bytes) != cudaSuccess) return fail(TCR_ERR_CUDA, "cudaMalloc(%zu bytes) failed", bytes);
+  h->allocs.push_back(q);
+  h->workspace_bytes += (int64_t)bytes;
+  *p = (T*)q;
+  return TCR_OK;
+}
+template <class T>
+static int dev_upload(tcr_handle* h, T** p, const std::vector<T>& v) {
+  int rc = dev_alloc(h, p, v.size());
+  if (rc) return rc;
+  if (!v.empty()) TCR_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return TCR_OK;
+}
+#define TCR_TRY(x)            \
+  do {                        \
+    int rc_ = (x);            \
+    if (rc_) return rc_;      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// front-end tables (datasets/preprocessors.py:64-96, 183-194; TF r1.13 op semantics)
+// ------------------------------------------------------------------------------------------------
+static int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+static int build_frontend_tables(tcr_handle* h) {
+  const tcr_config& c = h->cfg;
+  const int W = c.window_size_samples, fft = h->fft, nf2 = fft / 2, bins = nf2 + 1;
+  // tf.contrib.signal.hann_window(periodic=True): n = W + even - 1, w = 0.5 - 0.5 cos(2 pi i / n)
+  std::vector<float> win(W);
+  const int even = 1 - W % 2;
+  const double nn = (double)(W + even - 1);
+  for (int i = 0; i < W; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / nn));
+  std::vector<float2> tw(nf2), tw2(bins);
+  for (int i = 0; i < nf2; ++i) {
+    const double a = -2.0 * M_PI * i / nf2;
+    tw[i] = make_float2((float)cos(a), (float)sin(a));
+  }
+  for (int k = 0; k < bins; ++k) {
+    const double a = -2.0 * M_PI * k / fft;
+    tw2[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  // linear_to_mel_weight_matrix(num_mel_bins, bins, sample_rate, lower, upper): HTK mel, DC bin zeroed.
+  const int M = c.num_mel_bins;
+  auto mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+  std::vector<double> edges(M + 2);
+  const double mlo = mel(c.lower_edge_hertz), mhi = mel(c.upper_edge_hertz);
+  for (int i = 0; i < M + 2; ++i) edges[i] = mlo + (mhi - mlo) * i / (M + 1);
+  std::vector<int> start(M, 0), len(M, 0), off(M, 0);
+  std::vector<float> wts;
+  const double nyq = c.sample_rate / 2.0;
+  for (int m = 0; m < M; ++m) {
+    const double lo = edges[m], ce = edges[m + 1], up = edges[m + 2];
+    int first = -1, last = -1;
+    std::vector<float> row;
+    for (int k = 1; k < bins; ++k) {
+      const double fm = mel(nyq * k / (bins - 1));
+      const double w = std::max(0.0, std::min((fm - lo) / (ce - lo), (up - fm) / (up - ce)));
+      if (w > 0.0) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    off[m] = (int)wts.size();
+    if (first >= 0) {
+      start[m] = first;
+      len[m] = last - first + 1;
+      for (int k = first; k <= last; ++k) {
+        const double fm = mel(nyq * k / (bins - 1));
+        wts.push_back((float)std::max(0.0, std::min((fm - lo) / (ce - lo), (up - fm) / (up - ce))));
+      }
+    }
+  }
+  // mfccs_from_log_mel_spectrograms: DCT-II (unnormalised, x2) * rsqrt(2 M), first F coefficients.
+  const int F = h->features;
+  std::vector<float> dct((size_t)M * F);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < F; ++k)
+      dct[(size_t)m * F + k] = (float)(2.0 * cos(M_PI * k * (2.0 * m + 1.0) / (2.0 * M)) / sqrt(2.0 * M));
+  TCR_TRY(dev_upload(h, &h->d_window, win));
+  TCR_TRY(dev_upload(h, &h->d_tw, tw));
+  TCR_TRY(dev_upload(h, &h->d_tw2, tw2));
+  TCR_TRY(dev_upload(h, &h->d_mel_start, start));
+  TCR_TRY(dev_upload(h, &h->d_mel_len, len));
+  TCR_TRY(dev_upload(h, &h->d_mel_off, off));
+  TCR_TRY(dev_upload(h, &h->d_mel_w, wts));
+  TCR_TRY(dev_upload(h, &h->d_dct, dct));
+  return TCR_OK;
+}
+
+static MfccArgs mfcc_args(const tcr_handle* h, const float* wav, float* feat) {
+  MfccArgs a;
+  a.wav = wav;
+  a.feat = feat;
+  a.clip = h->cfg.clip_samples;
+  a.window = h->cfg.window_size_samples;
+  a.stride = h->cfg.window_stride_samples;
+  a.frames = h->frames;
+  a.features = h->features;
+  a.mel_bins = h->cfg.num_mel_bins;
+  a.fpb = h->fpb;
+  a.magnitude = h->cfg.feature_kind == TCR_FEATURE_LOG_MEL;
+  a.use_dct = h->cfg.feature_kind == TCR_FEATURE_MFCC;
+  a.window_tab = h->d_window;
+  a.tw = h->d_tw;
+  a.tw2 = h->d_tw2;
+  a.mel_start = h->d_mel_start;
+  a.mel_len = h->d_mel_len;
+  a.mel_off = h->d_mel_off;
+  a.mel_w = h->d_mel_w;
+  a.dct = h->d_dct;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer plan (audio_nets/tc_resnet.py:6-70) and variable table (tf.trainable_variables() order)
+// ------------------------------------------------------------------------------------------------
+static void same_padding(int len, int k, int s, int* out, int* left) {
+  *out = (len + s - 1) / s;
+  int total = std::max((*out - 1) * s + k - len, 0);
+  *left = total / 2;
+}
+
+static void add_desc(tcr_handle* h, const std::string& name, int kind, int rank, const int* shape, int64_t off, int64_t numel) {
+  tcr_param_desc d;
+  memset(&d, 0, sizeof(d));
+  snprintf(d.name, sizeof(d.name), "%s", name.c_str());
+  d.kind = kind;
+  d.rank = rank;
+  for (int i = 0; i < rank; ++i) d.shape[i] = shape[i];
+  d.offset = off;
+  d.numel = numel;
+  h->table.push_back(d);
+}
+
+static int build_plan(tcr_handle* h) {
+  const tcr_config& c = h->cfg;
+  std::vector<int> plan;
+  if (c.model == TCR_MODEL_TCRESNET8) {
+    h->scope = "TCResNet8";
+    plan = {16, 24, 32, 48};
+  } else if (c.model == TCR_MODEL_TCRESNET14) {
+    h->scope = "TCResNet14";
+    plan = {16, 24, 24, 32, 32, 48, 48};
+  } else {
+    return fail(TCR_ERR_INVALID, "unknown model %d (expected 8 or 14)", c.model);
+  }
+  for (int& x : plan) {
+    x = (int)((double)x * (double)c.width_multiplier);   // int(x * width_multiplier), tc_resnet.py:60
+    if (x <= 0 || x % 4 != 0)
+      return fail(TCR_ERR_UNSUPPORTED, "channel count %d (width_multiplier %g) is not a positive multiple of 4", x,
+                  c.width_multiplier);
+  }
+  if (h->features % 4 != 0) return fail(TCR_ERR_UNSUPPORTED, "feature count %d is not a multiple of 4", h->features);
+  auto mk = [&](const std::string& name, int cin, int cout, int k, int s, int t, int relu) {
+    ConvPlan cv;
+    cv.name = name;
+    cv.cin = cin;
+    cv.cout = cout;
+    cv.k = k;
+    cv.stride = s;
+    cv.t_in = t;
+    cv.relu = relu;
+    same_padding(t, k, s, &cv.t_out, &cv.pad_left);
+    h->convs.push_back(cv);
+    return (int)h->convs.size() - 1;
+  };
+  mk("conv0", h->features, plan[0], 3, 1, h->frames, 1);
+  int ch = plan[0], t = h->convs[0].t_out;
+  for (size_t i = 1; i < plan.size(); ++i) {
+    const int n = plan[i];
+    const std::string b = "block" + std::to_string(i - 1);
+    BlockPlan bp;
+    int stride = 1;
+    if (n != ch) {
+      stride = 2;
+      bp.down = mk(b + "/down", ch, n, 1, 2, t, 1);
+    }
+    bp.a = mk(b + "/conv" + std::to_string(i - 1) + "_0", ch, n, 9, stride, t, 1);
+    bp.b = mk(b + "/conv" + std::to_string(i - 1) + "_1", n, n, 9, 1, h->convs[bp.a].t_out, 0);
+    ch = n;
+    t = h->convs[bp.b].t_out;
+    bp.c = ch;
+    bp.t = t;
+    h->blocks.push_back(bp);
+  }
+  if ((int)h->convs.size() > kMaxConvs) return fail(TCR_ERR_UNSUPPORTED, "too many conv layers");
+  h->c_last = ch;
+  h->t_last = t;
+  // variable table: per conv weights, beta, gamma (creation order of slim.conv2d + slim.batch_norm), then fc, fc2
+  int64_t off = 0, moff = 0;
+  for (auto& cv : h->convs) {
+    const std::string p = h->scope + "/" + cv.name;
+    int shp[4] = {cv.k, 1, cv.cin, cv.cout};
+    cv.w_off = off;
+    add_desc(h, p + "/weights", TCR_KIND_WEIGHT, 4, shp, off, cv.wnumel());
+    off += cv.wnumel();
+    int s1[1] = {cv.cout};
+    cv.beta_off = off;
+    add_desc(h, p + "/BatchNorm/beta", TCR_KIND_BETA, 1, s1, off, cv.cout);
+    off += cv.cout;
+    cv.gamma_off = off;
+    add_desc(h, p + "/BatchNorm/gamma", TCR_KIND_GAMMA, 1, s1, off, cv.cout);
+    off += cv.cout;
+  }
+  {
+    int shp[4] = {1, 1, h->c_last, c.num_classes};
+    h->fc_off = off;
+    add_desc(h, h->scope + "/fc/weights", TCR_KIND_WEIGHT, 4, shp, off, (int64_t)h->c_last * c.num_classes);
+    off += (int64_t)h->c_last * c.num_classes;
+    int shp2[4] = {1, 1, h->c_last, 2};
+    h->fc2_off = off;
+    add_desc(h, h->scope + "/fc2/weights", TCR_KIND_WEIGHT, 4, shp2, off, (int64_t)h->c_last * 2);
+    off += (int64_t)h->c_last * 2;
+  }
+  h->n_train = off;
+  for (auto& cv : h->convs) {
+    const std::string p = h->scope + "/" + cv.name + "/BatchNorm/";
+    int s1[1] = {cv.cout};
+    cv.mm_off = moff;
+    add_desc(h, p + "moving_mean", TCR_KIND_MOVING_MEAN, 1, s1, moff, cv.cout);
+    moff += cv.cout;
+    cv.mv_off = moff;
+    add_desc(h, p + "moving_variance", TCR_KIND_MOVING_VAR, 1, s1, moff, cv.cout);
+    moff += cv.cout;
+  }
+  h->n_moving = moff;
+  return TCR_OK;
+}
+
+extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
+  if (!cfg || !out) return fail(TCR_ERR_INVALID, "cfg/out is NULL");
+  *out = nullptr;
+  if (cfg->max_batch <= 0) return fail(TCR_ERR_INVALID, "max_batch must be positive");
+  if (cfg->window_size_samples <= 0 || cfg->window_stride_samples <= 0 || cfg->clip_samples < cfg->window_size_samples)
+    return fail(TCR_ERR_INVALID, "bad window/stride/clip (%d/%d/%d)", cfg->window_size_samples,
+                cfg->window_stride_samples, cfg->clip_samples);
+  if (cfg->window_size_samples % 4 || cfg->window_stride_samples % 4 || cfg->clip_samples % 4)
+    return fail(TCR_ERR_UNSUPPORTED, "window, stride and clip lengths must be multiples of 4 samples (16-byte TMA rows)");
+  if (cfg->num_mel_bins <= 0 || cfg->num_mel_bins > 128 || cfg->num_mfccs <= 0 || cfg->num_mfccs > cfg->num_mel_bins)
+    return fail(TCR_ERR_INVALID, "bad num_mel_bins/num_mfccs (%d/%d)", cfg->num_mel_bins, cfg->num_mfccs);
+  if (cfg->feature_kind != TCR_FEATURE_MFCC && cfg->feature_kind != TCR_FEATURE_LOG_MEL)
+    return fail(TCR_ERR_INVALID, "bad feature_kind %d", cfg->feature_kind);
+  if (!(cfg->dropout_keep_prob > 0.f && cfg->dropout_keep_prob <= 1.f))
+    return fail(TCR_ERR_INVALID, "dropout_keep_prob must be in (0,1]");
+  if (cfg->num_classes <= 0 || cfg->num_classes > kMaxClasses)
+    return fail(TCR_ERR_UNSUPPORTED, "num_classes must be in [1,%d]", kMaxClasses);
+  tcr_handle* h = new tcr_handle();
+  h->cfg = *cfg;
+  auto bail = [&](int rc) {
+    tcr_destroy(h);
+    return rc;
+  };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(TCR_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device));
+  h->frames = 1 + (cfg->clip_samples - cfg->window_size_samples) / cfg->window_stride_samples;
+  h->features = cfg->feature_kind == TCR_FEATURE_MFCC ? cfg->num_mfccs : cfg->num_mel_bins;
+  h->fft = next_pow2(cfg->window_size_samples);
+  if (h->fft < 128 || h->fft > 2048) return bail(fail(TCR_ERR_UNSUPPORTED, "fft length %d outside [128, 2048]", h->fft));
+  // frames per CTA: a divisor-ish of T in [4, 8] so that chunks are balanced (49 -> 7, 98 -> 7)
+  h->fpb = 8;
+  {
+    int best = 8, best_waste = 1 << 30;
+    for (int f = 8; f >= 4; --f) {
+      const int chunks = (h->frames + f - 1) / f;
+      const int waste = chunks * f - h->frames;
+      if (waste < best_waste) {
+        best_waste = waste;
+        best = f;
+      }
+    }
+    h->fpb = std::min(best, h->frames);
+  }
+  int rc = build_frontend_tables(h);
+  if (rc) return bail(rc);
+  rc = build_plan(h);
+  if (rc) return bail(rc);
+  rc = net_alloc_workspace(h);
+  if (rc) return bail(fail(rc, "workspace allocation failed: %s", g_err));
+  *out = h;
+  return TCR_OK;
+}
+
+extern "C" int tcr_destroy(tcr_handle* h) {
+  if (!h) return TCR_OK;
+  comm_destroy(h);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_hyper) cudaFreeHost(h->h_hyper);
+  delete h;
+  return TCR_OK;
+}
+
+extern "C" int tcr_get_info(const tcr_handle* h, tcr_info* out) {
+  if (!h || !out) return fail(TCR_ERR_INVALID, "NULL argument");
+  memset(out, 0, sizeof(*out));
+  out->abi_version = TCR_ABI_VERSION;
+  out->frames = h->frames;
+  out->features = h->features;
+  out->fft_length = h->fft;
+  out->num_conv_layers = (int)h->convs.size();
+  out->num_blocks = (int)h->blocks.size();
+  out->last_channels = h->c_last;
+  out->last_frames = h->t_last;
+  out->num_trainable = h->n_train;
+  out->num_moving = h->n_moving;
+  int64_t fl = 0;
+  for (const auto& cv : h->convs) fl += 2ll * cv.t_out * cv.k * cv.cin * cv.cout;
+  fl += 2ll * h->c_last * h->cfg.num_classes + 2ll * h->c_last * 2;
+  out->forward_flops_per_utt = fl;
+  out->workspace_bytes = h->workspace_bytes;
+  return TCR_OK;
+}
+
+extern "C" int tcr_param_table(const tcr_handle* h, const tcr_param_desc** descs, int32_t* count) {
+  if (!h || !descs || !count) return fail(TCR_ERR_INVALID, "NULL argument");
+  *descs = h->table.data();
+  *count = (int32_t)h->table.size();
+  return TCR_OK;
+}
+
+extern "C" int tcr_init_variables(tcr_handle* h, float* params, float* slots, float* moving, uint64_t seed, tcr_stream stream) {
+  if (!h) return fail(TCR_ERR_INVALID, "NULL handle");
+  std::mt19937_64 rng(seed);
+  std::vector<float> p((size_t)h->n_train, 0.f), mv((size_t)h->n_moving, 0.f);
+  for (const auto& d : h->table) {
+    if (d.kind == TCR_KIND_WEIGHT) {
+      const double fan_in = (double)d.shape[0] * d.shape[1] * d.shape[2], fan_out = (double)d.shape[0] * d.shape[1] * d.shape[3];
+      const double lim = sqrt(6.0 / (fan_in + fan_out));   // slim xavier_initializer(uniform=True)
+      std::uniform_real_distribution<double> u(-lim, lim);
+      for (int64_t i = 0; i < d.numel; ++i) p[(size_t)(d.offset + i)] = (float)u(rng);
+    } else if (d.kind == TCR_KIND_GAMMA) {
+      for (int64_t i = 0; i < d.numel; ++i) p[(size_t)(d.offset + i)] = 1.f;
+    } else if (d.kind == TCR_KIND_MOVING_VAR) {
+      for (int64_t i = 0; i < d.numel; ++i) mv[(size_t)(d.offset + i)] = 1.f;
+    }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (params) TCR_CUDA(cudaMemcpyAsync(params, p.data(), p.size() * 4, cudaMemcpyHostToDevice, s));
+  if (moving) TCR_CUDA(cudaMemcpyAsync(moving, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice, s));
+  if (slots) TCR_CUDA(cudaMemsetAsync(slots, 0, (size_t)h->n_train * 4, s));
+  TCR_CUDA(cudaStreamSynchronize(s));   // host staging buffers go out of scope
+  return TCR_OK;
+}
+
+static int check_n(const tcr_handle* h, int n) {
+  if (n <= 0) return fail(TCR_ERR_INVALID, "n must be positive (got %d)", n);
+  if (n > h->cfg.max_batch) return fail(TCR_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->cfg.max_batch);
+  return TCR_OK;
+}
+
+extern "C" int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream) {
+  if (!h || !wav || !features) return fail(TCR_ERR_INVALID, "NULL argument");
+  TCR_TRY(check_n(h, n));
+  if (((uintptr_t)wav & 15) != 0) return fail(TCR_ERR_INVALID, "wav must be 16-byte aligned (TMA bulk copy)");
+  MfccArgs a = mfcc_args(h, wav, features);
+  if (mfcc_launch(a, n, h->fft, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc launch configuration failed");
+  TCR_CUDA(cudaGetLastError());
+  return TCR_OK;
+}
+
+extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, const float* params,
+                           const float* moving, int32_t n, int32_t is_training, uint64_t dropout_seed,
+                           const float* dropout_mask, const float* onehot, float weight_decay, float* logits,
+                           float* probs, float* losses, tcr_stream stream) {
+  if (!h || !input || !params) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (!is_training && !moving) return fail(TCR_ERR_INVALID, "eval-mode forward needs the moving statistics");
+  TCR_TRY(check_n(h, n));
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* feat = input;
+  if (!input_is_features) {
+    TCR_TRY(tcr_mfcc_forward(h, input, h->d_feat, n, stream));
+    feat = h->d_feat;
+  }
+  int rc = net_forward(h, feat, params, moving, n, is_training != 0, dropout_seed, dropout_mask, onehot, weight_decay,
+                       logits, probs, losses, /*backward=*/false, s);
+  if (rc) return fail(rc, "forward launch failed: %s", g_err);
+  TCR_CUDA(cudaGetLastError());
+  h->last_n = n;
+  return TCR_OK;
+}
+
+extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream stream) {
+  if (!h || !a || !a->input || !a->onehot || !a->params) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (a->apply_update && (!a->slots || !a->moving)) return fail(TCR_ERR_INVALID, "apply_update needs slots and moving");
+  TCR_TRY(check_n(h, a->n));
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* feat = a->input;
+  if (!a->input_is_features) {
+    TCR_TRY(tcr_mfcc_forward(h, a->input, h->d_feat, a->n, stream));
+    feat = h->d_feat;
+  }
+  int rc = net_forward(h, feat, a->params, nullptr, a->n, true, a->dropout_seed, a->dropout_mask, a->onehot,
+                       a->weight_decay, a->logits, a->probs, nullptr, /*backward=*/true, s);
+  if (rc) return fail(rc, "forward launch failed: %s", g_err);
+  rc = net_backward(h, feat, a->params, a->n, s);
+  if (rc) return fail(rc, "backward launch failed: %s", g_err);
+  rc = net_update(h, a, s);
+  if (rc) return fail(rc, "update launch failed: %s", g_err);
+  TCR_CUDA(cudaGetLastError());
+  h->last_n = a->n;
+  return TCR_OK;
+}
+
+extern "C" int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr, int64_t* numel) {
+  if (!h || !name || !ptr || !numel) return fail(TCR_ERR_INVALID, "NULL argument");
+  const int64_t n = h->last_n > 0 ? h->last_n : h->cfg.max_batch;
+  const std::string s(name);
+  auto ret = [&](float* p, int64_t k) {
+    *ptr = p;
+    *numel = k;
+    return TCR_OK;
+  };
+  if (s == "features") return ret(h->d_feat, n * h->frames * h->features);
+  if (s == "grads") return ret(h->d_grads, h->n_train);
+  if (s == "logits") return ret(h->d_logits, n * h->cfg.num_classes);
+  if (s == "probs") return ret(h->d_probs, n * h->cfg.num_classes);
+  const size_t colon = s.find(':');
+  if (colon != std::string::npos) {
+    const std::string kind = s.substr(0, colon), layer = s.substr(colon + 1);
+    for (size_t i = 0; i < h->blocks.size(); ++i) {
+      const std::string b = "block" + std::to_string(i);
+      if (layer == b) {
+        if (kind == "out") return ret(h->blocks[i].out, n * h->blocks[i].t * h->blocks[i].c);
+        if (kind == "g") return ret(h->blocks[i].gblk, n * h->blocks[i].t * h->blocks[i].c);
+      }
+    }
+    for (auto& cv : h->convs) {
+      if (cv.name != layer) continue;
+      if (kind == "y") return ret(cv.y, n * cv.t_out * cv.cout);
+      if (kind == "g" && cv.g) return ret(cv.g, n * cv.t_out * cv.cout);
+      if (kind == "bnf") return ret(cv.bnf, 4 * cv.cout);
+      if (kind == "var") return ret(cv.var, cv.cout);
+      if (kind == "bsum") return ret(cv.bsum, 2 * cv.cout);
+    }
+  }
+  return fail(TCR_ERR_INVALID, "unknown workspace tensor '%s'", name);
+}
+
+extern "C" int tcr_comm_unique_id(void* id128) {
+  int rc = comm_unique_id(id128);
+  return rc ? fail(rc, "ncclGetUniqueId unavailable: %s", comm_error()) : TCR_OK;
+}
+extern "C" int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int32_t world_size) {
+  if (!h || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(TCR_ERR_INVALID, "bad comm arguments");
+  int rc = comm_init(h, id128, rank, world_size);
+  return rc ? fail(rc, "ncclCommInitRank failed: %s", comm_error()) : TCR_OK;
+}
+extern "C" int tcr_comm_destroy(tcr_handle* h) {
+  if (!h) return TCR_OK;
+  comm_destroy(h);
+  return TCR_OK;
+}
+
+extern "C" int tcr_measure_fp32_peak(tcr_handle* h, double* tflops, tcr_stream stream) {
+  if (!h || !tflops) return fail(TCR_ERR_INVALID, "NULL argument");
+  int rc = measure_fp32_peak(h, tflops, (cudaStream_t)stream);
+  return rc ? fail(rc, "fp32 peak measurement failed") : TCR_OK;
+}
+
+namespace tcr {
+void set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+}  // namespace tcr

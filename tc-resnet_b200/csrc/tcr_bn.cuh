@@ -1,0 +1,148 @@
+// tcr_bn.cuh — BatchNorm table helpers shared by forward and backward kernels.
+// bnf layout: [4][C] = mean, rstd, scale (= gamma * rstd), beta.
+#pragma once
+#include "tcr_device.cuh"
+#include "tcr_internal.h"
+
+namespace tcr {
+
+__device__ __forceinline__ float4 relu4(float4 v) {
+  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// z = (y - mean) * scale + beta
+__device__ __forceinline__ float4 bn_apply4(float4 y, const float* __restrict__ bnf, int C, int c) {
+  const float4 mean = ldg4(bnf + c), scale = ldg4(bnf + 2 * C + c), beta = ldg4(bnf + 3 * C + c);
+  return make_float4(fmaf(y.x - mean.x, scale.x, beta.x), fmaf(y.y - mean.y, scale.y, beta.y),
+                     fmaf(y.z - mean.z, scale.z, beta.z), fmaf(y.w - mean.w, scale.w, beta.w));
+}
+__device__ __forceinline__ float bn_apply1(float y, const float* __restrict__ bnf, int C, int c) {
+  return fmaf(y - __ldg(bnf + c), __ldg(bnf + 2 * C + c), __ldg(bnf + 3 * C + c));
+}
+// xhat = (y - mean) * rstd
+__device__ __forceinline__ float4 bn_xhat4(float4 y, const float* __restrict__ bnf, int C, int c) {
+  const float4 mean = ldg4(bnf + c), rstd = ldg4(bnf + C + c);
+  return make_float4((y.x - mean.x) * rstd.x, (y.y - mean.y) * rstd.y, (y.z - mean.z) * rstd.z, (y.w - mean.w) * rstd.w);
+}
+
+// Activation source: raw tensor or relu(bn(y)).
+__device__ __forceinline__ float4 act_load4(const ActSrc& s, size_t ofs, int C, int c) {
+  float4 v = ld4(s.data + ofs);
+  if (s.kind == 1) v = relu4(bn_apply4(v, s.bnf, C, c));
+  return v;
+}
+
+// dy = scale * (dz - s1/M - xhat * s2/M); dz optionally masked by the layer's own ReLU (bn(y) > 0).
+__device__ __forceinline__ float4 dy_load4(const DySrc& d, size_t ofs, int C, int c) {
+  float4 dz = ld4(d.dz + ofs);
+  const float4 y = ld4(d.y + ofs);
+  const float4 mean = ldg4(d.bnf + c), rstd = ldg4(d.bnf + C + c), scale = ldg4(d.bnf + 2 * C + c);
+  if (d.mask_relu) {
+    const float4 beta = ldg4(d.bnf + 3 * C + c);
+    if (fmaf(y.x - mean.x, scale.x, beta.x) <= 0.f) dz.x = 0.f;
+    if (fmaf(y.y - mean.y, scale.y, beta.y) <= 0.f) dz.y = 0.f;
+    if (fmaf(y.z - mean.z, scale.z, beta.z) <= 0.f) dz.z = 0.f;
+    if (fmaf(y.w - mean.w, scale.w, beta.w) <= 0.f) dz.w = 0.f;
+  }
+  const float4 s1 = ldg4(d.bsum + c), s2 = ldg4(d.bsum + C + c);
+  const float im = d.inv_m;
+  float4 r;
+  r.x = scale.x * (dz.x - s1.x * im - (y.x - mean.x) * rstd.x * (s2.x * im));
+  r.y = scale.y * (dz.y - s1.y * im - (y.y - mean.y) * rstd.y * (s2.y * im));
+  r.z = scale.z * (dz.z - s1.z * im - (y.z - mean.z) * rstd.z * (s2.z * im));
+  r.w = scale.w * (dz.w - s1.w * im - (y.w - mean.w) * rstd.w * (s2.w * im));
+  return r;
+}
+
+// "Last CTA finalises": returns true in exactly one CTA of the grid, after every other CTA's global
+// writes are visible.  The counter is reset for the next launch.
+__device__ __forceinline__ bool last_block_done(unsigned* counter, unsigned nblocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    s_last = (prev == nblocks - 1);
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// Chan et al. combination of per-group (mean, M2) partials into the BN table (fp64, fixed order).
+__device__ __forceinline__ void bn_finalize(const BnFinalize& f, int groups, int U, int n, int t_out, float eps) {
+  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
+    double sum = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      const double cnt = (double)(imin(U, n - g * U) * t_out);
+      sum += cnt * (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2);
+    }
+    const double m_total = (double)n * t_out;
+    const double mean = sum / m_total;
+    double m2 = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      const double cnt = (double)(imin(U, n - g * U) * t_out);
+      const double d = (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2) - mean;
+      m2 += (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) + cnt * d * d;
+    }
+    const double var = m2 / m_total;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    f.bnf[c] = (float)mean;
+    f.bnf[f.c + c] = (float)rstd;
+    f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
+    f.bnf[3 * f.c + c] = f.beta[c];
+    f.var[c] = (float)var;
+  }
+}
+
+__device__ __forceinline__ void bwdsum_finalize(const BwdSumFinalize& f, int groups) {
+  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
+    const int q = i / f.c, c = i - q * f.c;
+    double s = 0.0;
+    for (int g = 0; g < groups; ++g) s += (double)__ldcg(f.bpart + ((size_t)g * f.c + c) * 2 + q);
+    f.bsum[q * f.c + c] = (float)s;
+  }
+}
+
+// Per-channel (mean, M2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}].
+// Requires C <= blockDim.x.  red: blockDim.x floats of scratch, smean: C floats.  Two passes over the
+// tile (mean, then squared deviations) so the partial is exact enough for the Chan combination.
+__device__ __forceinline__ void tile_stats(const float* tile, int rows, int C, float* red, float* smean, float* part_out) {
+  const int tid = threadIdx.x;
+  const int ns = imax(1, (int)blockDim.x / C);
+  const int seg = tid / C, c = tid - seg * C;
+  const bool act = seg < ns;
+  float s = 0.f;
+  if (act) {
+    for (int r = seg; r < rows; r += ns) s += tile[r * C + c];
+    red[seg * C + c] = s;
+  }
+  __syncthreads();
+  if (tid < C) {
+    float tot = 0.f;
+    for (int q = 0; q < ns; ++q) tot += red[q * C + tid];
+    smean[tid] = tot / (float)rows;
+  }
+  __syncthreads();
+  if (act) {
+    const float mu = smean[c];
+    float m2 = 0.f;
+    for (int r = seg; r < rows; r += ns) {
+      const float d = tile[r * C + c] - mu;
+      m2 = fmaf(d, d, m2);
+    }
+    red[seg * C + c] = m2;
+  }
+  __syncthreads();
+  if (tid < C) {
+    float tot = 0.f;
+    for (int q = 0; q < ns; ++q) tot += red[q * C + tid];
+    part_out[(size_t)tid * 2] = smean[tid];
+    part_out[(size_t)tid * 2 + 1] = tot;
+  }
+  __syncthreads();
+}
+
+}  // namespace tcr

@@ -1,0 +1,246 @@
+// tcr_mfcc.cu — fused MFCC / log-mel front-end for sm_100a.
+//
+// Replaces the TF graph built by datasets/preprocessors.py:64-96 (_log_mel_spectrogram:
+// stft -> power|magnitude -> mel matmul -> log(x + 1e-6)) and :183-194 (MFCC: DCT-II, first
+// num_mfccs coefficients) with ONE kernel:
+//   * grid = (frame chunks, utterances); a CTA owns FPB consecutive frames of one clip and stages the
+//     (FPB-1)*stride + window samples it needs with a single TMA bulk copy (cp.async.bulk + mbarrier);
+//   * one warp per frame: periodic-Hann window, real FFT of length fft = 2*NF2 done as a complex
+//     Stockham FFT of length NF2 in shared memory (radix 8/4/2 passes, fp32, table twiddles),
+//     real-FFT post-processing, power (or magnitude);
+//   * banded mel accumulation (<= 2 non-zeros per FFT bin: 942 weights instead of a 513x64 matmul),
+//     log(x + 1e-6), 64xF DCT from an L1-resident table, coalesced [N,T,F] store.
+// Algorithmic traffic: 4*clip bytes in + 4*T*F bytes out per utterance (64,000 + 7,840 B at T=49).
+#include "tcr_device.cuh"
+#include "tcr_mfcc.h"
+
+namespace tcr {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+template <int R> __device__ __forceinline__ void dft_small(float2* v);
+template <> __device__ __forceinline__ void dft_small<2>(float2* v) {
+  float2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <> __device__ __forceinline__ void dft_small<4>(float2* v) {
+  float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+  float2 a2 = cadd(v[1], v[3]), a3 = mul_neg_i(csub(v[1], v[3]));
+  v[0] = cadd(a0, a2);
+  v[2] = csub(a0, a2);
+  v[1] = cadd(a1, a3);
+  v[3] = csub(a1, a3);
+}
+template <> __device__ __forceinline__ void dft_small<8>(float2* v) {
+  float2 e[4] = {v[0], v[2], v[4], v[6]};
+  float2 o[4] = {v[1], v[3], v[5], v[7]};
+  dft_small<4>(e);
+  dft_small<4>(o);
+  const float h = 0.70710678118654752440f;
+  o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));     // * (1 - i)/sqrt2
+  o[2] = mul_neg_i(o[2]);                                               // * (-i)
+  o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));    // * (-1 - i)/sqrt2
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = cadd(e[k], o[k]);
+    v[k + 4] = csub(e[k], o[k]);
+  }
+}
+
+// Skewed index: one padding slot per 16 complex values keeps the strided Stockham stores 2-way
+// (the minimum for 64-bit accesses) instead of 16-way bank conflicted.
+__device__ __forceinline__ int zi(int i) { return i + (i >> 4); }
+
+// One Stockham pass of radix R over the warp-private buffer z (N complex values, skewed).
+// MAXQ = ceil(N / (32 R)) butterflies per lane, staged in registers so the pass is in place.
+template <int R, int MAXQ>
+__device__ __forceinline__ void fft_pass(float2* z, int N, int Ns, const float2* __restrict__ tw, int lane) {
+  const int nb = N / R;
+  const int tstep = N / (Ns * R);
+  float2 v[MAXQ][R];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int j = lane + 32 * q;
+    if (j < nb) {
+      const int k = j & (Ns - 1);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[q][r] = z[zi(j + r * nb)];
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[q][r] = cmul(v[q][r], tw[k * r * tstep]);
+      dft_small<R>(v[q]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int j = lane + 32 * q;
+    if (j < nb) {
+      const int k = j & (Ns - 1);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) z[zi(j0 + r * Ns)] = v[q][r];
+    }
+  }
+  __syncwarp();
+}
+
+template <int NF2>
+__device__ __forceinline__ void fft_warp(float2* z, const float2* __restrict__ tw, int lane) {
+  if (NF2 == 1024) {
+    fft_pass<8, 4>(z, 1024, 1, tw, lane);
+    fft_pass<8, 4>(z, 1024, 8, tw, lane);
+    fft_pass<8, 4>(z, 1024, 64, tw, lane);
+    fft_pass<2, 16>(z, 1024, 512, tw, lane);
+  } else if (NF2 == 512) {
+    fft_pass<8, 2>(z, 512, 1, tw, lane);
+    fft_pass<8, 2>(z, 512, 8, tw, lane);
+    fft_pass<8, 2>(z, 512, 64, tw, lane);
+  } else if (NF2 == 256) {
+    fft_pass<8, 1>(z, 256, 1, tw, lane);
+    fft_pass<8, 1>(z, 256, 8, tw, lane);
+    fft_pass<4, 2>(z, 256, 64, tw, lane);
+  } else if (NF2 == 128) {
+    fft_pass<8, 1>(z, 128, 1, tw, lane);
+    fft_pass<4, 1>(z, 128, 8, tw, lane);
+    fft_pass<4, 1>(z, 128, 32, tw, lane);
+  } else {  // 64
+    fft_pass<8, 1>(z, 64, 1, tw, lane);
+    fft_pass<8, 1>(z, 64, 8, tw, lane);
+  }
+}
+
+// Dynamic shared memory layout (bytes):
+//   [0, 16)                         mbarrier
+//   wav   : span floats             (TMA destination, 16-byte aligned)
+//   tw    : NF2 float2              FFT twiddles exp(-2 pi i n / NF2)
+//   per warp: z   (NF2 + NF2/16) float2, pw (NF2 + 1 [+pad]) floats, lm (mel_bins) floats
+template <int NF2>
+__global__ void __launch_bounds__(512) mfcc_kernel(MfccArgs a) {
+  TCR_DYNAMIC_SMEM(smem);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int utt = blockIdx.y;
+  const int f0 = blockIdx.x * a.fpb;
+  const int nf = min(a.fpb, a.frames - f0);
+
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* s_wav = reinterpret_cast<float*>(smem + 16);
+  const int span_max = (a.fpb - 1) * a.stride + a.window;
+  float2* s_tw = reinterpret_cast<float2*>(s_wav + span_max);
+  const int z_elems = NF2 + (NF2 >> 4);
+  const int pw_elems = ((NF2 + 1 + 3) / 4) * 4;
+  const int per_warp_floats = 2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3);
+  float* s_warp = reinterpret_cast<float*>(s_tw + NF2) + (size_t)warp * per_warp_floats;
+  float2* z = reinterpret_cast<float2*>(s_warp);
+  float* pw = s_warp + 2 * z_elems;
+  float* lm = pw + pw_elems;
+
+  const int span = (nf - 1) * a.stride + a.window;   // floats actually needed (multiple of 4)
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)span * 4u);
+    tma_load_1d(s_wav, a.wav + (size_t)utt * a.clip + (size_t)f0 * a.stride, (uint32_t)span * 4u, bar);
+  }
+  for (int i = threadIdx.x; i < NF2; i += blockDim.x) s_tw[i] = __ldg(&a.tw[i]);   // overlaps the bulk copy
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  const int half_w = a.window >> 1;
+  for (int f = warp; f < nf; f += nwarps) {
+    const float* x = s_wav + f * a.stride;
+    // windowed frame packed as complex: z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); zero padding to fft length
+    for (int n = lane; n < NF2; n += 32) {
+      float2 v = make_float2(0.f, 0.f);
+      if (n < half_w) {
+        const float2 xs = ld2(x + 2 * n);
+        const float2 ws = __ldg(reinterpret_cast<const float2*>(a.window_tab) + n);
+        v = make_float2(xs.x * ws.x, xs.y * ws.y);
+      }
+      z[zi(n)] = v;
+    }
+    __syncwarp();
+    fft_warp<NF2>(z, s_tw, lane);
+    // real-FFT post-processing: X[k] = E + (-i) e^{-2 pi i k / fft} O, E/O = (Z[k] +- conj(Z[NF2-k])) / 2
+    for (int k = lane; k <= NF2; k += 32) {
+      const float2 zk = z[zi(k & (NF2 - 1))];
+      const float2 zr = z[zi((NF2 - k) & (NF2 - 1))];
+      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
+      const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y + zr.y));
+      const float2 t = cmul(__ldg(&a.tw2[k]), o);
+      const float xr = e.x + t.y, xi = e.y - t.x;
+      const float p = xr * xr + xi * xi;
+      pw[k] = a.magnitude ? sqrtf(p) : p;
+    }
+    __syncwarp();
+    // banded mel + log
+    for (int m = lane; m < a.mel_bins; m += 32) {
+      const int start = __ldg(&a.mel_start[m]), len = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
+      float acc = 0.f;
+      for (int i = 0; i < len; ++i) acc = fmaf(pw[start + i], __ldg(&a.mel_w[off + i]), acc);
+      lm[m] = logf(acc + 1e-6f);
+    }
+    __syncwarp();
+    float* out = a.feat + ((size_t)utt * a.frames + (f0 + f)) * a.features;
+    if (a.use_dct) {
+      for (int c = lane; c < a.features; c += 32) {
+        float acc = 0.f;
+        for (int m = 0; m < a.mel_bins; ++m) acc = fmaf(lm[m], __ldg(&a.dct[m * a.features + c]), acc);
+        out[c] = acc;
+      }
+    } else {
+      for (int c = lane; c < a.features; c += 32) out[c] = lm[c];
+    }
+    __syncwarp();
+  }
+}
+
+size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps) {
+  const int span_max = (a.fpb - 1) * a.stride + a.window;
+  const int z_elems = nf2 + (nf2 >> 4);
+  const int pw_elems = ((nf2 + 1 + 3) / 4) * 4;
+  const size_t per_warp = (size_t)(2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3)) * 4;
+  return 16 + (size_t)span_max * 4 + (size_t)nf2 * 8 + per_warp * warps;
+}
+
+int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
+  const int nf2 = fft_length / 2;
+  const int warps = a.fpb;
+  dim3 grid((a.frames + a.fpb - 1) / a.fpb, n, 1);
+  dim3 block(32 * warps, 1, 1);
+  const size_t smem = mfcc_smem_bytes(a, nf2, warps);
+#ifndef TCR_EMU
+#define TCR_MFCC_CASE(NF2)                                                                                   \
+  case NF2: {                                                                                                \
+    auto k = mfcc_kernel<NF2>;                                                                               \
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+    TCR_LAUNCH(k, grid, block, smem, stream, a);                                                             \
+  } break;
+#else
+#define TCR_MFCC_CASE(NF2)                         \
+  case NF2: {                                      \
+    auto k = mfcc_kernel<NF2>;                     \
+    TCR_LAUNCH(k, grid, block, smem, stream, a);   \
+  } break;
+#endif
+  switch (nf2) {
+    TCR_MFCC_CASE(1024)
+    TCR_MFCC_CASE(512)
+    TCR_MFCC_CASE(256)
+    TCR_MFCC_CASE(128)
+    TCR_MFCC_CASE(64)
+    default:
+      return 2;
+  }
+#undef TCR_MFCC_CASE
+  return 0;
+}
+
+}  // namespace tcr

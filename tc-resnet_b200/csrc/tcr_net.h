@@ -1,0 +1,36 @@
+// tcr_net.h — host-side launch sequences implemented in tcr_net_fwd.cu / tcr_net_bwd.cu /
+// tcr_optim.cu / tcr_comm.cu.  All return 0 or a TCR_ERR_* code (message via tcr::set_error).
+#pragma once
+#include "tcr_plan.h"
+
+namespace tcr {
+
+void set_error(const char* msg);
+
+int net_alloc_workspace(tcr_handle* h);
+
+// Forward pass on features [n, T, F].  training: batch-statistics BN (+ dropout); otherwise the BN tables are
+// built from `moving`.  backward: the head additionally emits dlogits-derived tensors for net_backward.
+int net_forward(tcr_handle* h, const float* feat, const float* params, const float* moving, int n, bool training,
+                uint64_t seed, const float* mask, const float* onehot, float weight_decay, float* logits,
+                float* probs, float* losses, bool backward, cudaStream_t s);
+
+// Backward-data chain + all weight-gradient kernels; leaves per-layer partial sums in the workspace.
+int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s);
+
+// Gradient finalisation (+ weight decay), optional NCCL all-reduce, momentum update, BN moving averages, losses.
+int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s);
+
+int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int n, float* losses, cudaStream_t s);
+int head_groups(int n);
+
+int measure_fp32_peak(tcr_handle* h, double* tflops, cudaStream_t s);
+
+// NCCL through dlopen (tcr_comm.cu): no link-time dependency, the torch-bundled libnccl is reused when loaded.
+int comm_unique_id(void* id128);
+int comm_init(tcr_handle* h, const void* id128, int rank, int world);
+void comm_destroy(tcr_handle* h);
+int comm_allreduce_sum(tcr_handle* h, float* buf, int64_t count, cudaStream_t s);
+const char* comm_error();
+
+}  // namespace tcr

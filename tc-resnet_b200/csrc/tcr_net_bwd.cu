@@ -1,0 +1,484 @@
+// tcr_net_bwd.cu — TC-ResNet backward kernels for sm_100a (fp32 FMA pipe).
+//
+// Replaces the gradient graph slim.learning.create_train_op builds (helper/trainer.py:199-211):
+// Conv2DBackpropInput / Conv2DBackpropFilter / FusedBatchNormGrad / ReluGrad per layer.
+//   conv_bwd_data_kernel<K>   : dy = FusedBatchNormGrad(dz) is formed while staging the tile (two per-channel
+//                               sums s1 = sum dz, s2 = sum dz*xhat come finalised from the producer kernel);
+//                               dx = conv^T(dy, W) [+ the block's 1x1 shortcut conv^T] [+ identity gradient];
+//                               epilogue applies the consumer-side ReLU mask, writes the next dz and emits the
+//                               per-CTA partial (s1, s2) of the layer(s) below; the last CTA finalises them.
+//                               Stride-2 transposed convs are split by output-row parity so no FMA is spent on
+//                               the zeros of a dilated gradient.
+//   conv_bwd_weight_kernel<K> : dW[k,ci,co] = sum_rows x[row+k, ci] * dy[row, co]; each thread owns 2 ci x 4 co
+//                               x K taps in registers, CTAs split (co tile, row chunk); row-chunk partials are
+//                               reduced in a fixed order by the optimizer kernel (deterministic, no atomics).
+#include "tcr_bn.cuh"
+#include "tcr_net.h"
+
+namespace tcr {
+
+constexpr int TMB = 4;   // input rows per thread task (backward-data)
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float4 mask_pos4(float4 v, float4 z) {
+  return make_float4(z.x > 0.f ? v.x : 0.f, z.y > 0.f ? v.y : 0.f, z.z > 0.f ? v.z : 0.f, z.w > 0.f ? v.w : 0.f);
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
+// ------------------------------------------------------------------------------------------------
+// backward data
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int S = a.stride;
+  const int u0 = blockIdx.x * a.U;
+  const int Ue = imin(a.U, a.n - u0);
+  const int COS = chan_stride(a.cout);
+  const int PLd = (K - 1) / S;
+  const int PRd = imax(0, (a.t_in - 1 + a.pad_left) / S - (a.t_out - 1));
+  const int TPd = PLd + a.t_out + PRd;
+  const int COSD = a.has_down ? chan_stride(a.coutd) : 0;
+  const int Rin_max = a.U * a.t_in;
+  float* dys = smem;                                                 // [U][TPd][COS]
+  float* dysd = dys + (size_t)a.U * TPd * COS;                       // [U][t_out][COSD]
+  float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
+  float* red = dxs + (size_t)a.KS * Rin_max * a.cin;                 // [4][nseg][cin]
+
+  // ---- stage dy (BatchNorm backward applied on load) ----
+  {
+    const int c4n = a.cout >> 2, npad = PLd + PRd;
+    for (int idx = tid; idx < Ue * npad * c4n; idx += kThreads) {
+      const int c4 = idx % c4n, pr = (idx / c4n) % npad, u = idx / (c4n * npad);
+      const int row = pr < PLd ? pr : a.t_out + pr;
+      st4(dys + ((size_t)(u * TPd + row) * COS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    for (int idx = tid; idx < Ue * a.t_out * c4n; idx += kThreads) {
+      const int c4 = idx % c4n, t = (idx / c4n) % a.t_out, u = idx / (c4n * a.t_out);
+      const size_t gofs = ((size_t)(u0 + u) * a.t_out + t) * a.cout + 4 * c4;
+      st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * c4), dy_load4(a.dy, gofs, a.cout, 4 * c4));
+    }
+    if (a.has_down) {
+      const int d4n = a.coutd >> 2;
+      for (int idx = tid; idx < Ue * a.t_out * d4n; idx += kThreads) {
+        const int c4 = idx % d4n, t = (idx / d4n) % a.t_out, u = idx / (d4n * a.t_out);
+        const size_t gofs = ((size_t)(u0 + u) * a.t_out + t) * a.coutd + 4 * c4;
+        st4(dysd + ((size_t)(u * a.t_out + t) * COSD + 4 * c4), dy_load4(a.dyd, gofs, a.coutd, 4 * c4));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- transposed conv, one parity class of input rows at a time ----
+  // input row t belongs to class p = (t + pad_left) % S; it receives taps k = p + S m from dy row (t+pad_left-p)/S - m.
+  const int NCIG = a.cin >> 2;
+  int t0[2], np[2], nrt[2];
+  for (int p = 0; p < 2; ++p) {
+    t0[p] = ((p - a.pad_left) % S + S) % S;
+    np[p] = (p < S && t0[p] < a.t_in) ? (a.t_in - t0[p] + S - 1) / S : 0;
+    nrt[p] = (np[p] + TMB - 1) / TMB;
+  }
+  const int NRTU = nrt[0] + nrt[1];
+  const int NT0 = (K + S - 1) / S;
+  const int MPS = (NT0 + a.KS - 1) / a.KS;
+  const int ntasks = a.KS * Ue * NRTU * NCIG;
+  for (int task = tid; task < ntasks; task += kThreads) {
+    const int cig = task % NCIG;
+    int q = task / NCIG;
+    const int rtu = q % NRTU;
+    q /= NRTU;
+    const int u = q % Ue, ks = q / Ue;
+    const int p = rtu >= nrt[0] ? 1 : 0;
+    const int rt = rtu - p * nrt[0];
+    const float* dyr[TMB];
+    int tt[TMB];
+#pragma unroll
+    for (int i = 0; i < TMB; ++i) {
+      const int j = imin(rt * TMB + i, np[p] - 1);
+      tt[i] = t0[p] + S * j;
+      const int b = (tt[i] + a.pad_left - p) / S;
+      dyr[i] = dys + (size_t)(u * TPd + PLd + b) * COS;
+    }
+    float4 acc[TMB];
+#pragma unroll
+    for (int i = 0; i < TMB; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int NT = (K - p + S - 1) / S;
+    const int m_lo = ks * MPS, m_hi = imin(NT, m_lo + MPS);
+    for (int m = m_lo; m < m_hi; ++m) {
+      const float* wk = a.w + ((size_t)(p + S * m) * a.cin + 4 * cig) * a.cout;
+      for (int co = 0; co < a.cout; co += 4) {
+        const float4 w0 = ldg4(wk + co), w1 = ldg4(wk + a.cout + co), w2 = ldg4(wk + 2 * a.cout + co), w3 = ldg4(wk + 3 * a.cout + co);
+#pragma unroll
+        for (int i = 0; i < TMB; ++i) {
+          const float4 d = ld4(dyr[i] - m * COS + co);
+          acc[i].x += dot4(d, w0); acc[i].y += dot4(d, w1); acc[i].z += dot4(d, w2); acc[i].w += dot4(d, w3);
+        }
+      }
+    }
+    if (a.has_down && ks == 0 && (t0[p] & 1) == 0) {     // 1x1 stride-2 shortcut conv touches even input rows only
+      const float* wk = a.wd + (size_t)(4 * cig) * a.coutd;
+      for (int co = 0; co < a.coutd; co += 4) {
+        const float4 w0 = ldg4(wk + co), w1 = ldg4(wk + a.coutd + co), w2 = ldg4(wk + 2 * a.coutd + co), w3 = ldg4(wk + 3 * a.coutd + co);
+#pragma unroll
+        for (int i = 0; i < TMB; ++i) {
+          const float4 d = ld4(dysd + (size_t)(u * a.t_out + (tt[i] >> 1)) * COSD + co);
+          acc[i].x += dot4(d, w0); acc[i].y += dot4(d, w1); acc[i].z += dot4(d, w2); acc[i].w += dot4(d, w3);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TMB; ++i)
+      if (rt * TMB + i < np[p]) st4(dxs + ((size_t)ks * Rin_max + (size_t)u * a.t_in + tt[i]) * a.cin + 4 * cig, acc[i]);
+  }
+  __syncthreads();
+
+  // ---- epilogue: dz of the layer(s) below + partial BatchNorm-backward sums ----
+  const int Rin = Ue * a.t_in;
+  const int nseg = imax(1, kThreads / NCIG);
+  const int seg = tid / NCIG, cig = tid - seg * NCIG;
+  const size_t grow0 = (size_t)u0 * a.t_in;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, sd1 = s1, sd2 = s1;
+  if (seg < nseg) {
+    for (int r = seg; r < Rin; r += nseg) {
+      const size_t gofs = (grow0 + r) * a.cin + 4 * cig;
+      float4 v = ld4(dxs + (size_t)r * a.cin + 4 * cig);
+      for (int ks = 1; ks < a.KS; ++ks) v = add4(v, ld4(dxs + ((size_t)ks * Rin_max + r) * a.cin + 4 * cig));
+      if (a.gid) v = add4(v, ld4(a.gid + gofs));
+      const float4 yv = ld4(a.yp + gofs);
+      float4 g;
+      if (a.epi_kind == 1) g = mask_pos4(v, bn_apply4(yv, a.bnfp, a.cin, 4 * cig));
+      else g = mask_pos4(v, ld4(a.out_prev + gofs));
+      st4(a.gprev + gofs, g);
+      s1 = add4(s1, g);
+      s2 = add4(s2, mul4(g, bn_xhat4(yv, a.bnfp, a.cin, 4 * cig)));
+      if (a.epi_kind == 2 && a.ypd) {
+        const float4 yd = ld4(a.ypd + gofs);
+        const float4 gs = mask_pos4(g, bn_apply4(yd, a.bnfpd, a.cin, 4 * cig));
+        sd1 = add4(sd1, gs);
+        sd2 = add4(sd2, mul4(gs, bn_xhat4(yd, a.bnfpd, a.cin, 4 * cig)));
+      }
+    }
+    float* r0 = red + ((size_t)(0 * nseg + seg) * a.cin + 4 * cig);
+    st4(r0, s1);
+    st4(r0 + (size_t)nseg * a.cin, s2);
+    st4(r0 + (size_t)2 * nseg * a.cin, sd1);
+    st4(r0 + (size_t)3 * nseg * a.cin, sd2);
+  }
+  __syncthreads();
+  const int nq = (a.epi_kind == 2 && a.ypd) ? 4 : 2;
+  for (int i = tid; i < nq * a.cin; i += kThreads) {
+    const int qd = i / a.cin, c = i - qd * a.cin;
+    float s = 0.f;
+    for (int sg = 0; sg < nseg; ++sg) s += red[((size_t)qd * nseg + sg) * a.cin + c];
+    if (qd < 2) a.bpartp[((size_t)blockIdx.x * a.cin + c) * 2 + qd] = s;
+    else a.bpartpd[((size_t)blockIdx.x * a.cin + c) * 2 + (qd - 2)] = s;
+  }
+  if (last_block_done(a.counter, gridDim.x)) {
+    bwdsum_finalize(a.finp, gridDim.x);
+    if (nq == 4) bwdsum_finalize(a.finpd, gridDim.x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward weight
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(512) conv_bwd_weight_kernel(BwdWeightArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int cot0 = blockIdx.x * a.cot;
+  const int upc = (a.n + a.R - 1) / a.R;                       // utterances per row chunk
+  const int ubeg = blockIdx.y * upc, uend = imin(a.n, ubeg + upc);
+  const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
+  const int TP = a.pad_left + a.t_in + pad_right;
+  const int CI2 = a.cin >> 1;
+  const int NP = CI2 * (a.cot >> 2);
+  float* xs = smem;                                            // [UB][TP][cin]
+  float* dys = xs + (size_t)a.UB * TP * a.cin;                 // [UB * t_out][cot]
+  const int rg = tid / NP, pr = tid - rg * NP;
+  const int ci2 = pr % CI2, co4 = pr / CI2;
+  const bool worker = rg < a.RG;
+
+  float4 acc[K][2];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k][0] = acc[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int c4n = a.cin >> 2, d4n = a.cot >> 2, npad = a.pad_left + pad_right;
+  for (int ub0 = ubeg; ub0 < uend; ub0 += a.UB) {
+    const int Ue = imin(a.UB, uend - ub0);
+    for (int idx = tid; idx < Ue * npad * c4n; idx += blockDim.x) {
+      const int c4 = idx % c4n, prow = (idx / c4n) % npad, u = idx / (c4n * npad);
+      const int row = prow < a.pad_left ? prow : a.t_in + prow;
+      st4(xs + ((size_t)(u * TP + row) * a.cin + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    for (int idx = tid; idx < Ue * a.t_in * c4n; idx += blockDim.x) {
+      const int c4 = idx % c4n, t = (idx / c4n) % a.t_in, u = idx / (c4n * a.t_in);
+      const size_t gofs = ((size_t)(ub0 + u) * a.t_in + t) * a.cin + 4 * c4;
+      st4(xs + ((size_t)(u * TP + a.pad_left + t) * a.cin + 4 * c4), act_load4(a.x, gofs, a.cin, 4 * c4));
+    }
+    for (int idx = tid; idx < Ue * a.t_out * d4n; idx += blockDim.x) {
+      const int c4 = idx % d4n, r = idx / d4n;
+      const size_t gofs = ((size_t)ub0 * a.t_out + r) * a.cout + cot0 + 4 * c4;
+      st4(dys + (size_t)r * a.cot + 4 * c4, dy_load4(a.dy, gofs, a.cout, cot0 + 4 * c4));
+    }
+    __syncthreads();
+    if (worker) {
+      const int rows = Ue * a.t_out;
+      for (int r = rg; r < rows; r += a.RG) {
+        const int u = r / a.t_out, t = r - u * a.t_out;
+        const float* xrow = xs + (size_t)(u * TP + t * a.stride) * a.cin + 2 * ci2;
+        const float4 d = ld4(dys + (size_t)r * a.cot + 4 * co4);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float2 x = ld2(xrow + k * a.cin);
+          acc[k][0].x = fmaf(x.x, d.x, acc[k][0].x); acc[k][0].y = fmaf(x.x, d.y, acc[k][0].y);
+          acc[k][0].z = fmaf(x.x, d.z, acc[k][0].z); acc[k][0].w = fmaf(x.x, d.w, acc[k][0].w);
+          acc[k][1].x = fmaf(x.y, d.x, acc[k][1].x); acc[k][1].y = fmaf(x.y, d.y, acc[k][1].y);
+          acc[k][1].z = fmaf(x.y, d.z, acc[k][1].z); acc[k][1].w = fmaf(x.y, d.w, acc[k][1].w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- fixed-order reduction over the row groups of this CTA, then one partial per (row chunk, weight) ----
+  float* scratch = smem;                                       // [(RG-1)][NP][K][8], tiles are dead now
+  if (worker && rg > 0) {
+    float* sc = scratch + ((size_t)(rg - 1) * NP + pr) * K * 8;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      st4(sc + k * 8, acc[k][0]);
+      st4(sc + k * 8 + 4, acc[k][1]);
+    }
+  }
+  __syncthreads();
+  if (worker && rg == 0) {
+    for (int g = 1; g < a.RG; ++g) {
+      const float* sc = scratch + ((size_t)(g - 1) * NP + pr) * K * 8;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        acc[k][0] = add4(acc[k][0], ld4(sc + k * 8));
+        acc[k][1] = add4(acc[k][1], ld4(sc + k * 8 + 4));
+      }
+    }
+    float* out = a.dwpart + (size_t)blockIdx.y * K * a.cin * a.cout;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      st4(out + ((size_t)k * a.cin + 2 * ci2) * a.cout + cot0 + 4 * co4, acc[k][0]);
+      st4(out + ((size_t)k * a.cin + 2 * ci2 + 1) * a.cout + cot0 + 4 * co4, acc[k][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t kSmemBudget = 100 * 1024;
+static constexpr size_t kSmemBudgetW = 64 * 1024;
+
+static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int KS) {
+  const int S = cv.stride;
+  const int PLd = (cv.k - 1) / S;
+  const int PRd = std::max(0, (cv.t_in - 1 + cv.pad_left) / S - (cv.t_out - 1));
+  const int TPd = PLd + cv.t_out + PRd;
+  const int ncig = cv.cin / 4;
+  const int nseg = std::max(1, kThreads / ncig);
+  size_t f = (size_t)U * TPd * chan_stride(cv.cout) + (dn ? (size_t)U * cv.t_out * chan_stride(dn->cout) : 0);
+  f += (size_t)KS * U * cv.t_in * cv.cin + (size_t)4 * nseg * cv.cin;
+  return f * 4;
+}
+
+static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out) {
+  int U = std::max(1, (n + 147) / 148);
+  U = std::min(U, 16);
+  const int S = cv.stride, NT0 = (cv.k + S - 1) / S;
+  for (;; --U) {
+    int best_ks = 1;
+    double best_cost = 1e30;
+    for (int KS = 1; KS <= NT0; ++KS) {
+      const int mps = (NT0 + KS - 1) / KS;
+      if ((NT0 + mps - 1) / mps != KS) continue;   // skip slice counts that leave empty slices
+      const int rows = (cv.t_in + TMB - 1) / TMB + (S > 1 ? 1 : 0);
+      const long tasks = (long)KS * U * rows * (cv.cin / 4);
+      const double cost = (double)((tasks + kThreads - 1) / kThreads) * mps;
+      if (cost < best_cost - 1e-9 && bwd_data_smem(cv, dn, U, KS) <= kSmemBudget) {
+        best_cost = cost;
+        best_ks = KS;
+      }
+    }
+    if (best_cost < 1e29 || U == 1) {
+      *U_out = U;
+      *KS_out = best_ks;
+      return;
+    }
+  }
+}
+
+static size_t bwd_weight_smem(const ConvPlan& cv, int cot, int RG, int UB) {
+  const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
+  const int TP = cv.pad_left + cv.t_in + pad_right;
+  const size_t tiles = ((size_t)UB * TP * cv.cin + (size_t)UB * cv.t_out * cot) * 4;
+  const size_t np = (size_t)(cv.cin / 2) * (cot / 4);
+  const size_t scratch = (size_t)(RG - 1) * np * cv.k * 8 * 4;
+  return std::max(tiles, scratch);
+}
+
+// Static per-layer choice of (output-channel tile, row groups, row chunks, staged utterances).
+void plan_bwd_weight(tcr_handle* h) {
+  for (auto& cv : h->convs) {
+    int cot = 4;
+    for (int c = 4; c <= cv.cout; c += 4)
+      if (cv.cout % c == 0 && (cv.cin / 2) * (c / 4) <= 384) cot = c;
+    const int np = (cv.cin / 2) * (cot / 4);
+    int RG = std::max(1, std::min(8, 256 / np));
+    const int ncot = cv.cout / cot;
+    int R = std::max(1, std::min(64, (148 + ncot - 1) / ncot));
+    R = std::min(R, h->cfg.max_batch);
+    int UB = 16;
+    while (UB > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudgetW) --UB;
+    while (RG > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudget) --RG;
+    cv.dw_cot = cot;
+    cv.dw_RG = RG;
+    cv.dw_R = R;
+    cv.dw_UB = UB;
+  }
+}
+
+template <int K>
+static int launch_bwd_data(const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
+  auto kfn = conv_bwd_data_kernel<K>;
+#ifndef TCR_EMU
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+#endif
+  TCR_LAUNCH(kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  return 0;
+}
+
+template <int K>
+static int launch_bwd_weight(const BwdWeightArgs& a, int threads, size_t smem, cudaStream_t s) {
+  auto kfn = conv_bwd_weight_kernel<K>;
+#ifndef TCR_EMU
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+#endif
+  TCR_LAUNCH(kfn, dim3(a.cout / a.cot, a.R), dim3(threads), smem, s, a);
+  return 0;
+}
+
+static DySrc make_dy(const ConvPlan& cv, const float* dz, int mask, int n) {
+  return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, 1.0f / ((float)n * (float)cv.t_out)};
+}
+
+static int bwd_weight(tcr_handle* h, ConvPlan& cv, ActSrc x, DySrc dy, int n, cudaStream_t s) {
+  (void)h;
+  BwdWeightArgs a;
+  a.n = n; a.x = x; a.dy = dy;
+  a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride; a.t_in = cv.t_in; a.t_out = cv.t_out;
+  a.pad_left = cv.pad_left; a.cot = cv.dw_cot; a.RG = cv.dw_RG; a.R = cv.dw_R; a.UB = cv.dw_UB;
+  a.dwpart = cv.dwpart;
+  const int threads = ((a.RG * (cv.cin / 2) * (a.cot / 4) + 31) / 32) * 32;
+  const size_t smem = bwd_weight_smem(cv, a.cot, a.RG, a.UB);
+  switch (cv.k) {
+    case 1: return launch_bwd_weight<1>(a, threads, smem, s);
+    case 3: return launch_bwd_weight<3>(a, threads, smem, s);
+    case 9: return launch_bwd_weight<9>(a, threads, smem, s);
+    default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
+  }
+}
+
+static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, int slot, cudaStream_t s) {
+  int U, KS;
+  pick_bwd_tile(cv, dn, n, &U, &KS);
+  a.n = n; a.U = U;
+  a.w = params + cv.w_off; a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride;
+  a.t_in = cv.t_in; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
+  a.has_down = dn ? 1 : 0;
+  a.wd = dn ? params + dn->w_off : nullptr;
+  a.coutd = dn ? dn->cout : 0;
+  a.counter = h->d_counters + slot;
+  const int groups = (n + U - 1) / U;
+  const size_t smem = bwd_data_smem(cv, dn, U, KS);
+  switch (cv.k) {
+    case 3: return launch_bwd_data<3>(a, groups, smem, s);
+    case 9: return launch_bwd_data<9>(a, groups, smem, s);
+    default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
+  }
+}
+
+int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s) {
+  int slot = 32;
+  for (int i = (int)h->blocks.size() - 1; i >= 0; --i) {
+    BlockPlan& b = h->blocks[i];
+    ConvPlan& ca = h->convs[b.a];
+    ConvPlan& cb = h->convs[b.b];
+    ConvPlan* dn = b.down >= 0 ? &h->convs[b.down] : nullptr;
+    // (1) conv_b: dx is the gradient at relu(bn(y_a)); epilogue masks with bn(y_a) > 0 and sums for BN_a
+    {
+      BwdDataArgs a;
+      memset(&a, 0, sizeof(a));
+      a.dy = make_dy(cb, b.gblk, 0, n);
+      a.epi_kind = 1;
+      a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
+      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.cout};
+      a.finpd = a.finp;
+      int rc = bwd_data(h, cb, nullptr, a, params, n, slot++, s);
+      if (rc) return rc;
+    }
+    // (2) conv_a (+ down conv | identity): dx is the gradient at the block input
+    {
+      BwdDataArgs a;
+      memset(&a, 0, sizeof(a));
+      a.dy = make_dy(ca, ca.g, 0, n);
+      if (dn) a.dyd = make_dy(*dn, b.gblk, 1, n);
+      else a.gid = b.gblk;
+      if (i > 0) {
+        BlockPlan& pb = h->blocks[i - 1];
+        ConvPlan& pcb = h->convs[pb.b];
+        a.epi_kind = 2;
+        a.out_prev = pb.out;
+        a.yp = pcb.y; a.bnfp = pcb.bnf; a.bpartp = pcb.bpart;
+        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.cout};
+        a.finpd = a.finp;
+        if (pb.down >= 0) {
+          ConvPlan& pd = h->convs[pb.down];
+          a.ypd = pd.y; a.bnfpd = pd.bnf; a.bpartpd = pd.bpart;
+          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.cout};
+        }
+        a.gprev = pb.gblk;
+      } else {
+        ConvPlan& c0 = h->convs[0];
+        a.epi_kind = 1;
+        a.yp = c0.y; a.bnfp = c0.bnf; a.bpartp = c0.bpart; a.gprev = c0.g;
+        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.cout};
+        a.finpd = a.finp;
+      }
+      int rc = bwd_data(h, ca, dn, a, params, n, slot++, s);
+      if (rc) return rc;
+    }
+  }
+  // weight gradients: every layer's inputs are final now
+  {
+    ConvPlan& c0 = h->convs[0];
+    int rc = bwd_weight(h, c0, ActSrc{feat, nullptr, 0}, make_dy(c0, c0.g, 0, n), n, s);
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    BlockPlan& b = h->blocks[i];
+    ConvPlan& ca = h->convs[b.a];
+    ConvPlan& cb = h->convs[b.b];
+    const ActSrc xin = i == 0 ? ActSrc{h->convs[0].y, h->convs[0].bnf, 1} : ActSrc{h->blocks[i - 1].out, nullptr, 0};
+    int rc = bwd_weight(h, ca, xin, make_dy(ca, ca.g, 0, n), n, s);
+    if (rc) return rc;
+    if (b.down >= 0) {
+      ConvPlan& dn = h->convs[b.down];
+      rc = bwd_weight(h, dn, xin, make_dy(dn, b.gblk, 1, n), n, s);
+      if (rc) return rc;
+    }
+    rc = bwd_weight(h, cb, ActSrc{ca.y, ca.bnf, 1}, make_dy(cb, b.gblk, 0, n), n, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace tcr

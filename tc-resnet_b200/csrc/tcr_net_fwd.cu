@@ -1,0 +1,579 @@
+// tcr_net_fwd.cu — TC-ResNet forward kernels for sm_100a (fp32 CUDA-core FMA; see DESIGN.md for why the
+// 9x1 temporal convolutions stay on the FMA pipe: TF32/BF16 tensor-core products break the 1e-4 logit bound).
+//
+// Replaces tc_resnet() (audio_nets/tc_resnet.py:6-54) under TCResNet_arg_scope (:102-123):
+//   conv_fwd_kernel<K>  : [k,1] temporal conv (+ the block's 1x1/stride-2 shortcut conv from the same staged
+//                         input tile), BN+ReLU(+residual) of the PRODUCER applied while staging the tile,
+//                         per-CTA BatchNorm partial statistics in the epilogue, last CTA finalises the table.
+//   head_kernel         : residual + ReLU + global average pool + dropout + fc + softmax + cross-entropy and,
+//                         for training, dlogits -> gradient of the last block + fc weight-gradient partials.
+// A CTA owns U whole utterances, so SAME padding is a few zero rows of the shared-memory tile.
+#include "tcr_bn.cuh"
+#include "tcr_net.h"
+
+namespace tcr {
+
+constexpr int TM = 4;   // output rows per thread task
+
+// ------------------------------------------------------------------------------------------------
+// conv forward
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int u0 = blockIdx.x * a.U;
+  const int Ue = imin(a.U, a.n - u0);
+  const int CS = chan_stride(a.cin);
+  const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
+  const int TP = a.pad_left + a.t_in + pad_right;
+  const int Rmax = a.U * a.t_out;
+  float* xs = smem;                                   // [U][TP][CS]
+  float* ys = xs + (size_t)a.U * TP * CS;             // [KS][Rmax][cout]
+  float* ysd = ys + (size_t)a.KS * Rmax * a.cout;     // [Rmax][coutd]
+  float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);
+  float* smean = red + kThreads;
+
+  // ---- stage the input tile (producer's BN/ReLU/residual applied here) ----
+  const int c4n = a.cin >> 2;
+  const int npad = a.pad_left + pad_right;
+  for (int idx = tid; idx < Ue * npad * c4n; idx += kThreads) {
+    const int c4 = idx % c4n, pr = (idx / c4n) % npad, u = idx / (c4n * npad);
+    const int row = pr < a.pad_left ? pr : a.t_in + pr;
+    st4(xs + ((size_t)(u * TP + row) * CS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  for (int idx = tid; idx < Ue * a.t_in * c4n; idx += kThreads) {
+    const int c4 = idx % c4n, t = (idx / c4n) % a.t_in, u = idx / (c4n * a.t_in);
+    const size_t gofs = ((size_t)(u0 + u) * a.t_in + t) * a.cin + 4 * c4;
+    float4 v;
+    if (a.in_kind == 2) {
+      const float4 zb = bn_apply4(ld4(a.in.data + gofs), a.in.bnf, a.cin, 4 * c4);
+      const float4 sh = act_load4(a.shortcut, gofs, a.cin, 4 * c4);
+      v = relu4(add4(zb, sh));
+      if (a.out_write) st4(a.out_write + gofs, v);
+    } else {
+      v = act_load4(a.in, gofs, a.cin, 4 * c4);
+    }
+    st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * c4), v);
+  }
+  __syncthreads();
+
+  // ---- register-tiled conv: task = (k-slice, row tile of TM, 4 output channels) ----
+  const int R = Ue * a.t_out;
+  const int NRT = (R + TM - 1) / TM;
+  const int NCG = a.cout >> 2;
+  const int KPS = K / a.KS;
+  const int ntasks = NRT * NCG * a.KS;
+  const int NCGD = a.wd ? (a.coutd >> 2) : 0;
+  const int ntasks_all = ntasks + NRT * NCGD;
+  for (int task = tid; task < ntasks_all; task += kThreads) {
+    const bool is_down = task >= ntasks;
+    const int tk = is_down ? task - ntasks : task;
+    const int ncg = is_down ? NCGD : NCG;
+    const int cg = tk % ncg;
+    const int rt = (tk / ncg) % NRT;
+    const int ks = is_down ? 0 : tk / (ncg * NRT);
+    const float* xr[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int r = imin(rt * TM + i, R - 1);
+      const int u = r / a.t_out, t = r - u * a.t_out;
+      xr[i] = is_down ? xs + (size_t)(u * TP + a.pad_left + 2 * t) * CS : xs + (size_t)(u * TP + t * a.stride) * CS;
+    }
+    float4 acc[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k_lo = is_down ? 0 : ks * KPS, k_hi = is_down ? 1 : k_lo + KPS;
+    const int co_n = is_down ? a.coutd : a.cout;
+    const float* wbase = (is_down ? a.wd : a.w) + 4 * cg;
+    for (int k = k_lo; k < k_hi; ++k) {
+      const float* wk = wbase + (size_t)k * a.cin * co_n;
+      for (int ci = 0; ci < a.cin; ci += 4) {
+        const float4 w0 = ldg4(wk + (size_t)(ci + 0) * co_n), w1 = ldg4(wk + (size_t)(ci + 1) * co_n);
+        const float4 w2 = ldg4(wk + (size_t)(ci + 2) * co_n), w3 = ldg4(wk + (size_t)(ci + 3) * co_n);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          const float4 x = ld4(xr[i] + k * CS + ci);
+          acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y);
+          acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
+          acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y);
+          acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
+          acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y);
+          acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
+          acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y);
+          acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+        }
+      }
+    }
+    float* dst = is_down ? ysd : ys + (size_t)ks * Rmax * a.cout;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int r = rt * TM + i;
+      if (r < R) st4(dst + (size_t)r * co_n + 4 * cg, acc[i]);
+    }
+  }
+  __syncthreads();
+
+  // ---- epilogue: sum k-slices in fixed order, coalesced store of the pre-BN output ----
+  const size_t grow0 = (size_t)u0 * a.t_out;
+  for (int idx = tid; idx < R * NCG; idx += kThreads) {
+    float4 v = ld4(ys + (size_t)idx * 4);
+    for (int ks = 1; ks < a.KS; ++ks) v = add4(v, ld4(ys + (size_t)ks * Rmax * a.cout + (size_t)idx * 4));
+    st4(ys + (size_t)idx * 4, v);
+    st4(a.y + grow0 * a.cout + (size_t)idx * 4, v);
+  }
+  if (a.wd)
+    for (int idx = tid; idx < R * NCGD; idx += kThreads) st4(a.yd + grow0 * a.coutd + (size_t)idx * 4, ld4(ysd + (size_t)idx * 4));
+  if (!a.train) return;
+  __syncthreads();
+  tile_stats(ys, R, a.cout, red, smean, a.fpart + (size_t)blockIdx.x * a.cout * 2);
+  if (a.wd) tile_stats(ysd, R, a.coutd, red, smean, a.fpartd + (size_t)blockIdx.x * a.coutd * 2);
+  if (last_block_done(a.counter, gridDim.x)) {
+    bn_finalize(a.fin, gridDim.x, a.U, a.n, a.t_out, a.eps);
+    if (a.wd) bn_finalize(a.find, gridDim.x, a.U, a.n, a.t_out, a.eps);
+  }
+}
+
+// Eval mode: BN tables from the moving statistics (bn_forward with is_training=False).
+struct EvalBnArgs {
+  int nlayers;
+  const float* params;
+  const float* moving;
+  float eps;
+  int c[kMaxConvs];
+  int64_t gamma_off[kMaxConvs], beta_off[kMaxConvs], mm_off[kMaxConvs], mv_off[kMaxConvs];
+  float* bnf[kMaxConvs];
+};
+__global__ void bn_table_eval_kernel(EvalBnArgs a) {
+  const int l = blockIdx.x;
+  const int C = a.c[l];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = a.moving[a.mm_off[l] + c], var = a.moving[a.mv_off[l] + c];
+    const double rstd = 1.0 / sqrt((double)var + (double)a.eps);
+    a.bnf[l][c] = mean;
+    a.bnf[l][C + c] = (float)rstd;
+    a.bnf[l][2 * C + c] = (float)((double)a.params[a.gamma_off[l] + c] * rstd);
+    a.bnf[l][3 * C + c] = a.params[a.beta_off[l] + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: one warp per utterance
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadWarps = 8;
+constexpr int kHeadSlots = 4;   // channels per lane: c = lane + 32 j, C <= 128
+
+__global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int C = a.c, T = a.t, NC = a.classes;
+  float* s_sum = smem;                                   // [warps][4][C]
+  float* s_drop = s_sum + kHeadWarps * 4 * C;            // [warps][C]
+  float* s_dl = s_drop + kHeadWarps * C;                 // [warps][NC]
+  float* s_loss = s_dl + kHeadWarps * NC;                // [warps]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * kHeadWarps + warp;
+  const bool valid = n < a.n;
+
+  float pooled[kHeadSlots], mk[kHeadSlots], dropped[kHeadSlots];
+#pragma unroll
+  for (int j = 0; j < kHeadSlots; ++j) { pooled[j] = 0.f; mk[j] = 1.f; dropped[j] = 0.f; }
+  float loss_n = 0.f, dl = 0.f;
+  if (valid) {
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int j = 0; j < kHeadSlots; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const size_t ofs = ((size_t)n * T + t) * C + c;
+          const float zb = bn_apply1(a.in.data[ofs], a.in.bnf, C, c);
+          float sh = a.shortcut.data[ofs];
+          if (a.shortcut.kind == 1) sh = fmaxf(bn_apply1(sh, a.shortcut.bnf, C, c), 0.f);
+          const float o = fmaxf(zb + sh, 0.f);
+          if (a.out_write) a.out_write[ofs] = o;
+          pooled[j] += o;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadSlots; ++j) {
+      const int c = lane + 32 * j;
+      pooled[j] = pooled[j] / (float)T;
+      if (a.use_dropout && c < C) {
+        mk[j] = a.mask ? a.mask[(size_t)n * C + c] : floorf(a.keep + uniform01(a.seed, (uint64_t)n * C + c));
+        dropped[j] = pooled[j] / a.keep * mk[j];        // tf.nn.dropout: x / keep_prob * floor(keep_prob + U)
+      } else {
+        dropped[j] = pooled[j];
+      }
+    }
+    // fc (no bias): logits[k] = sum_c dropped[c] W[c,k]; lane k keeps logits[k]
+    float logit = 0.f;
+    for (int k = 0; k < NC; ++k) {
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < kHeadSlots; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) p = fmaf(dropped[j], __ldg(a.wfc + (size_t)c * NC + k), p);
+      }
+      p = warp_sum(p);
+      if (lane == k) logit = p;
+    }
+    const bool act = lane < NC;
+    const float mx = warp_max(act ? logit : -3.0e38f);
+    const float e = act ? expf(logit - mx) : 0.f;
+    const float se = warp_sum(e);
+    const float prob = e / se;
+    const float logp = (logit - mx) - logf(se);
+    if (act) {
+      if (a.logits) a.logits[(size_t)n * NC + lane] = logit;
+      if (a.probs) a.probs[(size_t)n * NC + lane] = prob;
+    }
+    if (a.onehot) {
+      float lab = act ? a.onehot[(size_t)n * NC + lane] : 0.f;
+      if (a.label_smoothing > 0.f && act) lab = lab * (1.f - a.label_smoothing) + a.label_smoothing / (float)NC;
+      const float labsum = warp_sum(lab);
+      loss_n = -warp_sum(act ? lab * logp : 0.f);
+      dl = act ? (prob * labsum - lab) * a.inv_n : 0.f;
+    }
+  }
+  if (!a.backward) {
+    if (a.onehot) {
+      if (lane == 0) s_loss[warp] = loss_n;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
+        a.loss_part[blockIdx.x] = s;
+      }
+      if (last_block_done(a.counter, gridDim.x) && threadIdx.x == 0) {
+        double s = 0.0;
+        for (unsigned g = 0; g < gridDim.x; ++g) s += (double)__ldcg(a.loss_part + g);
+        *a.loss_out = (float)s;
+      }
+    }
+    return;
+  }
+
+  // ---- head backward: d pooled -> gradient at the block output, BN-backward partial sums ----
+  float sb1[kHeadSlots], sb2[kHeadSlots], sd1[kHeadSlots], sd2[kHeadSlots];
+#pragma unroll
+  for (int j = 0; j < kHeadSlots; ++j) sb1[j] = sb2[j] = sd1[j] = sd2[j] = 0.f;
+  if (valid) {
+    float dnet[kHeadSlots];
+#pragma unroll
+    for (int j = 0; j < kHeadSlots; ++j) dnet[j] = 0.f;
+    for (int k = 0; k < NC; ++k) {
+      const float dlk = __shfl_sync(0xffffffffu, dl, k);
+#pragma unroll
+      for (int j = 0; j < kHeadSlots; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) dnet[j] = fmaf(dlk, __ldg(a.wfc + (size_t)c * NC + k), dnet[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadSlots; ++j) {
+      if (a.use_dropout) dnet[j] = dnet[j] / a.keep * mk[j];
+      dnet[j] = dnet[j] / (float)T;                       // AvgPoolGrad
+    }
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int j = 0; j < kHeadSlots; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const size_t ofs = ((size_t)n * T + t) * C + c;
+          const float o = a.out_write[ofs];
+          const float g = o > 0.f ? dnet[j] : 0.f;
+          a.gout[ofs] = g;
+          const float yb = a.yb[ofs];
+          sb1[j] += g;
+          sb2[j] = fmaf(g, (yb - __ldg(a.bnfb + c)) * __ldg(a.bnfb + C + c), sb2[j]);
+          if (a.ydn) {
+            const float yd = a.ydn[ofs];
+            const float zd = bn_apply1(yd, a.bnfd, C, c);
+            const float gs = zd > 0.f ? g : 0.f;
+            sd1[j] += gs;
+            sd2[j] = fmaf(gs, (yd - __ldg(a.bnfd + c)) * __ldg(a.bnfd + C + c), sd2[j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kHeadSlots; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) {
+      s_sum[(warp * 4 + 0) * C + c] = sb1[j];
+      s_sum[(warp * 4 + 1) * C + c] = sb2[j];
+      s_sum[(warp * 4 + 2) * C + c] = sd1[j];
+      s_sum[(warp * 4 + 3) * C + c] = sd2[j];
+      s_drop[warp * C + c] = dropped[j];
+    }
+  }
+  if (lane < NC) s_dl[warp * NC + lane] = dl;
+  if (lane == 0) s_loss[warp] = loss_n;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    const int q = i / C, c = i - q * C;
+    float s = 0.f;
+    for (int w = 0; w < kHeadWarps; ++w) s += s_sum[(w * 4 + q) * C + c];
+    if (q < 2) a.bpartb[((size_t)blockIdx.x * C + c) * 2 + q] = s;
+    else if (a.ydn) a.bpartd[((size_t)blockIdx.x * C + c) * 2 + (q - 2)] = s;
+  }
+  for (int i = threadIdx.x; i < C * NC; i += blockDim.x) {
+    const int c = i / NC, k = i - c * NC;
+    float s = 0.f;
+    for (int w = 0; w < kHeadWarps; ++w) s = fmaf(s_drop[w * C + c], s_dl[w * NC + k], s);
+    a.dwfc_part[(size_t)blockIdx.x * C * NC + i] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
+    a.loss_part[blockIdx.x] = s;
+  }
+  if (last_block_done(a.counter, gridDim.x)) {
+    bwdsum_finalize(a.finb, gridDim.x);
+    if (a.ydn) bwdsum_finalize(a.find, gridDim.x);
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (unsigned g = 0; g < gridDim.x; ++g) s += (double)__ldcg(a.loss_part + g);
+      *a.loss_out = (float)s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t kSmemBudget = 100 * 1024;   // keeps two CTAs resident per SM
+
+int head_groups(int n) { return (n + kHeadWarps - 1) / kHeadWarps; }
+
+static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int KS) {
+  const int CS = chan_stride(cv.cin);
+  const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
+  const int TP = cv.pad_left + cv.t_in + pad_right;
+  size_t f = (size_t)U * TP * CS + (size_t)KS * U * cv.t_out * cv.cout + (dn ? (size_t)U * cv.t_out * dn->cout : 0);
+  f += kThreads + std::max(cv.cout, dn ? dn->cout : 0);
+  return f * 4;
+}
+
+// Utterances per CTA and k-slices: fill 148 SMs, keep shared memory under budget, balance thread tasks.
+static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out) {
+  int U = std::max(1, (n + 147) / 148);
+  U = std::min(U, 16);
+  for (;; --U) {
+    int best_ks = 1;
+    double best_cost = 1e30;
+    for (int KS = 1; KS <= cv.k; ++KS) {
+      if (cv.k % KS) continue;
+      const int nrt = (U * cv.t_out + TM - 1) / TM;
+      const long tasks = (long)nrt * (cv.cout / 4) * KS + (dn ? (long)nrt * (dn->cout / 4) : 0);
+      const double cost = (double)((tasks + kThreads - 1) / kThreads) * (cv.k / KS);
+      if (cost < best_cost - 1e-9 && fwd_smem_bytes(cv, dn, U, KS) <= kSmemBudget) {
+        best_cost = cost;
+        best_ks = KS;
+      }
+    }
+    if (best_cost < 1e29 || U == 1) {
+      *U_out = U;
+      *KS_out = best_ks;
+      return;
+    }
+  }
+}
+
+template <class T>
+static int ws_alloc(tcr_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (cudaMalloc(&q, bytes) != cudaSuccess) {
+    set_error("cudaMalloc failed while sizing the workspace");
+    return TCR_ERR_CUDA;
+  }
+  h->allocs.push_back(q);
+  h->workspace_bytes += (int64_t)bytes;
+  *p = (T*)q;
+  return 0;
+}
+#define WS(x)             \
+  do {                    \
+    int rc_ = (x);        \
+    if (rc_) return rc_;  \
+  } while (0)
+
+void plan_bwd_weight(tcr_handle* h);   // tcr_net_bwd.cu
+int build_opt_segments(tcr_handle* h); // tcr_optim.cu
+
+int net_alloc_workspace(tcr_handle* h) {
+  const size_t N = (size_t)h->cfg.max_batch;
+  h->g_max = h->cfg.max_batch;                       // U >= 1 -> at most max_batch CTA groups
+  h->head_groups_max = head_groups(h->cfg.max_batch);
+  plan_bwd_weight(h);
+  WS(ws_alloc(h, &h->d_feat, N * h->frames * h->features));
+  WS(ws_alloc(h, &h->d_logits, N * h->cfg.num_classes));
+  WS(ws_alloc(h, &h->d_probs, N * h->cfg.num_classes));
+  for (auto& cv : h->convs) {
+    const size_t act = N * cv.t_out * cv.cout;
+    WS(ws_alloc(h, &cv.y, act));
+    WS(ws_alloc(h, &cv.bnf, 4 * (size_t)cv.cout));
+    WS(ws_alloc(h, &cv.var, (size_t)cv.cout));
+    WS(ws_alloc(h, &cv.fpart, (size_t)h->g_max * cv.cout * 2));
+    WS(ws_alloc(h, &cv.bpart, (size_t)std::max(h->g_max, h->head_groups_max) * cv.cout * 2));
+    WS(ws_alloc(h, &cv.bsum, 2 * (size_t)cv.cout));
+    WS(ws_alloc(h, &cv.dwpart, (size_t)cv.dw_R * cv.wnumel()));
+  }
+  WS(ws_alloc(h, &h->convs[0].g, N * h->convs[0].t_out * h->convs[0].cout));
+  for (auto& b : h->blocks) {
+    WS(ws_alloc(h, &b.out, N * b.t * b.c));
+    WS(ws_alloc(h, &b.gblk, N * b.t * b.c));
+    ConvPlan& ca = h->convs[b.a];
+    WS(ws_alloc(h, &ca.g, N * ca.t_out * ca.cout));
+    h->convs[b.b].g = b.gblk;
+    if (b.down >= 0) h->convs[b.down].g = b.gblk;
+  }
+  WS(ws_alloc(h, &h->d_loss_part, (size_t)h->head_groups_max));
+  WS(ws_alloc(h, &h->d_loss, 4));
+  WS(ws_alloc(h, &h->d_dwfc_part, (size_t)h->head_groups_max * h->c_last * h->cfg.num_classes));
+  WS(ws_alloc(h, &h->d_grads, (size_t)h->n_train));
+  WS(ws_alloc(h, &h->d_l2part, 4096));
+  WS(ws_alloc(h, &h->d_counters, 64));
+  if (cudaMemset(h->d_counters, 0, 64 * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
+  WS(ws_alloc(h, &h->d_hyper, 1));
+  if (cudaMallocHost((void**)&h->h_hyper, sizeof(Hyper)) != cudaSuccess) return TCR_ERR_CUDA;
+  return build_opt_segments(h);
+}
+
+template <int K>
+static int launch_conv_fwd(const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
+  auto kfn = conv_fwd_kernel<K>;
+#ifndef TCR_EMU
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+#endif
+  TCR_LAUNCH(kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  return 0;
+}
+
+static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const float* params, int n, bool training,
+                    int counter_slot, cudaStream_t s) {
+  int U, KS;
+  pick_fwd_tile(cv, dn, n, &U, &KS);
+  a.n = n; a.U = U; a.t_in = cv.t_in; a.cin = cv.cin;
+  a.w = params + cv.w_off; a.y = cv.y; a.fpart = cv.fpart;
+  a.cout = cv.cout; a.stride = cv.stride; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
+  a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
+  a.train = training ? 1 : 0;
+  a.counter = h->d_counters + counter_slot;
+  a.eps = h->cfg.bn_epsilon;
+  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.cout};
+  a.find = a.fin;
+  if (dn) {
+    a.wd = params + dn->w_off; a.yd = dn->y; a.fpartd = dn->fpart; a.coutd = dn->cout;
+    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->cout};
+  }
+  const int groups = (n + U - 1) / U;
+  const size_t smem = fwd_smem_bytes(cv, dn, U, KS);
+  switch (cv.k) {
+    case 3: return launch_conv_fwd<3>(a, groups, smem, s);
+    case 9: return launch_conv_fwd<9>(a, groups, smem, s);
+    case 1: return launch_conv_fwd<1>(a, groups, smem, s);
+    default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
+  }
+}
+
+int net_forward(tcr_handle* h, const float* feat, const float* params, const float* moving, int n, bool training,
+                uint64_t seed, const float* mask, const float* onehot, float weight_decay, float* logits,
+                float* probs, float* losses, bool backward, cudaStream_t s) {
+  (void)weight_decay;
+  if (h->c_last > 32 * kHeadSlots) { set_error("last_channels > 128 unsupported by the head kernel"); return TCR_ERR_UNSUPPORTED; }
+  if (!training) {
+    EvalBnArgs e;
+    e.nlayers = (int)h->convs.size();
+    e.params = params; e.moving = moving; e.eps = h->cfg.bn_epsilon;
+    for (int l = 0; l < e.nlayers; ++l) {
+      const ConvPlan& cv = h->convs[l];
+      e.c[l] = cv.cout; e.gamma_off[l] = cv.gamma_off; e.beta_off[l] = cv.beta_off;
+      e.mm_off[l] = cv.mm_off; e.mv_off[l] = cv.mv_off; e.bnf[l] = cv.bnf;
+    }
+    TCR_LAUNCH(bn_table_eval_kernel, dim3(e.nlayers), dim3(128), 0, s, e);
+  }
+  int slot = 0;
+  // conv0 on raw features
+  {
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in_kind = 0;
+    a.in = ActSrc{feat, nullptr, 0};
+    int rc = conv_fwd(h, h->convs[0], nullptr, a, params, n, training, slot++, s);
+    if (rc) return rc;
+  }
+  ActSrc prev{h->convs[0].y, h->convs[0].bnf, 1};   // activation feeding the next block
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    BlockPlan& b = h->blocks[i];
+    ConvPlan& ca = h->convs[b.a];
+    ConvPlan& cb = h->convs[b.b];
+    ConvPlan* dn = b.down >= 0 ? &h->convs[b.down] : nullptr;
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    if (i == 0) {
+      a.in_kind = 1;
+      a.in = prev;
+    } else {
+      // input = output of block i-1 = relu(bn(y_b) + shortcut); materialised here for the backward pass
+      BlockPlan& pb = h->blocks[i - 1];
+      a.in_kind = 2;
+      a.in = ActSrc{h->convs[pb.b].y, h->convs[pb.b].bnf, 0};
+      a.shortcut = pb.down >= 0 ? ActSrc{h->convs[pb.down].y, h->convs[pb.down].bnf, 1} : prev;
+      a.out_write = pb.out;
+    }
+    int rc = conv_fwd(h, ca, dn, a, params, n, training, slot++, s);
+    if (rc) return rc;
+    if (i > 0) prev = ActSrc{h->blocks[i - 1].out, nullptr, 0};   // materialised by the launch above
+    FwdArgs a2;
+    memset(&a2, 0, sizeof(a2));
+    a2.in_kind = 1;
+    a2.in = ActSrc{ca.y, ca.bnf, 1};
+    rc = conv_fwd(h, cb, nullptr, a2, params, n, training, slot++, s);
+    if (rc) return rc;
+    if (i + 1 == h->blocks.size()) {
+      BlockPlan& lb = b;
+      HeadArgs ha;
+      memset(&ha, 0, sizeof(ha));
+      ha.in = ActSrc{cb.y, cb.bnf, 0};
+      ha.shortcut = dn ? ActSrc{dn->y, dn->bnf, 1} : prev;
+      ha.out_write = lb.out;
+      ha.n = n; ha.t = lb.t; ha.c = lb.c; ha.classes = h->cfg.num_classes;
+      ha.wfc = params + h->fc_off;
+      ha.onehot = onehot;
+      ha.mask = mask; ha.seed = seed; ha.keep = h->cfg.dropout_keep_prob;
+      ha.use_dropout = (training && h->cfg.dropout_keep_prob < 1.0f) ? 1 : 0;
+      ha.label_smoothing = h->cfg.label_smoothing;
+      ha.logits = logits ? logits : h->d_logits;
+      ha.probs = probs ? probs : h->d_probs;
+      ha.loss_part = h->d_loss_part;
+      ha.backward = backward ? 1 : 0;
+      ha.inv_n = 1.0f / (float)n;
+      ha.gout = lb.gblk;
+      ha.yb = cb.y; ha.bnfb = cb.bnf; ha.bpartb = cb.bpart;
+      ha.ydn = dn ? dn->y : nullptr; ha.bnfd = dn ? dn->bnf : nullptr; ha.bpartd = dn ? dn->bpart : nullptr;
+      ha.dwfc_part = h->d_dwfc_part;
+      ha.counter = h->d_counters + slot++;
+      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.cout};
+      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->cout} : ha.finb;
+      ha.loss_out = h->d_loss;
+      const int groups = head_groups(n);
+      const size_t smem = (size_t)(kHeadWarps * 4 * lb.c + kHeadWarps * lb.c + kHeadWarps * ha.classes + kHeadWarps) * 4;
+      TCR_LAUNCH(head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+    }
+    // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next
+    // block's first kernel, so `prev` is updated at the top of the next iteration.
+  }
+  if (losses && onehot && !backward) {
+    int rc = launch_loss_only(h, params, weight_decay, n, losses, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace tcr

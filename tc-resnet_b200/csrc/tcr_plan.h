@@ -1,0 +1,69 @@
+// tcr_plan.h — host-side layer plan and handle of libtcr_b200.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "tcr_device.cuh"
+#include "tcr_internal.h"
+#include "tcr_mfcc.h"
+
+namespace tcr {
+
+struct ConvPlan {
+  std::string name;            // TF scope under <Net>/, e.g. "block0/conv0_0"
+  int cin = 0, cout = 0, k = 0, stride = 1, t_in = 0, t_out = 0, pad_left = 0, relu = 1;
+  int64_t w_off = 0, beta_off = 0, gamma_off = 0;   // offsets into the flat trainable buffer
+  int64_t mm_off = 0, mv_off = 0;                    // offsets into the flat moving-statistics buffer
+  // workspace (device)
+  float* y = nullptr;          // [N, t_out, cout] pre-BN
+  float* g = nullptr;          // [N, t_out, cout] dL/dz (conv_a / conv0 own one; conv_b and down alias gblk)
+  float* bnf = nullptr;        // [4][cout]
+  float* var = nullptr;        // [cout]
+  float* fpart = nullptr;      // [G][cout][2]
+  float* bpart = nullptr;      // [G][cout][2]
+  float* bsum = nullptr;       // [2][cout]
+  float* dwpart = nullptr;     // [R][k*cin*cout]
+  int dw_R = 1, dw_cot = 0, dw_RG = 1, dw_UB = 1;
+  int64_t wnumel() const { return (int64_t)k * cin * cout; }
+};
+
+struct BlockPlan {
+  int down = -1, a = -1, b = -1;   // indices into convs
+  int c = 0, t = 0;
+  float* out = nullptr;            // [N, t, c]
+  float* gblk = nullptr;           // [N, t, c]
+};
+
+}  // namespace tcr
+
+struct tcr_handle {
+  tcr_config cfg;
+  int frames = 0, features = 0, fft = 0, fpb = 1;
+  std::string scope;
+  std::vector<tcr::ConvPlan> convs;
+  std::vector<tcr::BlockPlan> blocks;
+  int c_last = 0, t_last = 0;
+  int64_t n_train = 0, n_moving = 0, fc_off = 0, fc2_off = 0;
+  std::vector<tcr_param_desc> table;
+  int g_max = 0;                 // max CTA groups of any producer kernel (partials are sized for it)
+  int head_groups_max = 0;
+  // front-end tables
+  float* d_window = nullptr; float2* d_tw = nullptr; float2* d_tw2 = nullptr;
+  int* d_mel_start = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr;
+  float* d_mel_w = nullptr; float* d_dct = nullptr;
+  // workspace
+  float* d_feat = nullptr;
+  float* d_logits = nullptr; float* d_probs = nullptr;
+  float* d_loss_part = nullptr; float* d_loss = nullptr; float* d_dwfc_part = nullptr;
+  float* d_grads = nullptr;
+  float* d_l2part = nullptr;
+  unsigned* d_counters = nullptr;
+  tcr::Hyper* d_hyper = nullptr; tcr::Hyper* h_hyper = nullptr;
+  tcr::OptSegment* d_segs = nullptr; int n_segs = 0;
+  tcr::MovingSegment* d_msegs = nullptr; int n_msegs = 0;
+  std::vector<void*> allocs;
+  int64_t workspace_bytes = 0;
+  // data-parallel
+  void* comm = nullptr; int rank = 0, world = 1;
+  int last_n = 0;
+};
