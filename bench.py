@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — utterances/sec of the TC-ResNet training step (MFCC front-end + fwd + bwd + SGD-momentum).
+
+  python bench.py --gpus N --steps K --warmup W                 # our sm_100a CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path restated (oracle port)
+
+Prints ONE JSON line (rank 0).  A "step" = one pass of the hot path over one batch of synthetic 16 kHz 1 s
+clips U(-1,1) (BASELINE.json configs[1]: TCResNet8-1.0, batch 512 per GPU, MFCC 49x40, 12 classes).
+`value` is device-timed with the batches already resident in HBM; `e2e` goes through the public Engine API
+from pinned HOST buffers with the H2D copy and the D2H loss read inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "utterances/sec (fwd+bwd+update) TCResNet8-1.0"
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="TCResNet8", choices=["TCResNet8", "TCResNet14"])
+    ap.add_argument("--width", type=float, default=1.0)
+    ap.add_argument("--batch", type=int, default=512, help="utterances per GPU per step")
+    ap.add_argument("--window-ms", type=float, default=40.0)
+    ap.add_argument("--stride-ms", type=float, default=20.0)
+    ap.add_argument("--rotate", type=int, default=8, help="distinct resident input batches (footprint > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    t = 1 + (16000 - int(16 * a.window_ms)) // int(16 * a.stride_ms)
+    return (f"{a.model}-{a.width:g} train step (MFCC {t}x40 front-end + fwd + bwd + SGD-momentum), synthetic 16 kHz 1 s clips, "
+            f"batch {a.batch}/GPU, 12 classes")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.proc, self.path = None, f"/tmp/tcr_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path restated (oracle port, PyTorch-CPU fp32, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_step_fn(a, batch):
+    import numpy as np
+    import torch
+    from oracle import tcr_oracle as O
+    from oracle.torch_port import TorchPort
+    torch.set_num_threads(os.cpu_count() or 1)
+    window, stride = int(16 * a.window_ms), int(16 * a.stride_ms)
+    spec = O.build_spec(a.model, a.width, O.num_frames(16000, window, stride))
+    params, moving = O.init_variables(spec, 0, np.float32)
+    port = TorchPort(spec, params, moving, window, stride, keep_prob=0.5)
+    wav_np, onehot_np = O.synthetic_batch(batch, seed_wav=1234)
+    wav, onehot = torch.from_numpy(wav_np), torch.from_numpy(onehot_np)
+
+    def step():
+        port.train_step(wav, onehot, 0.1, 0.9, 1e-3)
+    return step, torch.get_num_threads()
+
+
+def run_cpu_sample(a, seconds):
+    """Bounded sample of the same workload on the host cores: returns the cpu_baseline object."""
+    batch = a.batch
+    step, cores = cpu_port_step_fn(a, batch)
+    step()
+    t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
+    while dt > seconds / 3 and batch > 32:          # keep >= 3 timed steps inside the budget
+        batch //= 2
+        step, cores = cpu_port_step_fn(a, batch)
+        step()
+        t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
+    nsteps = max(3, min(50, int(seconds / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        step()
+    dt = (time.perf_counter() - t0) / nsteps
+    return {"value": batch / dt, "unit": "utterances/sec", "cores": cores, "kind": "port",
+            "sample": f"{nsteps} training steps of batch {batch} (same model/shape), PyTorch-CPU fp32 restatement of the "
+                      f"reference's TF-1.13 graph (TF 1.13.1 not installable here), {dt * 1e3:.1f} ms/step"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = a.batch
+    step, cores = cpu_port_step_fn(a, batch)
+    step()
+    t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
+    budget = 150.0
+    while dt * (a.steps + a.warmup) > budget and batch > 16:
+        batch //= 2
+        step, cores = cpu_port_step_fn(a, batch)
+        step()
+        t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = batch * a.steps / el
+    sample = (f"each step = one training step on a bounded sample of {batch} of the {a.batch} utterances, PyTorch-CPU fp32 "
+              f"restatement of the reference graph (TF 1.13.1 not installable), {cores} threads")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "utterances/sec", "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": el / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "global_batch": a.batch * a.gpus, "sample_batch": batch},
+           "cpu_baseline": {"value": value, "unit": "utterances/sec", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "utterances/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def kernel_work(plan, name, n):
+    """(algorithmic bytes, flops) of ONE launch of kernel `name` over n utterances."""
+    convs = {c.name: c for c in plan.convs()}
+    if name == "mfcc":
+        return n * (4 * plan.clip + 4 * plan.frames * plan.features), n * plan.frontend_flops()
+    kind, _, layer = name.partition(":")
+    if layer in convs:
+        c = convs[layer]
+        down = next((b.down for b in plan.blocks if b.conv_a.name == layer and b.down is not None), None)
+        macs = c.macs + (down.macs if (down and kind in ("fwd", "dx")) else 0)
+        act_in, act_out = 4 * c.t_in * c.cin, 4 * c.t_out * c.cout
+        if kind == "fwd":
+            bytes_ = n * (act_in + act_out + (4 * down.t_out * down.cout if down else 0)) + 4 * c.weights
+        elif kind == "dx":    # reads dz + y of this layer (+ down), y/out of the layer below, writes dz below
+            bytes_ = n * (2 * act_out + (8 * down.t_out * down.cout if down else 0) + 3 * act_in) + 4 * c.weights
+        else:                 # dw: reads x, dz, y; writes partials (counted once)
+            bytes_ = n * (act_in + 2 * act_out) + 4 * c.weights
+        return bytes_, 2.0 * n * macs
+    if name == "head":
+        return n * (3 * 4 * plan.t_last * plan.c_last), 2.0 * n * plan.c_last * plan.num_classes * 2
+    return 12.0 * plan.num_trainable, 4.0 * plan.num_trainable
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.engine import Engine
+    from tcresnet_b200.plan import build_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = a.batch
+    eng = Engine(model=a.model, width_multiplier=a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms,
+                 max_batch=n, dropout_keep_prob=0.5, device=local)
+    if world > 1:
+        eng.attach_process_group()
+    plan = build_plan(a.model, a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms)
+    params, slots, moving = eng.new_variables(seed=0)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    rot = max(1, a.rotate)
+    wavs = [torch.rand(n, plan.clip, device=dev, generator=gen) * 2 - 1 for _ in range(rot)]
+    labels = torch.randint(0, 12, (rot, n), device=dev, generator=torch.Generator(device=dev).manual_seed(4321))
+    onehots = [torch.nn.functional.one_hot(labels[i], 12).float().contiguous() for i in range(rot)]
+    losses = torch.zeros(2, device=dev)
+    lr, mom, wd = 0.1, 0.9, 1e-3
+
+    def step(i):
+        eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i, losses=losses)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(losses[0].item())
+    value = n * world * a.steps / (ms * 1e-3)
+
+    out = {"metric": METRIC, "value": value, "unit": "utterances/sec", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "ours",
+           "config": {"workload": workload_name(a), "global_batch": n * world, "parallelism": f"dp{world}",
+                      "l2": f"inputs rotate over {rot} resident batches ({rot * n * plan.clip * 4 / 1e6:.0f} MB > 126 MB L2)",
+                      "final_total_loss": final_loss},
+           "gpu_launches": int(launches), "clocks": clocks}
+
+    if rank == 0:
+        # ---- per-kernel durations (separate pass: event brackets add overhead, so not the timed region) ----
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        fp32_peak = eng.fp32_peak_tflops()
+        psteps = min(a.steps, 30)
+        eng.profile(True)
+        for i in range(psteps):
+            step(i)
+        torch.cuda.synchronize()
+        stats = eng.profile_read()
+        eng.profile(False)
+        total_ms = sum(v[0] for v in stats.values())
+        top = sorted(stats.items(), key=lambda kv: -kv[1][0])
+        kernels = []
+        for name, (tms, cnt) in top:
+            b, f = kernel_work(plan, name, n)
+            dur = tms / cnt * 1e-3
+            kernels.append({"name": name, "us": dur * 1e6, "share": tms / total_ms, "GBps": b / dur / 1e9, "TFLOPs": f / dur / 1e12})
+        dom = kernels[0]
+        out["roofline"] = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                           "frac": dom["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                           "kernel_share_of_step": dom["share"],
+                           "fp32": {"achieved_tflops": dom["TFLOPs"], "peak_tflops": fp32_peak, "frac": dom["TFLOPs"] / max(fp32_peak, 1e-9),
+                                    "peak_source": "measured in this run (tcr_measure_fp32_peak, FMA loop on all SMs)"},
+                           "step": {"train_flops_per_utt": plan.train_flops(), "min_bytes_per_utt": plan.min_bytes(n),
+                                    "fp32_frac": plan.train_flops() * (value / world) / 1e12 / max(fp32_peak, 1e-9),
+                                    "hbm_frac": plan.min_bytes(n) * (value / world) / 1e9 / hbm_peak}}
+        out["kernels"] = kernels[:12]
+
+    # ---- end to end through the public API: pinned host -> H2D -> step -> D2H loss, every step ----
+    if not a.no_e2e:
+        h_wavs = [w.cpu().pin_memory() for w in wavs[:min(rot, 4)]]
+        h_hots = [o.cpu().pin_memory() for o in onehots[:min(rot, 4)]]
+        d_wav, d_hot = torch.empty_like(wavs[0]), torch.empty_like(onehots[0])
+        h_loss = torch.zeros(2).pin_memory()
+        esteps = min(a.steps, 50)
+
+        def e2e_step(i):
+            d_wav.copy_(h_wavs[i % len(h_wavs)], non_blocking=True)
+            d_hot.copy_(h_hots[i % len(h_hots)], non_blocking=True)
+            eng.train_step(d_wav, d_hot, params, slots, moving, lr, mom, wd, dropout_seed=i, losses=losses)
+            h_loss.copy_(losses, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the trainer reads the loss of every step
+            return float(h_loss[0])
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(esteps):
+            e2e_step(i)
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(el, op=torch.distributed.ReduceOp.MAX)
+        out["e2e"] = {"value": n * world * esteps / float(el.item()), "unit": "utterances/sec",
+                      "h2d_bytes_per_step": int(d_wav.numel() * 4 + d_hot.numel() * 4), "d2h_bytes_per_step": 8, "steps": esteps,
+                      "api": "tcresnet_b200.engine.Engine.train_step from pinned host buffers, loss read back every step"}
+
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = run_cpu_sample(a, a.cpu_seconds)
+            except Exception as e:  # the oracle port must never take the bench line down
+                out["cpu_baseline"] = {"value": None, "unit": "utterances/sec", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"failed: {e}"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,20 @@ int tcr_comm_destroy(tcr_handle* h);
  * denominator by bench.py.  Launches a register-resident FMA loop and times it with CUDA events. */
 int tcr_measure_fp32_peak(tcr_handle* h, double* tflops, tcr_stream stream);
 
+/* Process-wide launch accounting (no reference counterpart; the reference only logs wall-clock per
+ * session.run, helper/trainer.py:312-321).  tcr_launch_count: kernels launched by this library so far.
+ * tcr_profile_enable(1) brackets every subsequent launch with CUDA events on its stream (adds overhead:
+ * use a separate pass, not the timed region); tcr_profile_read synchronises and returns one row per
+ * kernel name ("mfcc", "fwd:block0/conv0_0", "dx:...", "dw:...", "head", "grad_finalize", "update"). */
+typedef struct tcr_kernel_stat {
+  char    name[64];
+  double  total_ms;
+  int64_t launches;
+} tcr_kernel_stat;
+int tcr_profile_enable(int enable);
+int tcr_profile_read(const tcr_kernel_stat** stats, int32_t* count);
+int tcr_launch_count(uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

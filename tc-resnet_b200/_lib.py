@@ -50,6 +50,10 @@ class TcrParamDesc(C.Structure):
     ]
 
 
+class TcrKernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("total_ms", C.c_double), ("launches", C.c_int64)]
+
+
 class TcrStepArgs(C.Structure):
     _fields_ = [
         ("input", C.c_void_p), ("input_is_features", C.c_int32), ("onehot", C.c_void_p), ("n", C.c_int32),
@@ -80,6 +84,9 @@ SYMBOLS = {
     "tcr_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tcr_comm_destroy": (C.c_int, [C.c_void_p]),
     "tcr_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "tcr_profile_enable": (C.c_int, [C.c_int]),
+    "tcr_profile_read": (C.c_int, [C.POINTER(C.POINTER(TcrKernelStat)), C.POINTER(C.c_int32)]),
+    "tcr_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
 }
 
 

@@ -8,8 +8,16 @@
 #else
 #include <cuda_runtime.h>
 #include <stdint.h>
-#define TCR_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+namespace tcr {
+void prof_begin(const char* name, cudaStream_t s);   // tcr_prof.cu: launch counter + optional CUDA-event bracket
+void prof_end(cudaStream_t s);
+}
+#define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                           \
+    tcr::prof_begin((name), (cudaStream_t)(stream));                             \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);    \
+    tcr::prof_end((cudaStream_t)(stream));                                       \
+  } while (0)
 #define TCR_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #endif
 

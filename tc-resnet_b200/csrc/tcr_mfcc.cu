@@ -220,14 +220,18 @@ int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
 #define TCR_MFCC_CASE(NF2)                                                                                   \
   case NF2: {                                                                                                \
     auto k = mfcc_kernel<NF2>;                                                                               \
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-    TCR_LAUNCH(k, grid, block, smem, stream, a);                                                             \
+    static size_t smem_limit = 48 * 1024;                                                                    \
+    if (smem > smem_limit) {                                                                                 \
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+      smem_limit = smem;                                                                                     \
+    }                                                                                                        \
+    TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);                                                             \
   } break;
 #else
 #define TCR_MFCC_CASE(NF2)                         \
   case NF2: {                                      \
     auto k = mfcc_kernel<NF2>;                     \
-    TCR_LAUNCH(k, grid, block, smem, stream, a);   \
+    TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);   \
   } break;
 #endif
   switch (nf2) {

@@ -347,22 +347,30 @@ void plan_bwd_weight(tcr_handle* h) {
 }
 
 template <int K>
-static int launch_bwd_data(const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
+static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
   auto kfn = conv_bwd_data_kernel<K>;
 #ifndef TCR_EMU
-  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+  static size_t smem_limit = 48 * 1024;   // per template instantiation
+  if (smem > smem_limit) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+    smem_limit = smem;
+  }
 #endif
-  TCR_LAUNCH(kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  TCR_LAUNCH(name, kfn, dim3(groups), dim3(kThreads), smem, s, a);
   return 0;
 }
 
 template <int K>
-static int launch_bwd_weight(const BwdWeightArgs& a, int threads, size_t smem, cudaStream_t s) {
+static int launch_bwd_weight(const char* name, const BwdWeightArgs& a, int threads, size_t smem, cudaStream_t s) {
   auto kfn = conv_bwd_weight_kernel<K>;
 #ifndef TCR_EMU
-  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+  static size_t smem_limit = 48 * 1024;   // per template instantiation
+  if (smem > smem_limit) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+    smem_limit = smem;
+  }
 #endif
-  TCR_LAUNCH(kfn, dim3(a.cout / a.cot, a.R), dim3(threads), smem, s, a);
+  TCR_LAUNCH(name, kfn, dim3(a.cout / a.cot, a.R), dim3(threads), smem, s, a);
   return 0;
 }
 
@@ -380,9 +388,9 @@ static int bwd_weight(tcr_handle* h, ConvPlan& cv, ActSrc x, DySrc dy, int n, cu
   const int threads = ((a.RG * (cv.cin / 2) * (a.cot / 4) + 31) / 32) * 32;
   const size_t smem = bwd_weight_smem(cv, a.cot, a.RG, a.UB);
   switch (cv.k) {
-    case 1: return launch_bwd_weight<1>(a, threads, smem, s);
-    case 3: return launch_bwd_weight<3>(a, threads, smem, s);
-    case 9: return launch_bwd_weight<9>(a, threads, smem, s);
+    case 1: return launch_bwd_weight<1>(("dw:" + cv.name).c_str(), a, threads, smem, s);
+    case 3: return launch_bwd_weight<3>(("dw:" + cv.name).c_str(), a, threads, smem, s);
+    case 9: return launch_bwd_weight<9>(("dw:" + cv.name).c_str(), a, threads, smem, s);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }
@@ -400,8 +408,8 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   const int groups = (n + U - 1) / U;
   const size_t smem = bwd_data_smem(cv, dn, U, KS);
   switch (cv.k) {
-    case 3: return launch_bwd_data<3>(a, groups, smem, s);
-    case 9: return launch_bwd_data<9>(a, groups, smem, s);
+    case 3: return launch_bwd_data<3>(("dx:" + cv.name).c_str(), a, groups, smem, s);
+    case 9: return launch_bwd_data<9>(("dx:" + cv.name).c_str(), a, groups, smem, s);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }

@@ -446,12 +446,16 @@ int net_alloc_workspace(tcr_handle* h) {
 }
 
 template <int K>
-static int launch_conv_fwd(const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
+static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
   auto kfn = conv_fwd_kernel<K>;
 #ifndef TCR_EMU
-  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+  static size_t smem_limit = 48 * 1024;   // per template instantiation
+  if (smem > smem_limit) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+    smem_limit = smem;
+  }
 #endif
-  TCR_LAUNCH(kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  TCR_LAUNCH(name, kfn, dim3(groups), dim3(kThreads), smem, s, a);
   return 0;
 }
 
@@ -475,9 +479,9 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   const int groups = (n + U - 1) / U;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS);
   switch (cv.k) {
-    case 3: return launch_conv_fwd<3>(a, groups, smem, s);
-    case 9: return launch_conv_fwd<9>(a, groups, smem, s);
-    case 1: return launch_conv_fwd<1>(a, groups, smem, s);
+    case 3: return launch_conv_fwd<3>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
+    case 9: return launch_conv_fwd<9>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
+    case 1: return launch_conv_fwd<1>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }
@@ -496,7 +500,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       e.c[l] = cv.cout; e.gamma_off[l] = cv.gamma_off; e.beta_off[l] = cv.beta_off;
       e.mm_off[l] = cv.mm_off; e.mv_off[l] = cv.mv_off; e.bnf[l] = cv.bnf;
     }
-    TCR_LAUNCH(bn_table_eval_kernel, dim3(e.nlayers), dim3(128), 0, s, e);
+    TCR_LAUNCH("bn_table_eval", bn_table_eval_kernel, dim3(e.nlayers), dim3(128), 0, s, e);
   }
   int slot = 0;
   // conv0 on raw features
@@ -564,7 +568,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       const size_t smem = (size_t)(kHeadWarps * 4 * lb.c + kHeadWarps * lb.c + kHeadWarps * ha.classes + kHeadWarps) * 4;
-      TCR_LAUNCH(head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+      TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next
     // block's first kernel, so `prev` is updated at the top of the next iteration.

@@ -161,7 +161,7 @@ static int fc_segment(const tcr_handle* h) { return (int)h->convs.size() * 3; }
 int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   const int blocks = (int)((h->n_train + kOptThreads - 1) / kOptThreads);
   if (blocks > 4096) { set_error("parameter count too large for the l2 partial buffer"); return TCR_ERR_UNSUPPORTED; }
-  TCR_LAUNCH(grad_finalize_kernel, dim3(blocks), dim3(kOptThreads), 0, s, h->d_segs, h->n_segs, h->n_train, fc_segment(h),
+  TCR_LAUNCH("grad_finalize", grad_finalize_kernel, dim3(blocks), dim3(kOptThreads), 0, s, h->d_segs, h->n_segs, h->n_train, fc_segment(h),
              h->d_dwfc_part, head_groups(a->n), a->params, a->weight_decay, h->d_grads, h->d_l2part);
   if (h->comm && h->world > 1) {
     int rc = comm_allreduce_sum(h, h->d_grads, h->n_train, s);
@@ -177,12 +177,12 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   u.l2part = h->d_l2part; u.l2blocks = blocks;
   u.ce_sum = h->d_loss; u.inv_n = 1.0f / (float)a->n;
   u.losses = a->losses; u.grads_out = a->grads; u.apply = a->apply_update ? 1 : 0;
-  TCR_LAUNCH(update_kernel, dim3(blocks), dim3(kOptThreads), 0, s, u);
+  TCR_LAUNCH("update", update_kernel, dim3(blocks), dim3(kOptThreads), 0, s, u);
   return 0;
 }
 
 int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int n, float* losses, cudaStream_t s) {
-  TCR_LAUNCH(loss_only_kernel, dim3(1), dim3(1024), 0, s, h->d_segs, h->n_segs, params, weight_decay, h->d_loss,
+  TCR_LAUNCH("loss_only", loss_only_kernel, dim3(1), dim3(1024), 0, s, h->d_segs, h->n_segs, params, weight_decay, h->d_loss,
              1.0f / (float)n, losses);
   return 0;
 }

@@ -149,6 +149,6 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 
-#define TCR_LAUNCH(kernel, grid, block, smem, stream, ...) \
+#define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().dyn_smem

@@ -1,0 +1,49 @@
+"""Kernel LOGIC parity on a CPU box: the product kernel sources compiled against the test-only fiber
+emulator (tests/emu) and driven through the same C ABI, compared with the fp64 oracle.  Sizes are tiny; the real
+parity tests are the -m gpu ones (tests/test_gpu_parity.py) that run the sm_100a build."""
+import numpy as np
+import pytest
+
+from parity_cases import run_case
+from tcr_harness import Engine, NumpyBackend, rel_err
+from oracle import tcr_oracle as O
+
+
+@pytest.fixture(scope="module")
+def backend():
+    return NumpyBackend()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=5, keep=1.0),
+    dict(model="TCResNet14", wm=1.5, window=640, stride=320, n=3, keep=0.5),
+    dict(model="TCResNet8", wm=1.0, window=480, stride=160, n=3, keep=0.5, ls=0.1),
+    dict(model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False),
+    dict(model="TCResNet8", wm=1.5, window=640, stride=320, n=1, steps=2),
+], ids=["r8-T49", "r14x1.5-T49-dropout", "r8-T98-smoothing", "r14-T98-features", "r8x1.5-n1-2steps"])
+def test_emulated_kernels_match_oracle(backend, kw):
+    report = run_case(backend, **kw)
+    assert report["features"] < 1e-6
+
+
+def test_log_mel_front_end(backend):
+    eng = Engine(backend, feature_kind=1, max_batch=4)
+    wav, _ = O.synthetic_batch(2, adversarial=True)
+    got = eng.mfcc(wav)
+    ref = O.log_mel_spectrogram(wav, 640, 320, magnitude_squared=False)
+    assert got.shape == (2, 49, 64)
+    assert rel_err(got, ref) < 2e-5      # log of tiny magnitudes (square wave): fp32 FFT round-off
+    eng.close()
+
+
+def test_unsupported_width_is_an_error(backend):
+    with pytest.raises(Exception, match="multiple of 4"):
+        Engine(backend, width_multiplier=1.3)
+
+
+def test_batch_larger_than_workspace_is_an_error(backend):
+    eng = Engine(backend, max_batch=2)
+    wav, _ = O.synthetic_batch(3)
+    with pytest.raises(Exception, match="max_batch"):
+        eng.mfcc(wav)
+    eng.close()

@@ -1,0 +1,110 @@
+"""Parity tests proper: the sm_100a CUDA path through the C ABI vs the fp64 oracle, on a real B200."""
+import numpy as np
+import pytest
+
+from parity_cases import run_case, perturbed_variables
+from tcr_harness import Engine, rel_err
+from oracle import tcr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend():
+    from tcr_harness import TorchBackend
+    return TorchBackend()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=1),                      # config 1 (plumbing)
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=3, keep=0.5),            # eval-script batch size
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=39, keep=0.5, steps=2),  # test-script batch size
+    dict(model="TCResNet8", wm=1.0, window=480, stride=160, n=37, keep=0.5, ls=0.1),   # script shape T=98, pad (3,4)
+    dict(model="TCResNet14", wm=1.5, window=640, stride=320, n=21, keep=0.5),
+    dict(model="TCResNet14", wm=1.0, window=480, stride=160, n=16, use_wav=False, steps=3),
+    dict(model="TCResNet8", wm=1.5, window=640, stride=320, n=150, check_f32_floor=True),
+], ids=["r8-n1", "r8-n3", "r8-n39-2steps", "r8-T98-n37", "r14x1.5-n21", "r14-T98-3steps", "r8x1.5-n150"])
+def test_cuda_path_matches_oracle(backend, kw):
+    run_case(backend, **kw)
+
+
+def test_full_size_config2_tcresnet8_n512(backend):
+    report = run_case(backend, model="TCResNet8", wm=1.0, n=512, keep=0.5, max_batch=512, check_f32_floor=True)
+    print(report)
+
+
+def test_full_size_config3_tcresnet14x15_n1024(backend):
+    report = run_case(backend, model="TCResNet14", wm=1.5, n=1024, keep=0.5, max_batch=1024, check_f32_floor=True)
+    print(report)
+
+
+def test_launch_counter_proves_the_cuda_path_ran(backend):
+    import ctypes as C
+    before, after = C.c_uint64(), C.c_uint64()
+    backend.lib.tcr_launch_count(C.byref(before))
+    run_case(backend, n=4)
+    backend.lib.tcr_launch_count(C.byref(after))
+    assert after.value - before.value >= 40      # mfcc + eval forward + one full training step
+
+
+def test_training_step_is_bitwise_deterministic(backend):
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    params, moving = perturbed_variables(spec)
+    wav, onehot = O.synthetic_batch(300)
+    eng = Engine(backend, max_batch=300, dropout_keep_prob=0.5)
+    pf, mf = O.flatten_vars(spec, params), O.flatten_moving(spec, moving)
+    sf = np.zeros_like(pf)
+    a = eng.train_step(wav, onehot, pf, sf, mf, seed=11)
+    b = eng.train_step(wav, onehot, pf, sf, mf, seed=11)
+    for k in ("logits", "grads", "params", "moving", "losses"):
+        assert np.array_equal(a[k], b[k]), k
+    c = eng.train_step(wav, onehot, pf, sf, mf, seed=12)     # a different dropout seed changes the step
+    assert not np.array_equal(a["grads"], c["grads"])
+    eng.close()
+
+
+def test_eval_forward_is_per_utterance(backend):
+    """No cross-utterance coupling in the evaluate_audio.py path: permuting / slicing the batch permutes logits."""
+    spec = O.build_spec("TCResNet14", 1.0, 49)
+    params, moving = perturbed_variables(spec)
+    wav, _ = O.synthetic_batch(64, adversarial=True)
+    eng = Engine(backend, model=14, max_batch=64)
+    pf, mf = O.flatten_vars(spec, params), O.flatten_moving(spec, moving)
+    full = eng.forward(wav, pf, mf)["logits"]
+    perm = np.random.RandomState(0).permutation(64)
+    np.testing.assert_array_equal(eng.forward(wav[perm], pf, mf)["logits"], full[perm])
+    np.testing.assert_array_equal(eng.forward(wav[5:8], pf, mf)["logits"], full[5:8])
+    eng.close()
+
+
+def test_gradient_is_linear_in_the_shards(backend):
+    """Data-parallel identity used by the multi-GPU path: with BN statistics computed per shard, the mean of the
+    per-shard gradients of (CE) equals what N ranks all-reduce; checked against the oracle shard-wise."""
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    params, moving = perturbed_variables(spec)
+    wav, onehot = O.synthetic_batch(64)
+    feat = O.mfcc(wav, 640, 320)
+    eng = Engine(backend, max_batch=64, dropout_keep_prob=1.0)
+    pf, mf = O.flatten_vars(spec, params), O.flatten_moving(spec, moving)
+    sf = np.zeros_like(pf)
+    acc = np.zeros_like(pf, dtype=np.float64)
+    ref = np.zeros_like(pf, dtype=np.float64)
+    for r in range(2):
+        sl = slice(32 * r, 32 * (r + 1))
+        acc += eng.train_step(wav[sl], onehot[sl], pf, sf, mf, apply_update=False)["grads"]
+        logits, cache = O.forward(spec, params, moving, feat[sl], True)
+        ref += O.flatten_vars(spec, O.backward(spec, params, cache, logits, onehot[sl], 1e-3), np.float64)
+    assert rel_err(acc / 2, ref / 2) < 1e-4
+    eng.close()
+
+
+def test_silent_batch_and_full_scale(backend):
+    """Adversarial inputs of SURVEY 8(d): an all-silent clip gives log(1e-6) in every mel bin; +-1 square wave."""
+    eng = Engine(backend, max_batch=4)
+    wav = np.zeros((2, 16000), np.float32)
+    wav[1] = np.where((np.arange(16000) // 40) % 2 == 0, 1.0, -1.0)
+    got = eng.mfcc(wav)
+    ref = O.mfcc(wav, 640, 320)
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < 2e-5
+    eng.close()

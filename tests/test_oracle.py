@@ -219,3 +219,25 @@ def test_flat_roundtrip():
     back = O.unflatten_moving(spec, fm, np.float32)
     for k in moving:
         np.testing.assert_array_equal(moving[k], back[k])
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+    """The PyTorch-CPU port bench.py times as the CPU baseline is the same arithmetic as the NumPy oracle."""
+    from oracle.torch_port import TorchPort
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    params, moving = O.init_variables(spec, 0)
+    wav, onehot = O.synthetic_batch(6)
+    rng = np.random.RandomState(2)
+    mask = (rng.rand(6, spec.c_last) < 0.5).astype(np.float64)
+    port = TorchPort(spec, params, moving, 640, 320, keep_prob=0.5, dtype=torch.float64)
+    feat = O.mfcc(wav, 640, 320)
+    np.testing.assert_allclose(port.mfcc(torch.tensor(wav, dtype=torch.float64)).numpy(), feat, rtol=1e-7, atol=1e-7)
+    slots = O.zeros_like_vars(spec)
+    p1, mv1, s1, ref = O.train_step(spec, params, moving, slots, feat, onehot, 0.1, 0.9, 1e-3, 0.5, mask)
+    total, ce, logits = port.train_step(torch.tensor(wav, dtype=torch.float64), torch.tensor(onehot, dtype=torch.float64),
+                                        0.1, 0.9, 1e-3, torch.tensor(mask))
+    assert abs(total - ref["total_loss"]) < 1e-9 and abs(ce - ref["model_loss"]) < 1e-9
+    for k in p1:
+        np.testing.assert_allclose(port.p[k].detach().numpy(), p1[k], rtol=1e-7, atol=1e-9, err_msg=k)
+    for k in mv1:
+        np.testing.assert_allclose(port.mv[k].numpy(), mv1[k], rtol=1e-7, atol=1e-9, err_msg=k)
