@@ -78,32 +78,35 @@ def run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=4, ke
         assert abs(ev["losses"][0] - ref_total) <= 1e-4 * abs(ref_total) + 1e-6
         assert abs(ev["losses"][1] - ref_model) <= 1e-4 * abs(ref_model) + 1e-6
 
-        # training steps
-        p, mv, sl = params, moving, slots
+        # training steps.  Each step is compared against the oracle started from the CUDA path's OWN previous state
+        # (re-synchronised), so the check is per-step parity + correct carrying of state between calls, not the
+        # divergence of two chaotic lr=0.1 trajectories (ReLU masks flip under 1e-6 perturbations).
         pf_c, mf_c, sf_c = pf, mf, sf
         for step in range(steps):
-            ts = eng.train_step(inp, onehot, pf_c, sf_c, mf_c, lr, mom, wd, is_features=not use_wav, mask_np=mask)
-            p, mv, sl, ref = O.train_step(spec, p, mv, sl, feat, onehot, lr, mom, wd, keep, mask, ls)
+            p = O.unflatten_vars(spec, pf_c)
+            mv = O.unflatten_moving(spec, mf_c)
+            sl = O.unflatten_vars(spec, sf_c)
+            ts = eng.train_step(inp, onehot, pf_c, sf_c, mf_c, lr, mom, wd, is_features=not use_wav, mask_np=mask, seed=step)
+            p1, mv1, sl1, ref = O.train_step(spec, p, mv, sl, feat, onehot, lr, mom, wd, keep, mask, ls)
             pf_c, mf_c, sf_c = ts["params"], ts["moving"], ts["slots"]
             report[f"train_logits{step}"] = rel_err(ts["logits"], ref["logits"])
             report[f"grads{step}"] = rel_err(ts["grads"], O.flatten_vars(spec, ref["grads"], np.float64))
-            report[f"params{step}"] = rel_err(ts["params"], O.flatten_vars(spec, p, np.float64))
-            report[f"slots{step}"] = rel_err(ts["slots"], O.flatten_vars(spec, sl, np.float64))
-            report[f"moving{step}"] = rel_err(ts["moving"], O.flatten_moving(spec, mv, np.float64))
-            scale = 1.0 + step        # drift of the compared trajectories grows with the step count
+            report[f"params{step}"] = rel_err(ts["params"], O.flatten_vars(spec, p1, np.float64))
+            report[f"slots{step}"] = rel_err(ts["slots"], O.flatten_vars(spec, sl1, np.float64))
+            report[f"moving{step}"] = rel_err(ts["moving"], O.flatten_moving(spec, mv1, np.float64))
             floor = 0.0
             if check_f32_floor and step == 0:
-                p32, mv32, sl32 = (O.cast_vars(d, np.float32) for d in (params, moving, slots))
+                p32, mv32, sl32 = (O.cast_vars(d, np.float32) for d in (p, mv, sl))
                 _, _, _, r32 = O.train_step(spec, p32, mv32, sl32, feat.astype(np.float32), onehot, lr, mom, wd, keep, mask, ls)
                 floor = 4 * rel_err(O.flatten_vars(spec, r32["grads"], np.float64), O.flatten_vars(spec, ref["grads"], np.float64))
                 report["grads_f32_oracle_floor"] = floor / 4
-            assert report[f"train_logits{step}"] <= TOL_LOGITS * scale, report
-            assert report[f"grads{step}"] <= max(TOL_STATE, floor) * scale, report
-            assert report[f"params{step}"] <= TOL_STATE * scale, report
-            assert report[f"slots{step}"] <= max(TOL_STATE, floor) * scale, report
-            assert report[f"moving{step}"] <= TOL_STATE * scale, report
-            assert abs(ts["losses"][0] - ref["total_loss"]) <= 1e-4 * abs(ref["total_loss"]) * scale + 1e-6
-            assert abs(ts["losses"][1] - ref["model_loss"]) <= 1e-4 * abs(ref["model_loss"]) * scale + 1e-6
+            assert report[f"train_logits{step}"] <= TOL_LOGITS, report
+            assert report[f"grads{step}"] <= max(TOL_STATE, floor), report
+            assert report[f"params{step}"] <= TOL_STATE, report
+            assert report[f"slots{step}"] <= max(TOL_STATE, floor), report
+            assert report[f"moving{step}"] <= TOL_STATE, report
+            assert abs(ts["losses"][0] - ref["total_loss"]) <= 1e-4 * abs(ref["total_loss"]) + 1e-6
+            assert abs(ts["losses"][1] - ref["model_loss"]) <= 1e-4 * abs(ref["model_loss"]) + 1e-6
         return report
     finally:
         eng.close()
