@@ -71,39 +71,75 @@ __device__ __forceinline__ bool last_block_done(unsigned* counter, unsigned nblo
   return s_last != 0;
 }
 
-// Chan et al. combination of per-group (mean, M2) partials into the BN table (fp64, fixed order).
+// Chan et al. combination of per-group (mean, M2) partials into the BN table (fp64, fixed order), spread over
+// the whole CTA: thread (seg, c) owns every ns-th group of channel c, so each thread issues a handful of
+// independent loads instead of one thread walking all groups (that serial chain was a 20-30 us kernel tail).
+// Requires C <= blockDim.x <= 512.
 __device__ __forceinline__ void bn_finalize(const BnFinalize& f, int groups, int U, int n, int t_out, float eps) {
-  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
-    double sum = 0.0;
-    for (int g = 0; g < groups; ++g) {
-      const double cnt = (double)(imin(U, n - g * U) * t_out);
-      sum += cnt * (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2);
-    }
-    const double m_total = (double)n * t_out;
-    const double mean = sum / m_total;
-    double m2 = 0.0;
-    for (int g = 0; g < groups; ++g) {
-      const double cnt = (double)(imin(U, n - g * U) * t_out);
-      const double d = (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2) - mean;
-      m2 += (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) + cnt * d * d;
-    }
-    const double var = m2 / m_total;
-    const double rstd = 1.0 / sqrt(var + (double)eps);
-    f.bnf[c] = (float)mean;
-    f.bnf[f.c + c] = (float)rstd;
-    f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
-    f.bnf[3 * f.c + c] = f.beta[c];
-    f.var[c] = (float)var;
+  __shared__ double s_part[512];
+  __shared__ double s_mean[128];
+  const int tid = threadIdx.x, C = f.c;
+  const int ns = imax(1, (int)blockDim.x / C);
+  const int seg = tid / C, c = tid - seg * C;
+  const bool act = seg < ns;
+  const double m_total = (double)n * t_out;
+  double s = 0.0;
+  if (act)
+    for (int g = seg; g < groups; g += ns)
+      s += (double)(imin(U, n - g * U) * t_out) * (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2);
+  if (act) s_part[seg * C + c] = s;
+  __syncthreads();
+  if (tid < C) {
+    double tot = 0.0;
+    for (int q = 0; q < ns; ++q) tot += s_part[q * C + tid];
+    s_mean[tid] = tot / m_total;
   }
+  __syncthreads();
+  double m2 = 0.0;
+  if (act) {
+    const double mean = s_mean[c];
+    for (int g = seg; g < groups; g += ns) {
+      const double cnt = (double)(imin(U, n - g * U) * t_out);
+      const double d = (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2) - mean;
+      m2 += (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2 + 1) + cnt * d * d;
+    }
+    s_part[seg * C + c] = m2;
+  }
+  __syncthreads();
+  if (tid < C) {
+    double tot = 0.0;
+    for (int q = 0; q < ns; ++q) tot += s_part[q * C + tid];
+    const double var = tot / m_total;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    f.bnf[tid] = (float)s_mean[tid];
+    f.bnf[C + tid] = (float)rstd;
+    f.bnf[2 * C + tid] = (float)((double)f.gamma[tid] * rstd);
+    f.bnf[3 * C + tid] = f.beta[tid];
+    f.var[tid] = (float)var;
+  }
+  __syncthreads();
 }
 
+// Sum of per-group (sum dz, sum dz*xhat) partials, same thread layout (2C columns).
 __device__ __forceinline__ void bwdsum_finalize(const BwdSumFinalize& f, int groups) {
-  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
-    const int q = i / f.c, c = i - q * f.c;
+  __shared__ double s_part[512];
+  const int tid = threadIdx.x, C2 = 2 * f.c;
+  const int ns = imax(1, (int)blockDim.x / C2);
+  const int seg = tid / C2, i = tid - seg * C2;
+  const bool act = seg < ns;
+  if (act) {
+    const int c = i >> 1, q = i & 1;
     double s = 0.0;
-    for (int g = 0; g < groups; ++g) s += (double)__ldcg(f.bpart + ((size_t)g * f.c + c) * 2 + q);
-    f.bsum[q * f.c + c] = (float)s;
+    for (int g = seg; g < groups; g += ns) s += (double)__ldcg(f.bpart + ((size_t)g * f.c + c) * 2 + q);
+    s_part[seg * C2 + i] = s;
   }
+  __syncthreads();
+  if (tid < C2) {
+    double tot = 0.0;
+    for (int q = 0; q < ns; ++q) tot += s_part[q * C2 + tid];
+    f.bsum[(tid & 1) * f.c + (tid >> 1)] = (float)tot;
+  }
+  __syncthreads();
 }
 
 // Per-channel (mean, M2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}].

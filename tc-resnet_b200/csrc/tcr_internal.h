@@ -55,6 +55,7 @@ struct FwdArgs {
   // main conv
   const float* w; float* y; float* fpart;
   int cout, stride, t_out, pad_left, KS;
+  int w_smem;               // 1: filter bank(s) staged in shared memory by one TMA bulk copy
   // optional down conv (k=1, stride 2, no padding, same t_out)
   const float* wd; float* yd; float* fpartd; int coutd;
   // training statistics
@@ -100,6 +101,7 @@ struct DySrc {              // dy = scale * (dz - s1/M - xhat * s2/M), dz option
 
 struct BwdDataArgs {
   int n, U;
+  int w_smem;               // 1: filter bank(s) staged in shared memory by one TMA bulk copy
   // conv whose input gradient we compute
   DySrc dy; const float* w; int cin, cout, k, stride, t_in, t_out, pad_left, KS;
   // optional down conv sharing the same input (k=1, stride 2)
@@ -127,6 +129,17 @@ struct BwdWeightArgs {
   int R;                    // row chunks (gridDim.y)
   int UB;                   // utterances staged in shared memory at a time
   float* dwpart;            // [R][k*cin*cout]
+};
+
+constexpr int kDwThreads = 256;
+struct DwLayer {            // one row per conv layer of the grouped weight-gradient launch (static per handle)
+  const float* x_data;      // conv input activation; nullptr = the features pointer passed per call
+  const float* x_bnf; int x_kind;
+  const float* dz; const float* y; const float* bnf; const float* bsum; int mask_relu;
+  int cin, cout, k, stride, t_in, t_out, pad_left;
+  int cot, RG, R, UB;
+  float* dwpart;
+  int cta_begin;            // first virtual CTA of this layer
 };
 
 // ---------------- optimizer ----------------

@@ -121,7 +121,7 @@ __device__ __forceinline__ void fft_warp(float2* z, const float2* __restrict__ t
 //   tw    : NF2 float2              FFT twiddles exp(-2 pi i n / NF2)
 //   per warp: z   (NF2 + NF2/16) float2, pw (NF2 + 1 [+pad]) floats, lm (mel_bins) floats
 template <int NF2>
-__global__ void __launch_bounds__(512) mfcc_kernel(MfccArgs a) {
+__global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   TCR_DYNAMIC_SMEM(smem);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

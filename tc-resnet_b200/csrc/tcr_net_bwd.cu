@@ -42,7 +42,22 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   const int TPd = PLd + a.t_out + PRd;
   const int COSD = a.has_down ? chan_stride(a.coutd) : 0;
   const int Rin_max = a.U * a.t_in;
-  float* dys = smem;                                                 // [U][TPd][COS]
+  // shared memory: [mbarrier | W | W_down | dy tile | dy_down tile | dx planes | scratch]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* ws = smem + 4;
+  const int wn = a.w_smem ? K * a.cin * a.cout : 0;
+  const int wdn = (a.w_smem && a.has_down) ? a.cin * a.coutd : 0;
+  float* wsd = ws + wn;
+  if (a.w_smem) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, (uint32_t)(wn + wdn) * 4u);
+      tma_load_1d(ws, a.w, (uint32_t)wn * 4u, bar);
+      if (wdn) tma_load_1d(wsd, a.wd, (uint32_t)wdn * 4u, bar);
+    }
+  }
+  float* dys = wsd + wdn;                                            // [U][TPd][COS]
   float* dysd = dys + (size_t)a.U * TPd * COS;                       // [U][t_out][COSD]
   float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
   float* red = dxs + (size_t)a.KS * Rin_max * a.cin;                 // [4][nseg][cin]
@@ -69,6 +84,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       }
     }
   }
+  if (a.w_smem) mbar_wait(bar, 0);
   __syncthreads();
 
   // ---- transposed conv, one parity class of input rows at a time ----
@@ -107,9 +123,15 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     const int NT = (K - p + S - 1) / S;
     const int m_lo = ks * MPS, m_hi = imin(NT, m_lo + MPS);
     for (int m = m_lo; m < m_hi; ++m) {
-      const float* wk = a.w + ((size_t)(p + S * m) * a.cin + 4 * cig) * a.cout;
+      const float* wk = (a.w_smem ? ws : a.w) + ((size_t)(p + S * m) * a.cin + 4 * cig) * a.cout;
+#pragma unroll 2
       for (int co = 0; co < a.cout; co += 4) {
-        const float4 w0 = ldg4(wk + co), w1 = ldg4(wk + a.cout + co), w2 = ldg4(wk + 2 * a.cout + co), w3 = ldg4(wk + 3 * a.cout + co);
+        float4 w0, w1, w2, w3;
+        if (a.w_smem) {
+          w0 = ld4(wk + co); w1 = ld4(wk + a.cout + co); w2 = ld4(wk + 2 * a.cout + co); w3 = ld4(wk + 3 * a.cout + co);
+        } else {
+          w0 = ldg4(wk + co); w1 = ldg4(wk + a.cout + co); w2 = ldg4(wk + 2 * a.cout + co); w3 = ldg4(wk + 3 * a.cout + co);
+        }
 #pragma unroll
         for (int i = 0; i < TMB; ++i) {
           const float4 d = ld4(dyr[i] - m * COS + co);
@@ -118,9 +140,14 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       }
     }
     if (a.has_down && ks == 0 && (t0[p] & 1) == 0) {     // 1x1 stride-2 shortcut conv touches even input rows only
-      const float* wk = a.wd + (size_t)(4 * cig) * a.coutd;
+      const float* wk = (a.w_smem ? wsd : a.wd) + (size_t)(4 * cig) * a.coutd;
       for (int co = 0; co < a.coutd; co += 4) {
-        const float4 w0 = ldg4(wk + co), w1 = ldg4(wk + a.coutd + co), w2 = ldg4(wk + 2 * a.coutd + co), w3 = ldg4(wk + 3 * a.coutd + co);
+        float4 w0, w1, w2, w3;
+        if (a.w_smem) {
+          w0 = ld4(wk + co); w1 = ld4(wk + a.coutd + co); w2 = ld4(wk + 2 * a.coutd + co); w3 = ld4(wk + 3 * a.coutd + co);
+        } else {
+          w0 = ldg4(wk + co); w1 = ldg4(wk + a.coutd + co); w2 = ldg4(wk + 2 * a.coutd + co); w3 = ldg4(wk + 3 * a.coutd + co);
+        }
 #pragma unroll
         for (int i = 0; i < TMB; ++i) {
           const float4 d = ld4(dysd + (size_t)(u * a.t_out + (tt[i] >> 1)) * COSD + co);
@@ -185,13 +212,11 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
 // backward weight
 // ------------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(512) conv_bwd_weight_kernel(BwdWeightArgs a) {
-  TCR_DYNAMIC_SMEM(smem_raw);
-  float* smem = reinterpret_cast<float*>(smem_raw);
+__device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, float* smem) {
   const int tid = threadIdx.x;
-  const int cot0 = blockIdx.x * a.cot;
+  const int cot0 = bx * a.cot;
   const int upc = (a.n + a.R - 1) / a.R;                       // utterances per row chunk
-  const int ubeg = blockIdx.y * upc, uend = imin(a.n, ubeg + upc);
+  const int ubeg = by * upc, uend = imin(a.n, ubeg + upc);
   const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
   const int TP = a.pad_left + a.t_in + pad_right;
   const int CI2 = a.cin >> 1;
@@ -263,7 +288,7 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_kernel(BwdWeightArgs a) {
         acc[k][1] = add4(acc[k][1], ld4(sc + k * 8 + 4));
       }
     }
-    float* out = a.dwpart + (size_t)blockIdx.y * K * a.cin * a.cout;
+    float* out = a.dwpart + (size_t)by * K * a.cin * a.cout;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       st4(out + ((size_t)k * a.cin + 2 * ci2) * a.cout + cot0 + 4 * co4, acc[k][0]);
@@ -272,13 +297,36 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_kernel(BwdWeightArgs a) {
   }
 }
 
+// All layers' weight gradients in ONE launch: virtual CTA -> (layer, output-channel tile, row chunk) through a
+// static table, so ~600 CTAs of 256 threads keep every SM busy instead of ten serial 64-CTA launches.
+__global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
+                                                                const float* __restrict__ feat) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  int l = 0;
+  while (l + 1 < nlayers && (int)blockIdx.x >= layers[l + 1].cta_begin) ++l;
+  const DwLayer L = layers[l];
+  const int local = (int)blockIdx.x - L.cta_begin;
+  const int ncot = L.cout / L.cot;
+  BwdWeightArgs a;
+  a.n = n;
+  a.x = ActSrc{L.x_data ? L.x_data : feat, L.x_bnf, L.x_kind};
+  a.dy = DySrc{L.dz, L.y, L.bnf, L.bsum, L.mask_relu, 1.0f / ((float)n * (float)L.t_out)};
+  a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.stride = L.stride; a.t_in = L.t_in; a.t_out = L.t_out;
+  a.pad_left = L.pad_left; a.cot = L.cot; a.RG = L.RG; a.R = L.R; a.UB = L.UB; a.dwpart = L.dwpart;
+  const int bx = local % ncot, by = local / ncot;
+  if (L.k == 9) dw_body<9>(a, bx, by, smem);
+  else if (L.k == 3) dw_body<3>(a, bx, by, smem);
+  else dw_body<1>(a, bx, by, smem);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static constexpr size_t kSmemBudget = 100 * 1024;
 static constexpr size_t kSmemBudgetW = 64 * 1024;
 
-static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int KS) {
+static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int KS, bool w_smem) {
   const int S = cv.stride;
   const int PLd = (cv.k - 1) / S;
   const int PRd = std::max(0, (cv.t_in - 1 + cv.pad_left) / S - (cv.t_out - 1));
@@ -287,32 +335,41 @@ static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int K
   const int nseg = std::max(1, kThreads / ncig);
   size_t f = (size_t)U * TPd * chan_stride(cv.cout) + (dn ? (size_t)U * cv.t_out * chan_stride(dn->cout) : 0);
   f += (size_t)KS * U * cv.t_in * cv.cin + (size_t)4 * nseg * cv.cin;
+  f += 4 + (w_smem ? (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0) : 0);
   return f * 4;
 }
 
-static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out) {
-  int U = std::max(1, (n + 147) / 148);
+static constexpr size_t kSmemMax = 200 * 1024;
+
+static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
+  const size_t wbytes = ((size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0)) * 4;
+  int U = std::max(1, (n + 295) / 296);
   U = std::min(U, 16);
   const int S = cv.stride, NT0 = (cv.k + S - 1) / S;
   for (;; --U) {
-    int best_ks = 1;
-    double best_cost = 1e30;
-    for (int KS = 1; KS <= NT0; ++KS) {
-      const int mps = (NT0 + KS - 1) / KS;
-      if ((NT0 + mps - 1) / mps != KS) continue;   // skip slice counts that leave empty slices
-      const int rows = (cv.t_in + TMB - 1) / TMB + (S > 1 ? 1 : 0);
-      const long tasks = (long)KS * U * rows * (cv.cin / 4);
-      const double cost = (double)((tasks + kThreads - 1) / kThreads) * mps;
-      if (cost < best_cost - 1e-9 && bwd_data_smem(cv, dn, U, KS) <= kSmemBudget) {
-        best_cost = cost;
-        best_ks = KS;
+    for (int pass = 0; pass < 3; ++pass) {
+      const bool wsm = pass < 2;
+      const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+      if (wsm && wbytes + 16 * 1024 > budget) continue;
+      int best_ks = 0;
+      double best_cost = 1e30;
+      for (int KS = 1; KS <= NT0; ++KS) {
+        const int mps = (NT0 + KS - 1) / KS;
+        if ((NT0 + mps - 1) / mps != KS) continue;   // skip slice counts that leave empty slices
+        const int rows = (cv.t_in + TMB - 1) / TMB + (S > 1 ? 1 : 0);
+        const long tasks = (long)KS * U * rows * (cv.cin / 4);
+        const double cost = (double)((tasks + kThreads - 1) / kThreads) * mps;
+        if (cost < best_cost - 1e-9 && bwd_data_smem(cv, dn, U, KS, wsm) <= budget) {
+          best_cost = cost;
+          best_ks = KS;
+        }
+      }
+      if (best_ks) {
+        *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0;
+        return;
       }
     }
-    if (best_cost < 1e29 || U == 1) {
-      *U_out = U;
-      *KS_out = best_ks;
-      return;
-    }
+    if (U == 1) { *U_out = 1; *KS_out = 1; *wsm_out = 0; return; }
   }
 }
 
@@ -325,17 +382,25 @@ static size_t bwd_weight_smem(const ConvPlan& cv, int cot, int RG, int UB) {
   return std::max(tiles, scratch);
 }
 
-// Static per-layer choice of (output-channel tile, row groups, row chunks, staged utterances).
+// Static per-layer choice of (output-channel tile, row groups, row chunks, staged utterances) for 256-thread CTAs:
+// the tile that keeps most threads busy, chunks of roughly equal work (~0.7 M MAC) so all layers together give a
+// few waves of CTAs.
 void plan_bwd_weight(tcr_handle* h) {
+  const double target_macs = 0.7e6;
   for (auto& cv : h->convs) {
-    int cot = 4;
-    for (int c = 4; c <= cv.cout; c += 4)
-      if (cv.cout % c == 0 && (cv.cin / 2) * (c / 4) <= 384) cot = c;
+    int cot = 4, best_workers = 0;
+    for (int c = 4; c <= cv.cout; c += 4) {
+      if (cv.cout % c) continue;
+      const int np = (cv.cin / 2) * (c / 4);
+      if (np > kDwThreads) continue;
+      const int workers = (kDwThreads / np) * np;
+      if (workers >= best_workers) { best_workers = workers; cot = c; }
+    }
     const int np = (cv.cin / 2) * (cot / 4);
-    int RG = std::max(1, std::min(8, 256 / np));
-    const int ncot = cv.cout / cot;
-    int R = std::max(1, std::min(64, (148 + ncot - 1) / ncot));
-    R = std::min(R, h->cfg.max_batch);
+    int RG = std::max(1, kDwThreads / np);
+    const double macs_per_utt = (double)cv.t_out * cv.k * cv.cin * cot;
+    int upc = std::max(1, (int)(target_macs / macs_per_utt));          // utterances per chunk
+    int R = std::max(1, std::min(64, (h->cfg.max_batch + upc - 1) / upc));
     int UB = 16;
     while (UB > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudgetW) --UB;
     while (RG > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudget) --RG;
@@ -344,6 +409,47 @@ void plan_bwd_weight(tcr_handle* h) {
     cv.dw_R = R;
     cv.dw_UB = UB;
   }
+}
+
+// Device table of the grouped weight-gradient launch (pointers are workspace addresses: static per handle).
+int build_dw_table(tcr_handle* h) {
+  std::vector<DwLayer> tab;
+  int cta = 0;
+  size_t smem = 0;
+  auto add = [&](ConvPlan& cv, const float* xd, const float* xb, int xk, const float* dz, int mask) {
+    DwLayer L;
+    L.x_data = xd; L.x_bnf = xb; L.x_kind = xk;
+    L.dz = dz; L.y = cv.y; L.bnf = cv.bnf; L.bsum = cv.bsum; L.mask_relu = mask;
+    L.cin = cv.cin; L.cout = cv.cout; L.k = cv.k; L.stride = cv.stride; L.t_in = cv.t_in; L.t_out = cv.t_out;
+    L.pad_left = cv.pad_left; L.cot = cv.dw_cot; L.RG = cv.dw_RG; L.R = cv.dw_R; L.UB = cv.dw_UB;
+    L.dwpart = cv.dwpart;
+    L.cta_begin = cta;
+    cta += (cv.cout / cv.dw_cot) * cv.dw_R;
+    smem = std::max(smem, bwd_weight_smem(cv, cv.dw_cot, cv.dw_RG, cv.dw_UB));
+    tab.push_back(L);
+  };
+  ConvPlan& c0 = h->convs[0];
+  add(c0, nullptr, nullptr, 0, c0.g, 0);                       // x = features (pointer supplied per call)
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    BlockPlan& b = h->blocks[i];
+    ConvPlan& ca = h->convs[b.a];
+    ConvPlan& cb = h->convs[b.b];
+    const float* xd = i == 0 ? c0.y : h->blocks[i - 1].out;
+    const float* xb = i == 0 ? c0.bnf : nullptr;
+    const int xk = i == 0 ? 1 : 0;
+    add(ca, xd, xb, xk, ca.g, 0);
+    if (b.down >= 0) add(h->convs[b.down], xd, xb, xk, b.gblk, 1);
+    add(cb, ca.y, ca.bnf, 1, b.gblk, 0);
+  }
+  h->dw_ctas = cta;
+  h->dw_smem = smem;
+  h->n_dw_layers = (int)tab.size();
+  void* p = nullptr;
+  if (cudaMalloc(&p, tab.size() * sizeof(DwLayer)) != cudaSuccess) return TCR_ERR_CUDA;
+  h->allocs.push_back(p);
+  h->d_dw_layers = (DwLayer*)p;
+  if (cudaMemcpy(p, tab.data(), tab.size() * sizeof(DwLayer), cudaMemcpyHostToDevice) != cudaSuccess) return TCR_ERR_CUDA;
+  return 0;
 }
 
 template <int K>
@@ -360,45 +466,14 @@ static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, s
   return 0;
 }
 
-template <int K>
-static int launch_bwd_weight(const char* name, const BwdWeightArgs& a, int threads, size_t smem, cudaStream_t s) {
-  auto kfn = conv_bwd_weight_kernel<K>;
-#ifndef TCR_EMU
-  static size_t smem_limit = 48 * 1024;   // per template instantiation
-  if (smem > smem_limit) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
-    smem_limit = smem;
-  }
-#endif
-  TCR_LAUNCH(name, kfn, dim3(a.cout / a.cot, a.R), dim3(threads), smem, s, a);
-  return 0;
-}
-
 static DySrc make_dy(const ConvPlan& cv, const float* dz, int mask, int n) {
   return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, 1.0f / ((float)n * (float)cv.t_out)};
 }
 
-static int bwd_weight(tcr_handle* h, ConvPlan& cv, ActSrc x, DySrc dy, int n, cudaStream_t s) {
-  (void)h;
-  BwdWeightArgs a;
-  a.n = n; a.x = x; a.dy = dy;
-  a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride; a.t_in = cv.t_in; a.t_out = cv.t_out;
-  a.pad_left = cv.pad_left; a.cot = cv.dw_cot; a.RG = cv.dw_RG; a.R = cv.dw_R; a.UB = cv.dw_UB;
-  a.dwpart = cv.dwpart;
-  const int threads = ((a.RG * (cv.cin / 2) * (a.cot / 4) + 31) / 32) * 32;
-  const size_t smem = bwd_weight_smem(cv, a.cot, a.RG, a.UB);
-  switch (cv.k) {
-    case 1: return launch_bwd_weight<1>(("dw:" + cv.name).c_str(), a, threads, smem, s);
-    case 3: return launch_bwd_weight<3>(("dw:" + cv.name).c_str(), a, threads, smem, s);
-    case 9: return launch_bwd_weight<9>(("dw:" + cv.name).c_str(), a, threads, smem, s);
-    default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
-  }
-}
-
 static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, int slot, cudaStream_t s) {
-  int U, KS;
-  pick_bwd_tile(cv, dn, n, &U, &KS);
-  a.n = n; a.U = U;
+  int U, KS, wsm;
+  pick_bwd_tile(cv, dn, n, &U, &KS, &wsm);
+  a.n = n; a.U = U; a.w_smem = wsm;
   a.w = params + cv.w_off; a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride;
   a.t_in = cv.t_in; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.has_down = dn ? 1 : 0;
@@ -406,7 +481,7 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.coutd = dn ? dn->cout : 0;
   a.counter = h->d_counters + slot;
   const int groups = (n + U - 1) / U;
-  const size_t smem = bwd_data_smem(cv, dn, U, KS);
+  const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
   switch (cv.k) {
     case 3: return launch_bwd_data<3>(("dx:" + cv.name).c_str(), a, groups, smem, s);
     case 9: return launch_bwd_data<9>(("dx:" + cv.name).c_str(), a, groups, smem, s);
@@ -465,26 +540,17 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       if (rc) return rc;
     }
   }
-  // weight gradients: every layer's inputs are final now
+  // weight gradients: every layer's inputs are final now -> one grouped launch over all layers
   {
-    ConvPlan& c0 = h->convs[0];
-    int rc = bwd_weight(h, c0, ActSrc{feat, nullptr, 0}, make_dy(c0, c0.g, 0, n), n, s);
-    if (rc) return rc;
-  }
-  for (size_t i = 0; i < h->blocks.size(); ++i) {
-    BlockPlan& b = h->blocks[i];
-    ConvPlan& ca = h->convs[b.a];
-    ConvPlan& cb = h->convs[b.b];
-    const ActSrc xin = i == 0 ? ActSrc{h->convs[0].y, h->convs[0].bnf, 1} : ActSrc{h->blocks[i - 1].out, nullptr, 0};
-    int rc = bwd_weight(h, ca, xin, make_dy(ca, ca.g, 0, n), n, s);
-    if (rc) return rc;
-    if (b.down >= 0) {
-      ConvPlan& dn = h->convs[b.down];
-      rc = bwd_weight(h, dn, xin, make_dy(dn, b.gblk, 1, n), n, s);
-      if (rc) return rc;
+    auto kfn = dw_grouped_kernel;
+#ifndef TCR_EMU
+    static size_t smem_limit = 48 * 1024;
+    if (h->dw_smem > smem_limit) {
+      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dw_smem) != cudaSuccess) return TCR_ERR_CUDA;
+      smem_limit = h->dw_smem;
     }
-    rc = bwd_weight(h, cb, ActSrc{ca.y, ca.bnf, 1}, make_dy(cb, b.gblk, 0, n), n, s);
-    if (rc) return rc;
+#endif
+    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat);
   }
   return 0;
 }

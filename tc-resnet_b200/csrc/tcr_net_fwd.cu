@@ -29,11 +29,28 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
   const int TP = a.pad_left + a.t_in + pad_right;
   const int Rmax = a.U * a.t_out;
-  float* xs = smem;                                   // [U][TP][CS]
+  // shared memory: [mbarrier | W (TMA bulk destination) | W_down | x tile | y tiles | scratch]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* ws = smem + 4;                               // [K][cin][cout]   (only when a.w_smem)
+  const int wn = a.w_smem ? K * a.cin * a.cout : 0;
+  const int wdn = (a.w_smem && a.wd) ? a.cin * a.coutd : 0;
+  float* wsd = ws + wn;                               // [cin][coutd]
+  float* xs = wsd + wdn;                              // [U][TP][CS]
   float* ys = xs + (size_t)a.U * TP * CS;             // [KS][Rmax][cout]
   float* ysd = ys + (size_t)a.KS * Rmax * a.cout;     // [Rmax][coutd]
   float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);
   float* smean = red + kThreads;
+
+  // ---- one TMA bulk copy brings the whole filter bank into shared memory while the tile is staged ----
+  if (a.w_smem) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, (uint32_t)(wn + wdn) * 4u);
+      tma_load_1d(ws, a.w, (uint32_t)wn * 4u, bar);
+      if (wdn) tma_load_1d(wsd, a.wd, (uint32_t)wdn * 4u, bar);
+    }
+  }
 
   // ---- stage the input tile (producer's BN/ReLU/residual applied here) ----
   const int c4n = a.cin >> 2;
@@ -57,6 +74,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     }
     st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * c4), v);
   }
+  if (a.w_smem) mbar_wait(bar, 0);
   __syncthreads();
 
   // ---- register-tiled conv: task = (k-slice, row tile of TM, 4 output channels) ----
@@ -86,12 +104,19 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int k_lo = is_down ? 0 : ks * KPS, k_hi = is_down ? 1 : k_lo + KPS;
     const int co_n = is_down ? a.coutd : a.cout;
-    const float* wbase = (is_down ? a.wd : a.w) + 4 * cg;
+    const float* wbase = (a.w_smem ? (is_down ? wsd : ws) : (is_down ? a.wd : a.w)) + 4 * cg;
     for (int k = k_lo; k < k_hi; ++k) {
       const float* wk = wbase + (size_t)k * a.cin * co_n;
+#pragma unroll 2
       for (int ci = 0; ci < a.cin; ci += 4) {
-        const float4 w0 = ldg4(wk + (size_t)(ci + 0) * co_n), w1 = ldg4(wk + (size_t)(ci + 1) * co_n);
-        const float4 w2 = ldg4(wk + (size_t)(ci + 2) * co_n), w3 = ldg4(wk + (size_t)(ci + 3) * co_n);
+        float4 w0, w1, w2, w3;
+        if (a.w_smem) {
+          w0 = ld4(wk + (ci + 0) * co_n); w1 = ld4(wk + (ci + 1) * co_n);
+          w2 = ld4(wk + (ci + 2) * co_n); w3 = ld4(wk + (ci + 3) * co_n);
+        } else {
+          w0 = ldg4(wk + (size_t)(ci + 0) * co_n); w1 = ldg4(wk + (size_t)(ci + 1) * co_n);
+          w2 = ldg4(wk + (size_t)(ci + 2) * co_n); w3 = ldg4(wk + (size_t)(ci + 3) * co_n);
+        }
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           const float4 x = ld4(xr[i] + k * CS + ci);
@@ -349,37 +374,52 @@ static constexpr size_t kSmemBudget = 100 * 1024;   // keeps two CTAs resident p
 
 int head_groups(int n) { return (n + kHeadWarps - 1) / kHeadWarps; }
 
-static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int KS) {
+static size_t fwd_weight_floats(const ConvPlan& cv, const ConvPlan* dn) {
+  return (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0);
+}
+
+static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int KS, bool w_smem) {
   const int CS = chan_stride(cv.cin);
   const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
   const int TP = cv.pad_left + cv.t_in + pad_right;
   size_t f = (size_t)U * TP * CS + (size_t)KS * U * cv.t_out * cv.cout + (dn ? (size_t)U * cv.t_out * dn->cout : 0);
   f += kThreads + std::max(cv.cout, dn ? dn->cout : 0);
+  f += 4 + (w_smem ? fwd_weight_floats(cv, dn) : 0);
   return f * 4;
 }
 
-// Utterances per CTA and k-slices: fill 148 SMs, keep shared memory under budget, balance thread tasks.
-static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out) {
-  int U = std::max(1, (n + 147) / 148);
+// Utterances per CTA, k-slices and whether the filter bank is staged in shared memory.
+// Goals: >= 2 resident CTAs per SM when the batch allows (latency hiding), all 148 SMs busy, balanced thread tasks.
+static constexpr size_t kSmemMax = 200 * 1024;      // opt-in limit we are willing to use for one CTA
+
+static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
+  const size_t wbytes = fwd_weight_floats(cv, dn) * 4;
+  int U = std::max(1, (n + 295) / 296);             // two CTAs per SM worth of groups
   U = std::min(U, 16);
   for (;; --U) {
-    int best_ks = 1;
-    double best_cost = 1e30;
-    for (int KS = 1; KS <= cv.k; ++KS) {
-      if (cv.k % KS) continue;
-      const int nrt = (U * cv.t_out + TM - 1) / TM;
-      const long tasks = (long)nrt * (cv.cout / 4) * KS + (dn ? (long)nrt * (dn->cout / 4) : 0);
-      const double cost = (double)((tasks + kThreads - 1) / kThreads) * (cv.k / KS);
-      if (cost < best_cost - 1e-9 && fwd_smem_bytes(cv, dn, U, KS) <= kSmemBudget) {
-        best_cost = cost;
-        best_ks = KS;
+    for (int pass = 0; pass < 3; ++pass) {
+      // pass 0: weights in smem, two CTAs per SM; pass 1: weights in smem, one CTA per SM; pass 2: weights via L1/L2
+      const bool wsm = pass < 2;
+      const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+      if (wsm && wbytes + 16 * 1024 > budget) continue;
+      int best_ks = 0;
+      double best_cost = 1e30;
+      for (int KS = 1; KS <= cv.k; ++KS) {
+        if (cv.k % KS) continue;
+        const int nrt = (U * cv.t_out + TM - 1) / TM;
+        const long tasks = (long)nrt * (cv.cout / 4) * KS + (dn ? (long)nrt * (dn->cout / 4) : 0);
+        const double cost = (double)((tasks + kThreads - 1) / kThreads) * (cv.k / KS);
+        if (cost < best_cost - 1e-9 && fwd_smem_bytes(cv, dn, U, KS, wsm) <= budget) {
+          best_cost = cost;
+          best_ks = KS;
+        }
+      }
+      if (best_ks) {
+        *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0;
+        return;
       }
     }
-    if (best_cost < 1e29 || U == 1) {
-      *U_out = U;
-      *KS_out = best_ks;
-      return;
-    }
+    if (U == 1) { *U_out = 1; *KS_out = 1; *wsm_out = 0; return; }
   }
 }
 
@@ -405,6 +445,7 @@ static int ws_alloc(tcr_handle* h, T** p, size_t count) {
 
 void plan_bwd_weight(tcr_handle* h);   // tcr_net_bwd.cu
 int build_opt_segments(tcr_handle* h); // tcr_optim.cu
+int build_dw_table(tcr_handle* h);     // tcr_net_bwd.cu
 
 int net_alloc_workspace(tcr_handle* h) {
   const size_t N = (size_t)h->cfg.max_batch;
@@ -442,6 +483,8 @@ int net_alloc_workspace(tcr_handle* h) {
   if (cudaMemset(h->d_counters, 0, 64 * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
   WS(ws_alloc(h, &h->d_hyper, 1));
   if (cudaMallocHost((void**)&h->h_hyper, sizeof(Hyper)) != cudaSuccess) return TCR_ERR_CUDA;
+  int rc = build_dw_table(h);
+  if (rc) return rc;
   return build_opt_segments(h);
 }
 
@@ -461,9 +504,9 @@ static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_
 
 static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const float* params, int n, bool training,
                     int counter_slot, cudaStream_t s) {
-  int U, KS;
-  pick_fwd_tile(cv, dn, n, &U, &KS);
-  a.n = n; a.U = U; a.t_in = cv.t_in; a.cin = cv.cin;
+  int U, KS, wsm;
+  pick_fwd_tile(cv, dn, n, &U, &KS, &wsm);
+  a.n = n; a.U = U; a.t_in = cv.t_in; a.cin = cv.cin; a.w_smem = wsm;
   a.w = params + cv.w_off; a.y = cv.y; a.fpart = cv.fpart;
   a.cout = cv.cout; a.stride = cv.stride; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
@@ -477,7 +520,7 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
     a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->cout};
   }
   const int groups = (n + U - 1) / U;
-  const size_t smem = fwd_smem_bytes(cv, dn, U, KS);
+  const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
   switch (cv.k) {
     case 3: return launch_conv_fwd<3>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
     case 9: return launch_conv_fwd<9>(("fwd:" + cv.name).c_str(), a, groups, smem, s);

@@ -38,8 +38,16 @@ __global__ void __launch_bounds__(kOptThreads) grad_finalize_kernel(const OptSeg
     const float* part = si == fc_seg ? fc_part : sg.part;
     const int R = si == fc_seg ? fc_R : sg.R;
     float g = 0.f;
-    if (part)
-      for (int r = 0; r < R; ++r) g += part[(size_t)r * sg.numel + i];
+    if (part) {                      // 8 independent loads in flight, fixed summation order (deterministic)
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int r = 0;
+      for (; r + 8 <= R; r += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += part[(size_t)(r + j) * sg.numel + i];
+      }
+      for (; r < R; ++r) acc[0] += part[(size_t)r * sg.numel + i];
+      g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    }
     if (sg.decay) {
       const float w = params[p];
       g = fmaf(weight_decay, w, g);
@@ -67,6 +75,7 @@ struct UpdateArgs {
   float* losses;          // may be null
   float* grads_out;       // may be null: scaled gradient actually applied
   int apply;
+  int param_blocks;
 };
 
 __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
@@ -80,27 +89,34 @@ __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
       a.params[p] = a.params[p] - a.lr * m;                // var -= lr * accum
     }
   }
-  if (blockIdx.x == 0) {
+  // extra CTAs past the parameter range: one per BN layer (moving averages) + one for the loss scalars, so no
+  // serial tail hangs off block 0
+  const int extra = (int)blockIdx.x - a.param_blocks;
+  if (extra >= 0 && extra < a.nmsegs) {
     if (a.apply && a.moving) {
-      for (int l = 0; l < a.nmsegs; ++l) {
-        const MovingSegment ms = a.msegs[l];
-        const float m_rows = (float)a.n * (float)ms.t_out;
-        const float unb = m_rows > 1.f ? m_rows / (m_rows - 1.f) : 1.f;
-        for (int c = threadIdx.x; c < ms.c; c += kOptThreads) {
-          float mm = a.moving[ms.mm_off + c], mv = a.moving[ms.mv_off + c];
-          mm -= (mm - ms.bnf[c]) * a.one_minus_decay;      // assign_moving_average, zero_debias=False
-          mv -= (mv - ms.var[c] * unb) * a.one_minus_decay;
-          a.moving[ms.mm_off + c] = mm;
-          a.moving[ms.mv_off + c] = mv;
-        }
+      const MovingSegment ms = a.msegs[extra];
+      const float m_rows = (float)a.n * (float)ms.t_out;
+      const float unb = m_rows > 1.f ? m_rows / (m_rows - 1.f) : 1.f;
+      for (int c = threadIdx.x; c < ms.c; c += kOptThreads) {
+        float mm = a.moving[ms.mm_off + c], mv = a.moving[ms.mv_off + c];
+        mm -= (mm - ms.bnf[c]) * a.one_minus_decay;      // assign_moving_average, zero_debias=False
+        mv -= (mv - ms.var[c] * unb) * a.one_minus_decay;
+        a.moving[ms.mm_off + c] = mm;
+        a.moving[ms.mv_off + c] = mv;
       }
     }
-    if (a.losses && threadIdx.x == 0) {
-      double l2 = 0.0;
-      for (int i = 0; i < a.l2blocks; ++i) l2 += (double)a.l2part[i];
+  } else if (extra == a.nmsegs && a.losses) {
+    __shared__ double s_l2[kOptThreads];
+    double l2 = 0.0;
+    for (int i = threadIdx.x; i < a.l2blocks; i += kOptThreads) l2 += (double)a.l2part[i];
+    s_l2[threadIdx.x] = l2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < kOptThreads; ++i) tot += s_l2[i];
       const float model = *a.ce_sum * a.inv_n;
       a.losses[1] = model;
-      a.losses[0] = model + a.weight_decay * (float)(0.5 * l2);
+      a.losses[0] = model + a.weight_decay * (float)(0.5 * tot);
     }
   }
 }
@@ -177,7 +193,8 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   u.l2part = h->d_l2part; u.l2blocks = blocks;
   u.ce_sum = h->d_loss; u.inv_n = 1.0f / (float)a->n;
   u.losses = a->losses; u.grads_out = a->grads; u.apply = a->apply_update ? 1 : 0;
-  TCR_LAUNCH("update", update_kernel, dim3(blocks), dim3(kOptThreads), 0, s, u);
+  u.param_blocks = blocks;
+  TCR_LAUNCH("update", update_kernel, dim3(blocks + h->n_msegs + 1), dim3(kOptThreads), 0, s, u);
   return 0;
 }
 

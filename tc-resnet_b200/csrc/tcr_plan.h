@@ -61,6 +61,7 @@ struct tcr_handle {
   tcr::Hyper* d_hyper = nullptr; tcr::Hyper* h_hyper = nullptr;
   tcr::OptSegment* d_segs = nullptr; int n_segs = 0;
   tcr::MovingSegment* d_msegs = nullptr; int n_msegs = 0;
+  tcr::DwLayer* d_dw_layers = nullptr; int n_dw_layers = 0; int dw_ctas = 0; size_t dw_smem = 0;
   std::vector<void*> allocs;
   int64_t workspace_bytes = 0;
   // data-parallel
