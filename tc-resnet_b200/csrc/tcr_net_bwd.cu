@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     int tt[TMB];
 #pragma unroll
     for (int i = 0; i < TMB; ++i) {
-      const int j = imin(rt * TMB + i, np[p] - 1);
+      const int j = imin(rt + i * nrt[p], np[p] - 1);   // rows of a task are nrt apart: adjacent lanes -> adjacent rows
       tt[i] = t0[p] + S * j;
       const int b = (tt[i] + a.pad_left - p) / S;
       dyr[i] = dys + (size_t)(u * TPd + PLd + b) * COS;
@@ -123,41 +123,50 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     const int NT = (K - p + S - 1) / S;
     const int m_lo = ks * MPS, m_hi = imin(NT, m_lo + MPS);
     for (int m = m_lo; m < m_hi; ++m) {
-      const float* wk = (a.w_smem ? ws : a.w) + ((size_t)(p + S * m) * a.cin + 4 * cig) * a.cout;
+      // transposed filter bank wT[k][co][ci]: lanes (adjacent cig) read adjacent float4s -> no bank conflicts
+      const float* wk = (a.w_smem ? ws : a.w) + (size_t)(p + S * m) * a.cout * a.cin + 4 * cig;
 #pragma unroll 2
       for (int co = 0; co < a.cout; co += 4) {
-        float4 w0, w1, w2, w3;
+        float4 w0, w1, w2, w3;          // w_j = wT[k][co + j][4cig .. 4cig+3]
         if (a.w_smem) {
-          w0 = ld4(wk + co); w1 = ld4(wk + a.cout + co); w2 = ld4(wk + 2 * a.cout + co); w3 = ld4(wk + 3 * a.cout + co);
+          w0 = ld4(wk + (co + 0) * a.cin); w1 = ld4(wk + (co + 1) * a.cin); w2 = ld4(wk + (co + 2) * a.cin); w3 = ld4(wk + (co + 3) * a.cin);
         } else {
-          w0 = ldg4(wk + co); w1 = ldg4(wk + a.cout + co); w2 = ldg4(wk + 2 * a.cout + co); w3 = ldg4(wk + 3 * a.cout + co);
+          w0 = ldg4(wk + (size_t)(co + 0) * a.cin); w1 = ldg4(wk + (size_t)(co + 1) * a.cin);
+          w2 = ldg4(wk + (size_t)(co + 2) * a.cin); w3 = ldg4(wk + (size_t)(co + 3) * a.cin);
         }
 #pragma unroll
         for (int i = 0; i < TMB; ++i) {
           const float4 d = ld4(dyr[i] - m * COS + co);
-          acc[i].x += dot4(d, w0); acc[i].y += dot4(d, w1); acc[i].z += dot4(d, w2); acc[i].w += dot4(d, w3);
+          acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+          acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+          acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+          acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
         }
       }
     }
     if (a.has_down && ks == 0 && (t0[p] & 1) == 0) {     // 1x1 stride-2 shortcut conv touches even input rows only
-      const float* wk = (a.w_smem ? wsd : a.wd) + (size_t)(4 * cig) * a.coutd;
+      const float* wk = (a.w_smem ? wsd : a.wd) + 4 * cig;          // wdT[co][ci]
       for (int co = 0; co < a.coutd; co += 4) {
         float4 w0, w1, w2, w3;
         if (a.w_smem) {
-          w0 = ld4(wk + co); w1 = ld4(wk + a.coutd + co); w2 = ld4(wk + 2 * a.coutd + co); w3 = ld4(wk + 3 * a.coutd + co);
+          w0 = ld4(wk + (co + 0) * a.cin); w1 = ld4(wk + (co + 1) * a.cin); w2 = ld4(wk + (co + 2) * a.cin); w3 = ld4(wk + (co + 3) * a.cin);
         } else {
-          w0 = ldg4(wk + co); w1 = ldg4(wk + a.coutd + co); w2 = ldg4(wk + 2 * a.coutd + co); w3 = ldg4(wk + 3 * a.coutd + co);
+          w0 = ldg4(wk + (size_t)(co + 0) * a.cin); w1 = ldg4(wk + (size_t)(co + 1) * a.cin);
+          w2 = ldg4(wk + (size_t)(co + 2) * a.cin); w3 = ldg4(wk + (size_t)(co + 3) * a.cin);
         }
 #pragma unroll
         for (int i = 0; i < TMB; ++i) {
           const float4 d = ld4(dysd + (size_t)(u * a.t_out + (tt[i] >> 1)) * COSD + co);
-          acc[i].x += dot4(d, w0); acc[i].y += dot4(d, w1); acc[i].z += dot4(d, w2); acc[i].w += dot4(d, w3);
+          acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+          acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+          acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+          acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
         }
       }
     }
 #pragma unroll
     for (int i = 0; i < TMB; ++i)
-      if (rt * TMB + i < np[p]) st4(dxs + ((size_t)ks * Rin_max + (size_t)u * a.t_in + tt[i]) * a.cin + 4 * cig, acc[i]);
+      if (rt + i * nrt[p] < np[p]) st4(dxs + ((size_t)ks * Rin_max + (size_t)u * a.t_in + tt[i]) * a.cin + 4 * cig, acc[i]);
   }
   __syncthreads();
 
@@ -206,6 +215,24 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     bwdsum_finalize(a.finp, gridDim.x);
     if (nq == 4) bwdsum_finalize(a.finpd, gridDim.x);
   }
+}
+
+// Transposed filter banks wT[k][co][ci] for the backward-data kernels (all conv layers, one launch).  `params`
+// is caller-owned and may change between calls, so the copy is refreshed at the start of every backward pass
+// (65 K - 300 K floats: a few microseconds).
+struct WtLayer { int64_t w_off; float* wT; int k, cin, cout; int64_t begin; };
+struct WtArgs { WtLayer layer[kMaxConvs]; int nlayers; int64_t total; const float* params; };
+__global__ void __launch_bounds__(256) weight_transpose_kernel(WtArgs a) {
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (p >= a.total) return;
+  int l = 0;
+  while (l + 1 < a.nlayers && p >= a.layer[l + 1].begin) ++l;
+  const WtLayer L = a.layer[l];
+  const int64_t i = p - L.begin;                       // index into wT: ((k*cout + co)*cin + ci)
+  const int ci = (int)(i % L.cin);
+  const int co = (int)((i / L.cin) % L.cout);
+  const int k = (int)(i / ((int64_t)L.cin * L.cout));
+  L.wT[i] = a.params[L.w_off + ((int64_t)k * L.cin + ci) * L.cout + co];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -456,7 +483,7 @@ template <int K>
 static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
   auto kfn = conv_bwd_data_kernel<K>;
 #ifndef TCR_EMU
-  static size_t smem_limit = 48 * 1024;   // per template instantiation
+  static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
   if (smem > smem_limit) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
     smem_limit = smem;
@@ -474,10 +501,11 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   int U, KS, wsm;
   pick_bwd_tile(cv, dn, n, &U, &KS, &wsm);
   a.n = n; a.U = U; a.w_smem = wsm;
-  a.w = params + cv.w_off; a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride;
+  (void)params;
+  a.w = cv.wT; a.cin = cv.cin; a.cout = cv.cout; a.k = cv.k; a.stride = cv.stride;
   a.t_in = cv.t_in; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.has_down = dn ? 1 : 0;
-  a.wd = dn ? params + dn->w_off : nullptr;
+  a.wd = dn ? dn->wT : nullptr;
   a.coutd = dn ? dn->cout : 0;
   a.counter = h->d_counters + slot;
   const int groups = (n + U - 1) / U;
@@ -491,6 +519,18 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
 
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s) {
   int slot = 32;
+  {
+    WtArgs w;
+    w.nlayers = 0;
+    w.total = 0;
+    w.params = params;
+    for (auto& cv : h->convs) {
+      if (&cv == &h->convs[0]) continue;               // conv0 needs no input gradient
+      w.layer[w.nlayers++] = WtLayer{cv.w_off, cv.wT, cv.k, cv.cin, cv.cout, w.total};
+      w.total += cv.wnumel();
+    }
+    TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
+  }
   for (int i = (int)h->blocks.size() - 1; i >= 0; --i) {
     BlockPlan& b = h->blocks[i];
     ConvPlan& ca = h->convs[b.a];
@@ -544,7 +584,7 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
   {
     auto kfn = dw_grouped_kernel;
 #ifndef TCR_EMU
-    static size_t smem_limit = 48 * 1024;
+    static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default
     if (h->dw_smem > smem_limit) {
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dw_smem) != cudaSuccess) return TCR_ERR_CUDA;
       smem_limit = h->dw_smem;

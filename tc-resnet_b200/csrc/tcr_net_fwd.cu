@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     const float* xr[TM];
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-      const int r = imin(rt * TM + i, R - 1);
+      const int r = imin(rt + i * NRT, R - 1);      // rows of a task are NRT apart: adjacent lanes -> adjacent rows
       const int u = r / a.t_out, t = r - u * a.t_out;
       xr[i] = is_down ? xs + (size_t)(u * TP + a.pad_left + 2 * t) * CS : xs + (size_t)(u * TP + t * a.stride) * CS;
     }
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     float* dst = is_down ? ysd : ys + (size_t)ks * Rmax * a.cout;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-      const int r = rt * TM + i;
+      const int r = rt + i * NRT;
       if (r < R) st4(dst + (size_t)r * co_n + 4 * cg, acc[i]);
     }
   }
@@ -464,6 +464,7 @@ int net_alloc_workspace(tcr_handle* h) {
     WS(ws_alloc(h, &cv.bpart, (size_t)std::max(h->g_max, h->head_groups_max) * cv.cout * 2));
     WS(ws_alloc(h, &cv.bsum, 2 * (size_t)cv.cout));
     WS(ws_alloc(h, &cv.dwpart, (size_t)cv.dw_R * cv.wnumel()));
+    WS(ws_alloc(h, &cv.wT, (size_t)cv.wnumel()));
   }
   WS(ws_alloc(h, &h->convs[0].g, N * h->convs[0].t_out * h->convs[0].cout));
   for (auto& b : h->blocks) {
@@ -492,7 +493,7 @@ template <int K>
 static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
   auto kfn = conv_fwd_kernel<K>;
 #ifndef TCR_EMU
-  static size_t smem_limit = 48 * 1024;   // per template instantiation
+  static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
   if (smem > smem_limit) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
     smem_limit = smem;

@@ -23,6 +23,7 @@ struct ConvPlan {
   float* bpart = nullptr;      // [G][cout][2]
   float* bsum = nullptr;       // [2][cout]
   float* dwpart = nullptr;     // [R][k*cin*cout]
+  float* wT = nullptr;         // [k][cout][cin] transposed filter bank (refreshed per backward pass)
   int dw_R = 1, dw_cot = 0, dw_RG = 1, dw_UB = 1;
   int64_t wnumel() const { return (int64_t)k * cin * cout; }
 };
