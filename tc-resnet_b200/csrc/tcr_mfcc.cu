@@ -220,7 +220,7 @@ int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
 #define TCR_MFCC_CASE(NF2)                                                                                   \
   case NF2: {                                                                                                \
     auto k = mfcc_kernel<NF2>;                                                                               \
-    static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default                                                                    \
+    static size_t smem_limit = 32 * 1024;                                                                    \
     if (smem > smem_limit) {                                                                                 \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
       smem_limit = smem;                                                                                     \
