@@ -55,6 +55,77 @@ __device__ __forceinline__ float4 dy_load4(const DySrc& d, size_t ofs, int C, in
   return r;
 }
 
+// ---- per-channel constants hoisted into registers -------------------------------------------------
+// Staging loops give every thread a FIXED group of 4 channels and walk rows, so the BN table entries (and the
+// BN-backward sums) are loaded once per thread instead of once per element.
+struct Chan4 { float4 mean, rstd, scale, beta; };
+__device__ __forceinline__ Chan4 chan4_load(const float* __restrict__ bnf, int C, int c) {
+  Chan4 k;
+  k.mean = ldg4(bnf + c); k.rstd = ldg4(bnf + C + c); k.scale = ldg4(bnf + 2 * C + c); k.beta = ldg4(bnf + 3 * C + c);
+  return k;
+}
+__device__ __forceinline__ float4 chan4_bn(const Chan4& k, float4 y) {
+  return make_float4(fmaf(y.x - k.mean.x, k.scale.x, k.beta.x), fmaf(y.y - k.mean.y, k.scale.y, k.beta.y),
+                     fmaf(y.z - k.mean.z, k.scale.z, k.beta.z), fmaf(y.w - k.mean.w, k.scale.w, k.beta.w));
+}
+__device__ __forceinline__ float4 chan4_xhat(const Chan4& k, float4 y) {
+  return make_float4((y.x - k.mean.x) * k.rstd.x, (y.y - k.mean.y) * k.rstd.y, (y.z - k.mean.z) * k.rstd.z, (y.w - k.mean.w) * k.rstd.w);
+}
+// activation source with hoisted constants
+struct Act4 { const float* data; Chan4 k; int kind; };
+__device__ __forceinline__ Act4 act4_make(const ActSrc& s, int C, int c) {
+  Act4 a;
+  a.data = s.data; a.kind = s.kind;
+  if (s.kind == 1) a.k = chan4_load(s.bnf, C, c);
+  return a;
+}
+__device__ __forceinline__ float4 act4_load(const Act4& a, size_t ofs) {
+  float4 v = ld4(a.data + ofs);
+  if (a.kind == 1) v = relu4(chan4_bn(a.k, v));
+  return v;
+}
+// dy = scale * (dz - s1/M - xhat * s2/M) with hoisted constants
+struct Dy4 { const float* dz; const float* y; Chan4 k; float4 s1m, s2m; int mask; };
+__device__ __forceinline__ Dy4 dy4_make(const DySrc& d, int C, int c) {
+  Dy4 r;
+  r.dz = d.dz; r.y = d.y; r.mask = d.mask_relu;
+  r.k = chan4_load(d.bnf, C, c);
+  const float4 s1 = ldg4(d.bsum + c), s2 = ldg4(d.bsum + C + c);
+  const float im = d.inv_m;
+  r.s1m = make_float4(s1.x * im, s1.y * im, s1.z * im, s1.w * im);
+  r.s2m = make_float4(s2.x * im, s2.y * im, s2.z * im, s2.w * im);
+  return r;
+}
+__device__ __forceinline__ float4 dy4_load(const Dy4& d, size_t ofs) {
+  float4 dz = ld4(d.dz + ofs);
+  const float4 y = ld4(d.y + ofs);
+  if (d.mask) {
+    const float4 z = chan4_bn(d.k, y);
+    if (z.x <= 0.f) dz.x = 0.f;
+    if (z.y <= 0.f) dz.y = 0.f;
+    if (z.z <= 0.f) dz.z = 0.f;
+    if (z.w <= 0.f) dz.w = 0.f;
+  }
+  float4 r;
+  r.x = d.k.scale.x * (dz.x - d.s1m.x - (y.x - d.k.mean.x) * d.k.rstd.x * d.s2m.x);
+  r.y = d.k.scale.y * (dz.y - d.s1m.y - (y.y - d.k.mean.y) * d.k.rstd.y * d.s2m.y);
+  r.z = d.k.scale.z * (dz.z - d.s1m.z - (y.z - d.k.mean.z) * d.k.rstd.z * d.s2m.z);
+  r.w = d.k.scale.w * (dz.w - d.s1m.w - (y.w - d.k.mean.w) * d.k.rstd.w * d.s2m.w);
+  return r;
+}
+
+// 2-D walk of a [rows][c4n] float4 grid by the CTA: c4 fixed per thread, rows advance by rstep.
+// Threads beyond rstep * c4n idle (row = huge).
+struct RowWalk { int c4, row, rstep; };
+__device__ __forceinline__ RowWalk row_walk(int tid, int nthreads, int c4n) {
+  RowWalk w;
+  w.rstep = nthreads / c4n;
+  w.c4 = tid % c4n;
+  w.row = tid / c4n;
+  if (w.row >= w.rstep) w.row = 1 << 29;
+  return w;
+}
+
 // "Last CTA finalises": returns true in exactly one CTA of the grid, after every other CTA's global
 // writes are visible.  The counter is reset for the next launch.
 __device__ __forceinline__ bool last_block_done(unsigned* counter, unsigned nblocks) {

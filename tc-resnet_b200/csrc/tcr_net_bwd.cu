@@ -70,17 +70,29 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       const int row = pr < PLd ? pr : a.t_out + pr;
       st4(dys + ((size_t)(u * TPd + row) * COS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    for (int idx = tid; idx < Ue * a.t_out * c4n; idx += kThreads) {
-      const int c4 = idx % c4n, t = (idx / c4n) % a.t_out, u = idx / (c4n * a.t_out);
-      const size_t gofs = ((size_t)(u0 + u) * a.t_out + t) * a.cout + 4 * c4;
-      st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * c4), dy_load4(a.dy, gofs, a.cout, 4 * c4));
+    {
+      const RowWalk w = row_walk(tid, kThreads, c4n);
+      const int rows = Ue * a.t_out;
+      const size_t grow = (size_t)u0 * a.t_out;
+      if (w.row < rows) {
+        const Dy4 d = dy4_make(a.dy, a.cout, 4 * w.c4);
+        int u = w.row / a.t_out, t = w.row - u * a.t_out;
+        for (int row = w.row; row < rows; row += w.rstep) {
+          st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * w.c4), dy4_load(d, (grow + row) * a.cout + 4 * w.c4));
+          t += w.rstep;
+          while (t >= a.t_out) { t -= a.t_out; ++u; }
+        }
+      }
     }
     if (a.has_down) {
       const int d4n = a.coutd >> 2;
-      for (int idx = tid; idx < Ue * a.t_out * d4n; idx += kThreads) {
-        const int c4 = idx % d4n, t = (idx / d4n) % a.t_out, u = idx / (d4n * a.t_out);
-        const size_t gofs = ((size_t)(u0 + u) * a.t_out + t) * a.coutd + 4 * c4;
-        st4(dysd + ((size_t)(u * a.t_out + t) * COSD + 4 * c4), dy_load4(a.dyd, gofs, a.coutd, 4 * c4));
+      const RowWalk w = row_walk(tid, kThreads, d4n);
+      const int rows = Ue * a.t_out;
+      const size_t grow = (size_t)u0 * a.t_out;
+      if (w.row < rows) {
+        const Dy4 d = dy4_make(a.dyd, a.coutd, 4 * w.c4);
+        for (int row = w.row; row < rows; row += w.rstep)
+          st4(dysd + ((size_t)row * COSD + 4 * w.c4), dy4_load(d, (grow + row) * a.coutd + 4 * w.c4));
       }
     }
   }
@@ -177,6 +189,10 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   const size_t grow0 = (size_t)u0 * a.t_in;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, sd1 = s1, sd2 = s1;
   if (seg < nseg) {
+    const Chan4 kp = chan4_load(a.bnfp, a.cin, 4 * cig);
+    const bool has_pd = a.epi_kind == 2 && a.ypd;
+    Chan4 kpd = kp;
+    if (has_pd) kpd = chan4_load(a.bnfpd, a.cin, 4 * cig);
     for (int r = seg; r < Rin; r += nseg) {
       const size_t gofs = (grow0 + r) * a.cin + 4 * cig;
       float4 v = ld4(dxs + (size_t)r * a.cin + 4 * cig);
@@ -184,16 +200,16 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       if (a.gid) v = add4(v, ld4(a.gid + gofs));
       const float4 yv = ld4(a.yp + gofs);
       float4 g;
-      if (a.epi_kind == 1) g = mask_pos4(v, bn_apply4(yv, a.bnfp, a.cin, 4 * cig));
+      if (a.epi_kind == 1) g = mask_pos4(v, chan4_bn(kp, yv));
       else g = mask_pos4(v, ld4(a.out_prev + gofs));
       st4(a.gprev + gofs, g);
       s1 = add4(s1, g);
-      s2 = add4(s2, mul4(g, bn_xhat4(yv, a.bnfp, a.cin, 4 * cig)));
-      if (a.epi_kind == 2 && a.ypd) {
+      s2 = add4(s2, mul4(g, chan4_xhat(kp, yv)));
+      if (has_pd) {
         const float4 yd = ld4(a.ypd + gofs);
-        const float4 gs = mask_pos4(g, bn_apply4(yd, a.bnfpd, a.cin, 4 * cig));
+        const float4 gs = mask_pos4(g, chan4_bn(kpd, yd));
         sd1 = add4(sd1, gs);
-        sd2 = add4(sd2, mul4(gs, bn_xhat4(yd, a.bnfpd, a.cin, 4 * cig)));
+        sd2 = add4(sd2, mul4(gs, chan4_xhat(kpd, yd)));
       }
     }
     float* r0 = red + ((size_t)(0 * nseg + seg) * a.cin + 4 * cig);
@@ -266,30 +282,48 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
       const int row = prow < a.pad_left ? prow : a.t_in + prow;
       st4(xs + ((size_t)(u * TP + row) * a.cin + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    for (int idx = tid; idx < Ue * a.t_in * c4n; idx += blockDim.x) {
-      const int c4 = idx % c4n, t = (idx / c4n) % a.t_in, u = idx / (c4n * a.t_in);
-      const size_t gofs = ((size_t)(ub0 + u) * a.t_in + t) * a.cin + 4 * c4;
-      st4(xs + ((size_t)(u * TP + a.pad_left + t) * a.cin + 4 * c4), act_load4(a.x, gofs, a.cin, 4 * c4));
+    {
+      const RowWalk w = row_walk(tid, (int)blockDim.x, c4n);
+      const int rows = Ue * a.t_in;
+      if (w.row < rows) {
+        const Act4 src = act4_make(a.x, a.cin, 4 * w.c4);
+        int u = w.row / a.t_in, t = w.row - u * a.t_in;
+        for (int row = w.row; row < rows; row += w.rstep) {
+          st4(xs + ((size_t)(u * TP + a.pad_left + t) * a.cin + 4 * w.c4),
+              act4_load(src, ((size_t)ub0 * a.t_in + row) * a.cin + 4 * w.c4));
+          t += w.rstep;
+          while (t >= a.t_in) { t -= a.t_in; ++u; }
+        }
+      }
     }
-    for (int idx = tid; idx < Ue * a.t_out * d4n; idx += blockDim.x) {
-      const int c4 = idx % d4n, r = idx / d4n;
-      const size_t gofs = ((size_t)ub0 * a.t_out + r) * a.cout + cot0 + 4 * c4;
-      st4(dys + (size_t)r * a.cot + 4 * c4, dy_load4(a.dy, gofs, a.cout, cot0 + 4 * c4));
+    {
+      const RowWalk w = row_walk(tid, (int)blockDim.x, d4n);
+      const int rows = Ue * a.t_out;
+      if (w.row < rows) {
+        const Dy4 d = dy4_make(a.dy, a.cout, cot0 + 4 * w.c4);
+        for (int row = w.row; row < rows; row += w.rstep)
+          st4(dys + (size_t)row * a.cot + 4 * w.c4, dy4_load(d, ((size_t)ub0 * a.t_out + row) * a.cout + cot0 + 4 * w.c4));
+      }
     }
     __syncthreads();
     if (worker) {
-      const int rows = Ue * a.t_out;
-      for (int r = rg; r < rows; r += a.RG) {
-        const int u = r / a.t_out, t = r - u * a.t_out;
-        const float* xrow = xs + (size_t)(u * TP + t * a.stride) * a.cin + 2 * ci2;
-        const float4 d = ld4(dys + (size_t)r * a.cot + 4 * co4);
+      // worker rg takes t = rg, rg + RG, ... of every staged utterance: no division in the row loop
+      const float* xu = xs + 2 * ci2;
+      const float* du = dys + 4 * co4;
+      const int xstep = a.stride * a.cin;
+      for (int u = 0; u < Ue; ++u, xu += (size_t)TP * a.cin, du += (size_t)a.t_out * a.cot) {
+        const float* xrow = xu + (size_t)rg * xstep;
+        const float* drow = du + (size_t)rg * a.cot;
+        for (int t = rg; t < a.t_out; t += a.RG, xrow += (size_t)a.RG * xstep, drow += (size_t)a.RG * a.cot) {
+          const float4 d = ld4(drow);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const float2 x = ld2(xrow + k * a.cin);
-          acc[k][0].x = fmaf(x.x, d.x, acc[k][0].x); acc[k][0].y = fmaf(x.x, d.y, acc[k][0].y);
-          acc[k][0].z = fmaf(x.x, d.z, acc[k][0].z); acc[k][0].w = fmaf(x.x, d.w, acc[k][0].w);
-          acc[k][1].x = fmaf(x.y, d.x, acc[k][1].x); acc[k][1].y = fmaf(x.y, d.y, acc[k][1].y);
-          acc[k][1].z = fmaf(x.y, d.z, acc[k][1].z); acc[k][1].w = fmaf(x.y, d.w, acc[k][1].w);
+          for (int k = 0; k < K; ++k) {
+            const float2 x = ld2(xrow + k * a.cin);
+            acc[k][0].x = fmaf(x.x, d.x, acc[k][0].x); acc[k][0].y = fmaf(x.x, d.y, acc[k][0].y);
+            acc[k][0].z = fmaf(x.x, d.z, acc[k][0].z); acc[k][0].w = fmaf(x.x, d.w, acc[k][0].w);
+            acc[k][1].x = fmaf(x.y, d.x, acc[k][1].x); acc[k][1].y = fmaf(x.y, d.y, acc[k][1].y);
+            acc[k][1].z = fmaf(x.y, d.z, acc[k][1].z); acc[k][1].w = fmaf(x.y, d.w, acc[k][1].w);
+          }
         }
       }
     }

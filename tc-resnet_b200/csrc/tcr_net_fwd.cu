@@ -60,19 +60,34 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     const int row = pr < a.pad_left ? pr : a.t_in + pr;
     st4(xs + ((size_t)(u * TP + row) * CS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
   }
-  for (int idx = tid; idx < Ue * a.t_in * c4n; idx += kThreads) {
-    const int c4 = idx % c4n, t = (idx / c4n) % a.t_in, u = idx / (c4n * a.t_in);
-    const size_t gofs = ((size_t)(u0 + u) * a.t_in + t) * a.cin + 4 * c4;
-    float4 v;
-    if (a.in_kind == 2) {
-      const float4 zb = bn_apply4(ld4(a.in.data + gofs), a.in.bnf, a.cin, 4 * c4);
-      const float4 sh = act_load4(a.shortcut, gofs, a.cin, 4 * c4);
-      v = relu4(add4(zb, sh));
-      if (a.out_write) st4(a.out_write + gofs, v);
-    } else {
-      v = act_load4(a.in, gofs, a.cin, 4 * c4);
+  {
+    // c4 fixed per thread (per-channel constants in registers), rows advance incrementally: no div/mod per element
+    const RowWalk w = row_walk(tid, kThreads, c4n);
+    const int rows = Ue * a.t_in;
+    const size_t grow = (size_t)u0 * a.t_in;
+    if (w.row < rows) {
+      int u = w.row / a.t_in, t = w.row - u * a.t_in;
+      if (a.in_kind == 2) {
+        const Chan4 kb = chan4_load(a.in.bnf, a.cin, 4 * w.c4);
+        const Act4 sh = act4_make(a.shortcut, a.cin, 4 * w.c4);
+        for (int row = w.row; row < rows; row += w.rstep) {
+          const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
+          const float4 v = relu4(add4(chan4_bn(kb, ld4(a.in.data + gofs)), act4_load(sh, gofs)));
+          if (a.out_write) st4(a.out_write + gofs, v);
+          st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), v);
+          t += w.rstep;
+          while (t >= a.t_in) { t -= a.t_in; ++u; }
+        }
+      } else {
+        const Act4 src = act4_make(a.in, a.cin, 4 * w.c4);
+        for (int row = w.row; row < rows; row += w.rstep) {
+          const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
+          st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), act4_load(src, gofs));
+          t += w.rstep;
+          while (t >= a.t_in) { t -= a.t_in; ++u; }
+        }
+      }
     }
-    st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * c4), v);
   }
   if (a.w_smem) mbar_wait(bar, 0);
   __syncthreads();
