@@ -102,7 +102,7 @@ def run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=4, ke
                 report["grads_f32_oracle_floor"] = floor / 4
             assert report[f"train_logits{step}"] <= TOL_LOGITS, report
             assert report[f"grads{step}"] <= max(TOL_STATE, floor), report
-            assert report[f"params{step}"] <= TOL_STATE, report
+            assert report[f"params{step}"] <= max(TOL_STATE, floor), report
             assert report[f"slots{step}"] <= max(TOL_STATE, floor), report
             assert report[f"moving{step}"] <= TOL_STATE, report
             assert abs(ts["losses"][0] - ref["total_loss"]) <= 1e-4 * abs(ref["total_loss"]) + 1e-6
