@@ -193,12 +193,11 @@ class Engine:
         world, rank = dist.get_world_size(), dist.get_rank()
         if world == 1:
             return
+        from .dp import broadcast_bytes
         buf = (C.c_char * 128)()
         if rank == 0:
             L.check(self.lib, self.lib.tcr_comm_unique_id(buf), "tcr_comm_unique_id")
-        ids = [bytes(buf) if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        idbuf = (C.c_char * 128).from_buffer_copy(ids[0])
+        idbuf = (C.c_char * 128).from_buffer_copy(broadcast_bytes(bytes(buf) if rank == 0 else None))
         with torch.cuda.device(self.device):
             L.check(self.lib, self.lib.tcr_comm_init(self._h, idbuf, rank, world), "tcr_comm_init")
         self.world_size = world

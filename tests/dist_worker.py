@@ -1,0 +1,82 @@
+"""Worker for the multi-process tests (launched by tests/test_dist.py).
+
+mode gloo : CPU, world 2.  Host-side DP logic: shard bounds, unique-id style byte broadcast, and the identity the
+            GPU path relies on — mean over ranks of per-shard gradients (local BN statistics) == oracle computed
+            shard-wise and averaged; a data-parallel SGD-momentum step on the averaged gradient keeps replicas identical.
+mode nccl : GPU, one rank per GPU.  The CUDA path with its NCCL all-reduce vs the same oracle average.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tcresnet_b200  # noqa: E402,F401
+from tcresnet_b200.dp import broadcast_bytes, shard_bounds  # noqa: E402
+from oracle import tcr_oracle as O  # noqa: E402
+from parity_cases import perturbed_variables  # noqa: E402
+
+
+def oracle_shard_grads(spec, params, moving, feat, onehot, wd):
+    logits, cache = O.forward(spec, params, moving, feat, True)
+    return O.flatten_vars(spec, O.backward(spec, params, cache, logits, onehot, wd), np.float64)
+
+
+def main():
+    mode = sys.argv[1]
+    dist.init_process_group("gloo" if mode == "gloo" else "nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_global = 16 * world
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    params, moving = perturbed_variables(spec)
+    wav, onehot = O.synthetic_batch(n_global)
+    lo, hi = shard_bounds(n_global, rank, world)
+    assert (hi - lo) * world == n_global and lo == rank * 16
+    token = broadcast_bytes(bytes(range(128)) if rank == 0 else None)
+    assert token == bytes(range(128))
+    feat = O.mfcc(wav, 640, 320)
+    wd, lr, mom = 1e-3, 0.1, 0.9
+    ref = np.mean([oracle_shard_grads(spec, params, moving, feat[r * 16:(r + 1) * 16], onehot[r * 16:(r + 1) * 16], wd)
+                   for r in range(world)], axis=0)
+    if mode == "gloo":
+        mine = torch.from_numpy(oracle_shard_grads(spec, params, moving, feat[lo:hi], onehot[lo:hi], wd))
+        dist.all_reduce(mine)
+        avg = (mine / world).numpy()
+        assert np.abs(avg - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        new = O.flatten_vars(spec, params, np.float64) - lr * avg          # slots start at 0
+        gathered = [torch.zeros_like(torch.from_numpy(new)) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(new))
+        assert all(torch.equal(g, gathered[0]) for g in gathered)          # replicas stay identical
+    else:
+        from tcresnet_b200.engine import Engine
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        eng = Engine(max_batch=16, dropout_keep_prob=1.0)
+        eng.attach_process_group()
+        dev = eng.device
+        p = torch.from_numpy(O.flatten_vars(spec, params)).to(dev)
+        mv = torch.from_numpy(O.flatten_moving(spec, moving)).to(dev)
+        sl = torch.zeros_like(p)
+        out = eng.train_step(torch.from_numpy(wav[lo:hi]).to(dev), torch.from_numpy(onehot[lo:hi]).to(dev), p, sl, mv,
+                             lr, mom, wd, want_grads=True)
+        torch.cuda.synchronize()
+        g = out["grads"].cpu().numpy().astype(np.float64)
+        err = np.abs(g - ref).max() / np.abs(ref).max()
+        assert err < 1e-4, f"rank {rank}: averaged gradient off by {err}"
+        expect = O.flatten_vars(spec, params, np.float64) - lr * ref
+        perr = np.abs(p.cpu().numpy() - expect).max() / np.abs(expect).max()
+        assert perr < 1e-4, perr
+        gathered = [torch.zeros_like(p) for _ in range(world)]
+        dist.all_gather(gathered, p)
+        assert all(torch.equal(x, gathered[0]) for x in gathered), "replicas diverged"
+        if rank == 0:
+            print(f"nccl world={world}: grad rel err {err:.2e}, params rel err {perr:.2e}, replicas bit-identical")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""N>1 path: world_size-2 gloo test on CPU (host logic + DP identity), torchrun NCCL test on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _torchrun(mode, nproc, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "dist_worker.py"), mode]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+def test_data_parallel_identity_gloo_world2():
+    r = _torchrun("gloo", 2, 29611)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_nccl_gradient_allreduce_matches_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun("nccl", min(torch.cuda.device_count(), 8), 29612)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "replicas bit-identical" in r.stdout

@@ -1,0 +1,114 @@
+"""The reference's Python surface: the recipes' exact command lines parse, the registries expose the
+reference's names, and (GPU) a short train -> checkpoint -> evaluate run works through train_audio / evaluate_audio."""
+import glob
+import os
+import shlex
+
+import numpy as np
+import pytest
+
+import tcresnet_b200  # noqa: F401
+from tcresnet_b200 import evaluate_audio, train_audio
+from tcresnet_b200.common import checkpoint as ckpt
+from tcresnet_b200.datasets import preprocessor_factory
+from tcresnet_b200.factory import audio_nets
+from tcresnet_b200.helper.trainer import piecewise_constant
+from tcresnet_b200.runtime import Node, Session
+
+REF_SCRIPTS = "/root/reference/scripts/commands"
+
+# verbatim copies of the TC-ResNet recipe lines (scripts/commands/TCResNet8Model-1.0_mfcc_40_3010_0.001_mom_l1.sh:3,5,7)
+TRAIN_LINE = ("--dataset_path google_speech_commands/splitted_data --dataset_split_name train --output_name output/softmax "
+              "--num_classes 12 --train_dir work/v1/TCResNet8Model-1.0/mfcc_40_3010_0.001_mom_l1 --num_silent 1854 "
+              "--augmentation_method anchored_slice_or_pad_with_shift --preprocess_method mfcc --num_mfccs 40 "
+              "--clip_duration_ms 1000 --window_size_ms 30 --window_stride_ms 10 --batch_size 100 --boundaries 10000 20000 "
+              "--max_step_from_restore 30000 --lr_list 0.1 0.01 0.001 --absolute_schedule --no-boundaries_epoch --max_to_keep 20 "
+              "--step_save_checkpoint 500 --step_evaluation 500 --optimizer mom --momentum 0.9 TCResNet8Model --weight_decay 0.001 "
+              "--width_multiplier 1.0")
+EVAL_LINE = ("--dataset_path google_speech_commands/splitted_data --dataset_split_name valid --output_name output/softmax "
+             "--num_classes 12 --checkpoint_path work/v1/TCResNet8Model-1.0/mfcc_40_3010_0.001_mom_l1 --num_silent 258 "
+             "--augmentation_method anchored_slice_or_pad --preprocess_method mfcc --num_mfccs 40 --clip_duration_ms 1000 "
+             "--window_size_ms 30 --window_stride_ms 10 --background_frequency 0.0 --background_max_volume 0.0 "
+             "--max_step_from_restore 30000 --batch_size 3 --no-shuffle --valid_type loop TCResNet8Model --weight_decay 0.001 "
+             "--width_multiplier 1.0")
+
+
+def test_recipe_command_lines_parse():
+    a = train_audio.parse_arguments(shlex.split(TRAIN_LINE))
+    assert (a.model, a.weight_decay, a.width_multiplier, a.batch_size) == ("TCResNet8Model", 0.001, 1.0, 100)
+    assert a.lr_list == [0.1, 0.01, 0.001] and a.boundaries == [10000, 20000] and a.relative is False
+    assert a.boundaries_epoch is False and a.optimizer == "mom" and a.momentum == 0.9
+    assert (a.window_size_ms, a.window_stride_ms, a.num_mfccs, a.num_mel_bins) == (30.0, 10.0, 40, 64)
+    e = evaluate_audio.parse_arguments(shlex.split(EVAL_LINE))
+    assert (e.model, e.valid_type, e.batch_size, e.shuffle) == ("TCResNet8Model", "loop", 3, False)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCRIPTS), reason="reference tree not mounted (GPU box)")
+def test_every_reference_recipe_parses():
+    n = 0
+    for path in sorted(glob.glob(os.path.join(REF_SCRIPTS, "*.sh"))):
+        for line in open(path):
+            line = line.strip().rstrip("&").strip()
+            if line.startswith("python train_audio.py"):
+                train_audio.parse_arguments(shlex.split(line)[2:])
+                n += 1
+            elif line.startswith("python evaluate_audio.py"):
+                evaluate_audio.parse_arguments(shlex.split(line)[2:])
+                n += 1
+    assert n >= 40
+
+
+def test_registries_expose_the_reference_names():
+    ref = ["KWSModel", "Res8Model", "Res8NarrowModel", "Res15Model", "Res15NarrowModel", "DSCNNSModel", "DSCNNMModel",
+           "DSCNNLModel", "TCResNet8Model", "TCResNet14Model", "ResNet2D8Model", "ResNet2D8PoolModel"]
+    assert audio_nets._available_nets == ref                      # factory/audio_nets.py:19-32
+    for name in ref:
+        assert hasattr(audio_nets, name)
+    assert set(preprocessor_factory._available_preprocessors) == {"log_mel_spectrogram", "mfcc", "no_preprocessing"}
+    with pytest.raises(NotImplementedError):
+        preprocessor_factory.factory("nope", "s", "n")
+    pre = preprocessor_factory.factory("mfcc", "input/audio/preprocessing", "input/audio/preprocessed")
+    node = pre.preprocess(Node("wav", [None, 16000, 1]), 480, 160, False, num_mfccs=40, num_mel_bins=64, sample_rate=16000)
+    assert node.shape == [None, 98, 40, 1] and pre.preprocessed_node is node
+
+
+def test_learning_rate_schedule_and_checkpoints(tmp_path):
+    assert [piecewise_constant(s, [10000, 20000], [0.1, 0.01, 0.001]) for s in (0, 10000, 10001, 20001)] == [0.1, 0.1, 0.01, 0.001]
+    var = {"TCResNet8/conv0/weights": np.arange(6, dtype=np.float32).reshape(3, 1, 2, 1)}
+    for step in (500, 1000, 1500):
+        path = ckpt.save(tmp_path, "TCResNet8Model", step, var, max_to_keep=2)
+    assert ckpt.checkpoint_step(path) == 1500 and ckpt.latest_checkpoint(tmp_path) == path
+    assert len(list(tmp_path.glob("*.npz"))) == 2                  # max_to_keep
+    back = ckpt.load(path)
+    assert int(back["global_step"]) == 1500
+    np.testing.assert_array_equal(back["TCResNet8/conv0/weights"], var["TCResNet8/conv0/weights"])
+    assert next(ckpt.checkpoints_iterator(tmp_path, timeout=0)) == path
+
+
+def test_session_requires_a_bound_model():
+    with pytest.raises(RuntimeError):
+        Session().run({"x": Node("total_loss")})
+    assert Session().run(Node("noop")) is None
+
+
+@pytest.mark.gpu
+def test_train_then_evaluate_through_the_reference_cli(tmp_path):
+    common = (f"--dataset_path synthetic:96 --output_name output/softmax --num_classes 12 --preprocess_method mfcc "
+              f"--num_mfccs 40 --clip_duration_ms 1000 --window_size_ms 30 --window_stride_ms 10 ")
+    train_args = train_audio.parse_arguments(shlex.split(
+        common + f"--dataset_split_name train --train_dir {tmp_path} --augmentation_method anchored_slice_or_pad_with_shift "
+        "--batch_size 32 --boundaries 10 20 --max_step_from_restore 12 --lr_list 0.1 0.01 0.001 --absolute_schedule "
+        "--no-boundaries_epoch --step_save_checkpoint 6 --step_evaluation 6 --optimizer mom --momentum 0.9 "
+        "TCResNet8Model --weight_decay 0.001 --width_multiplier 1.0"))
+    trainer = train_audio.train(train_args)
+    assert trainer.model.global_step == 12
+    saved = ckpt.latest_checkpoint(tmp_path)
+    assert saved is not None and ckpt.checkpoint_step(saved) == 12
+    names = set(ckpt.load(saved))
+    assert "TCResNet8/block0/conv0_0/BatchNorm/moving_variance" in names and "TCResNet8/fc/weights/Momentum" in names
+    eval_args = evaluate_audio.parse_arguments(shlex.split(
+        common + f"--dataset_split_name valid --checkpoint_path {tmp_path} --augmentation_method anchored_slice_or_pad "
+        "--batch_size 3 --no-shuffle --valid_type once TCResNet8Model --weight_decay 0.001 --width_multiplier 1.0"))
+    results = evaluate_audio.main(eval_args)
+    assert len(results) == 1 and 0.0 <= results[0]["accuracy"] <= 1.0 and np.isfinite(results[0]["total_loss"])
+    assert (tmp_path / "valid" / "accuracy").is_dir()              # best-checkpoint directory the test recipe reads
