@@ -28,8 +28,16 @@ def oracle_shard_grads(spec, params, moving, feat, onehot, wd):
 
 def main():
     mode = sys.argv[1]
-    dist.init_process_group("gloo" if mode == "gloo" else "nccl")
+    if mode == "gloo":
+        dist.init_process_group("gloo")
+    else:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)                      # before ANY NCCL collective (one GPU per rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
+
+    def mark(msg):
+        print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
     n_global = 16 * world
     spec = O.build_spec("TCResNet8", 1.0, 49)
     params, moving = perturbed_variables(spec)
@@ -53,9 +61,10 @@ def main():
         assert all(torch.equal(g, gathered[0]) for g in gathered)          # replicas stay identical
     else:
         from tcresnet_b200.engine import Engine
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         eng = Engine(max_batch=16, dropout_keep_prob=1.0)
+        mark("engine created")
         eng.attach_process_group()
+        mark("communicator attached")
         dev = eng.device
         p = torch.from_numpy(O.flatten_vars(spec, params)).to(dev)
         mv = torch.from_numpy(O.flatten_moving(spec, moving)).to(dev)
@@ -63,6 +72,7 @@ def main():
         out = eng.train_step(torch.from_numpy(wav[lo:hi]).to(dev), torch.from_numpy(onehot[lo:hi]).to(dev), p, sl, mv,
                              lr, mom, wd, want_grads=True)
         torch.cuda.synchronize()
+        mark("train step done")
         g = out["grads"].cpu().numpy().astype(np.float64)
         err = np.abs(g - ref).max() / np.abs(ref).max()
         assert err < 1e-4, f"rank {rank}: averaged gradient off by {err}"
