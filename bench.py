@@ -261,8 +261,19 @@ def run_ours(a):
                       "final_total_loss": final_loss},
            "gpu_launches": int(launches), "clocks": clocks}
 
+    # ---- per-kernel durations (separate pass: event brackets add overhead, so not the timed region).  Every rank runs
+    # the steps (they contain the gradient all-reduce); rank 0 reports.
+    psteps = min(a.steps, 30)
+    fp32_peak = eng.fp32_peak_tflops() if rank == 0 else 0.0
+    barrier()
+    eng.profile(True)
+    for i in range(psteps):
+        step(i)
+    torch.cuda.synchronize()
+    stats = eng.profile_read()
+    eng.profile(False)
+    barrier()
     if rank == 0:
-        # ---- per-kernel durations (separate pass: event brackets add overhead, so not the timed region) ----
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -270,14 +281,6 @@ def run_ours(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        fp32_peak = eng.fp32_peak_tflops()
-        psteps = min(a.steps, 30)
-        eng.profile(True)
-        for i in range(psteps):
-            step(i)
-        torch.cuda.synchronize()
-        stats = eng.profile_read()
-        eng.profile(False)
         total_ms = sum(v[0] for v in stats.values())
         top = sorted(stats.items(), key=lambda kv: -kv[1][0])
         kernels = []
