@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--workload", default="train", choices=["train", "dscnn"],
+                    help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point)")
     return ap.parse_args()
 
 
@@ -341,8 +343,43 @@ def run_ours(a):
         torch.distributed.destroy_process_group()
 
 
+def run_dscnn(a):
+    """Config 5: DS-CNN-S forward, MFCC 49x40 features resident in HBM, batch 512, one B200 (2-D-conv comparison point)."""
+    import torch
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.dscnn import DsCnn
+    dev = torch.device("cuda", 0)
+    n = a.batch
+    net = DsCnn("S", 49, 40, 12, max_batch=n)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    params = torch.randn(net.num_params, device=dev, generator=gen) * 0.1
+    for d in net.table:                                           # moving variances must be positive
+        if d["name"].endswith("moving_variance"):
+            params[d["offset"]:d["offset"] + d["numel"]] = 1.0
+    feats = [torch.randn(n, 49, 40, device=dev, generator=gen) for _ in range(a.rotate)]
+    for i in range(max(a.warmup, 3)):
+        net.forward(feats[i % a.rotate], params)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        net.forward(feats[i % a.rotate], params)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = n * a.steps / (ms * 1e-3)
+    print(json.dumps({"metric": "utterances/sec (forward) DS-CNN-S", "value": value, "unit": "utterances/sec", "n_gpus": 1,
+                      "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+                      "config": {"workload": f"DS-CNN-S forward (inference), MFCC 49x40 features resident in HBM, batch {n}",
+                                 "forward_flops_per_utt": net.forward_flops},
+                      "fp32_tflops": value * net.forward_flops / 1e12}), flush=True)
+
+
 def main():
     a = parse_args()
+    if a.workload == "dscnn":
+        return run_dscnn(a)
     if a.impl == "reference":
         run_reference(a)
     else:

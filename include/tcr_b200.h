@@ -173,6 +173,27 @@ int tcr_comm_destroy(tcr_handle* h);
  * denominator by bench.py.  Launches a register-resident FMA loop and times it with CUDA events. */
 int tcr_measure_fp32_peak(tcr_handle* h, double* tflops, tcr_stream stream);
 
+/* DS-CNN (Hello-Edge) forward pass, inference mode: the reference's 2-D-conv comparison model
+ * (audio_nets/ds_cnn.py:20-118; factory/audio_nets.py DSCNN{S,M,L}Model.build_inference; BASELINE.json config 5).
+ * features [n, height, width] (== [N,H,W,1]); params = one flat fp32 buffer laid out by tcr_dscnn_param_table
+ * (TF variable names "DSCNN/conv_1/weights", ".../batch_norm/moving_mean", "DSCNN/fc1/biases", ...).
+ * size: 'S' or 'M' ('L' builds its table but its 276-channel head is not supported yet). */
+typedef struct tcr_dscnn tcr_dscnn;
+typedef struct tcr_dscnn_config {
+  int32_t size;          /* 'S' | 'M' | 'L' */
+  int32_t height;        /* frames, 49 */
+  int32_t width;         /* coefficients, 40 (10 in the reference's DS-CNN recipes) */
+  int32_t num_classes;   /* 12 */
+  int32_t max_batch;
+  int32_t device;
+} tcr_dscnn_config;
+int tcr_dscnn_create(const tcr_dscnn_config* cfg, tcr_dscnn** out);
+int tcr_dscnn_destroy(tcr_dscnn* d);
+int tcr_dscnn_param_table(const tcr_dscnn* d, const tcr_param_desc** descs, int32_t* count, int64_t* num_params,
+                          int64_t* forward_flops_per_utt);
+int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const float* params, int32_t n, float* logits, float* probs,
+                      tcr_stream stream);
+
 /* Process-wide launch accounting (no reference counterpart; the reference only logs wall-clock per
  * session.run, helper/trainer.py:312-321).  tcr_launch_count: kernels launched by this library so far.
  * tcr_profile_enable(1) brackets every subsequent launch with CUDA events on its stream (adds overhead:

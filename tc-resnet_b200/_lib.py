@@ -54,6 +54,11 @@ class TcrKernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("total_ms", C.c_double), ("launches", C.c_int64)]
 
 
+class TcrDscnnConfig(C.Structure):
+    _fields_ = [("size", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("num_classes", C.c_int32),
+                ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
 class TcrStepArgs(C.Structure):
     _fields_ = [
         ("input", C.c_void_p), ("input_is_features", C.c_int32), ("onehot", C.c_void_p), ("n", C.c_int32),
@@ -84,6 +89,11 @@ SYMBOLS = {
     "tcr_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tcr_comm_destroy": (C.c_int, [C.c_void_p]),
     "tcr_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "tcr_dscnn_create": (C.c_int, [C.POINTER(TcrDscnnConfig), C.POINTER(C.c_void_p)]),
+    "tcr_dscnn_destroy": (C.c_int, [C.c_void_p]),
+    "tcr_dscnn_param_table": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(TcrParamDesc)), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tcr_dscnn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tcr_profile_enable": (C.c_int, [C.c_int]),
     "tcr_profile_read": (C.c_int, [C.POINTER(C.POINTER(TcrKernelStat)), C.POINTER(C.c_int32)]),
     "tcr_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
