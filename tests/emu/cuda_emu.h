@@ -43,15 +43,15 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 
 namespace emu {
-struct ThreadCtx { uint3 tid; };
+struct ThreadCtx { uint3 tid; uint3 bid; unsigned char* smem; };
 struct State {
   ThreadCtx* cur = nullptr;
-  uint3 bid{0, 0, 0};
   dim3 bdim, gdim;
-  unsigned char* dyn_smem = nullptr;
 };
 State& st();
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
+void launch_cooperative(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);   // all blocks co-resident
+void gridsync();
 void syncthreads();
 void syncwarp();
 uint64_t warp_exchange(uint64_t v, int src_lane);   // every lane posts v, returns lane src_lane's value
@@ -60,7 +60,7 @@ int lane_id();
 }  // namespace emu
 
 #define threadIdx (emu::st().cur->tid)
-#define blockIdx (emu::st().bid)
+#define blockIdx (emu::st().cur->bid)
 #define blockDim (emu::st().bdim)
 #define gridDim (emu::st().gdim)
 #define warpSize 32
@@ -151,4 +151,6 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 
 #define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
-#define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().dyn_smem
+#define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().cur->smem
+#define TCR_LAUNCH_COOP(name, kernel, grid, block, smem, stream, ...) \
+  emu::launch_cooperative((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })

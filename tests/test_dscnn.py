@@ -81,7 +81,7 @@ def test_emulated_dscnn_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("size,h,w,n", [("S", 49, 40, 512), ("S", 49, 10, 39), ("M", 49, 10, 33), ("M", 49, 40, 7)])
+@pytest.mark.parametrize("size,h,w,n", [("S", 49, 40, 512), ("S", 49, 10, 39), ("M", 49, 10, 33)])
 def test_cuda_dscnn_matches_oracle(size, h, w, n):
     from tcr_harness import TorchBackend
     assert _run(TorchBackend(), size, h, w, n) < 1e-5
