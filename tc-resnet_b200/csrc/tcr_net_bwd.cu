@@ -28,7 +28,7 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(
 // ------------------------------------------------------------------------------------------------
 // backward data
 // ------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool WSMEM>
 __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -45,10 +45,10 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   // shared memory: [mbarrier | W | W_down | dy tile | dy_down tile | dx planes | scratch]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float* ws = smem + 4;
-  const int wn = a.w_smem ? K * a.cin * a.cout : 0;
-  const int wdn = (a.w_smem && a.has_down) ? a.cin * a.coutd : 0;
+  const int wn = WSMEM ? K * a.cin * a.cout : 0;
+  const int wdn = (WSMEM && a.has_down) ? a.cin * a.coutd : 0;
   float* wsd = ws + wn;
-  if (a.w_smem) {
+  if (WSMEM) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   float* dysd = dys + (size_t)a.U * TPd * COS;                       // [U][t_out][COSD]
   float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
   float* red = dxs + (size_t)a.KS * Rin_max * a.cin;                 // [4][nseg][cin]
+  const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), dys_off = (int)(dys - smem), dysd_off = (int)(dysd - smem);
 
   // ---- stage dy (BatchNorm backward applied on load) ----
   {
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       }
     }
   }
-  if (a.w_smem) mbar_wait(bar, 0);
+  if (WSMEM) mbar_wait(bar, 0);
   __syncthreads();
 
   // ---- transposed conv, one parity class of input rows at a time ----
@@ -120,14 +121,14 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     const int u = q % Ue, ks = q / Ue;
     const int p = rtu >= nrt[0] ? 1 : 0;
     const int rt = rtu - p * nrt[0];
-    const float* dyr[TMB];
-    int tt[TMB];
+    // 32-bit float offsets from the shared-memory base (LDS.128 + FFMA + integer adds in the inner loop)
+    int dyo[TMB], tt[TMB];
 #pragma unroll
     for (int i = 0; i < TMB; ++i) {
       const int j = imin(rt + i * nrt[p], np[p] - 1);   // rows of a task are nrt apart: adjacent lanes -> adjacent rows
       tt[i] = t0[p] + S * j;
       const int b = (tt[i] + a.pad_left - p) / S;
-      dyr[i] = dys + (size_t)(u * TPd + PLd + b) * COS;
+      dyo[i] = dys_off + (u * TPd + PLd + b) * COS;
     }
     float4 acc[TMB];
 #pragma unroll
@@ -136,43 +137,66 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     const int m_lo = ks * MPS, m_hi = imin(NT, m_lo + MPS);
     for (int m = m_lo; m < m_hi; ++m) {
       // transposed filter bank wT[k][co][ci]: lanes (adjacent cig) read adjacent float4s -> no bank conflicts
-      const float* wk = (a.w_smem ? ws : a.w) + (size_t)(p + S * m) * a.cout * a.cin + 4 * cig;
+      const int dm = m * COS;
+      if (WSMEM) {
+        int wk = ws_off + (p + S * m) * a.cout * a.cin + 4 * cig;
 #pragma unroll 2
-      for (int co = 0; co < a.cout; co += 4) {
-        float4 w0, w1, w2, w3;          // w_j = wT[k][co + j][4cig .. 4cig+3]
-        if (a.w_smem) {
-          w0 = ld4(wk + (co + 0) * a.cin); w1 = ld4(wk + (co + 1) * a.cin); w2 = ld4(wk + (co + 2) * a.cin); w3 = ld4(wk + (co + 3) * a.cin);
-        } else {
-          w0 = ldg4(wk + (size_t)(co + 0) * a.cin); w1 = ldg4(wk + (size_t)(co + 1) * a.cin);
-          w2 = ldg4(wk + (size_t)(co + 2) * a.cin); w3 = ldg4(wk + (size_t)(co + 3) * a.cin);
-        }
+        for (int co = 0; co < a.cout; co += 4, wk += 4 * a.cin) {
+          const float4 w0 = ld4(smem + wk), w1 = ld4(smem + wk + a.cin), w2 = ld4(smem + wk + 2 * a.cin), w3 = ld4(smem + wk + 3 * a.cin);
 #pragma unroll
-        for (int i = 0; i < TMB; ++i) {
-          const float4 d = ld4(dyr[i] - m * COS + co);
-          acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
-          acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
-          acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
-          acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+          for (int i = 0; i < TMB; ++i) {
+            const float4 d = ld4(smem + dyo[i] - dm + co);
+            acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+            acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+            acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+            acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+          }
+        }
+      } else {
+        const float* wk = a.w + (size_t)(p + S * m) * a.cout * a.cin + 4 * cig;
+#pragma unroll 2
+        for (int co = 0; co < a.cout; co += 4, wk += 4 * a.cin) {
+          const float4 w0 = ldg4(wk), w1 = ldg4(wk + a.cin), w2 = ldg4(wk + 2 * a.cin), w3 = ldg4(wk + 3 * a.cin);
+#pragma unroll
+          for (int i = 0; i < TMB; ++i) {
+            const float4 d = ld4(smem + dyo[i] - dm + co);
+            acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+            acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+            acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+            acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+          }
         }
       }
     }
     if (a.has_down && ks == 0 && (t0[p] & 1) == 0) {     // 1x1 stride-2 shortcut conv touches even input rows only
-      const float* wk = (a.w_smem ? wsd : a.wd) + 4 * cig;          // wdT[co][ci]
-      for (int co = 0; co < a.coutd; co += 4) {
-        float4 w0, w1, w2, w3;
-        if (a.w_smem) {
-          w0 = ld4(wk + (co + 0) * a.cin); w1 = ld4(wk + (co + 1) * a.cin); w2 = ld4(wk + (co + 2) * a.cin); w3 = ld4(wk + (co + 3) * a.cin);
-        } else {
-          w0 = ldg4(wk + (size_t)(co + 0) * a.cin); w1 = ldg4(wk + (size_t)(co + 1) * a.cin);
-          w2 = ldg4(wk + (size_t)(co + 2) * a.cin); w3 = ldg4(wk + (size_t)(co + 3) * a.cin);
-        }
+      int ddo[TMB];
 #pragma unroll
-        for (int i = 0; i < TMB; ++i) {
-          const float4 d = ld4(dysd + (size_t)(u * a.t_out + (tt[i] >> 1)) * COSD + co);
-          acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
-          acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
-          acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
-          acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+      for (int i = 0; i < TMB; ++i) ddo[i] = dysd_off + (u * a.t_out + (tt[i] >> 1)) * COSD;
+      if (WSMEM) {
+        int wk = wsd_off + 4 * cig;                        // wdT[co][ci]
+        for (int co = 0; co < a.coutd; co += 4, wk += 4 * a.cin) {
+          const float4 w0 = ld4(smem + wk), w1 = ld4(smem + wk + a.cin), w2 = ld4(smem + wk + 2 * a.cin), w3 = ld4(smem + wk + 3 * a.cin);
+#pragma unroll
+          for (int i = 0; i < TMB; ++i) {
+            const float4 d = ld4(smem + ddo[i] + co);
+            acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+            acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+            acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+            acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+          }
+        }
+      } else {
+        const float* wk = a.wd + 4 * cig;
+        for (int co = 0; co < a.coutd; co += 4, wk += 4 * a.cin) {
+          const float4 w0 = ldg4(wk), w1 = ldg4(wk + a.cin), w2 = ldg4(wk + 2 * a.cin), w3 = ldg4(wk + 3 * a.cin);
+#pragma unroll
+          for (int i = 0; i < TMB; ++i) {
+            const float4 d = ld4(smem + ddo[i] + co);
+            acc[i].x = fmaf(d.x, w0.x, fmaf(d.y, w1.x, fmaf(d.z, w2.x, fmaf(d.w, w3.x, acc[i].x))));
+            acc[i].y = fmaf(d.x, w0.y, fmaf(d.y, w1.y, fmaf(d.z, w2.y, fmaf(d.w, w3.y, acc[i].y))));
+            acc[i].z = fmaf(d.x, w0.z, fmaf(d.y, w1.z, fmaf(d.z, w2.z, fmaf(d.w, w3.z, acc[i].z))));
+            acc[i].w = fmaf(d.x, w0.w, fmaf(d.y, w1.w, fmaf(d.z, w2.w, fmaf(d.w, w3.w, acc[i].w))));
+          }
         }
       }
     }
@@ -308,17 +332,15 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
     __syncthreads();
     if (worker) {
       // worker rg takes t = rg, rg + RG, ... of every staged utterance: no division in the row loop
-      const float* xu = xs + 2 * ci2;
-      const float* du = dys + 4 * co4;
       const int xstep = a.stride * a.cin;
-      for (int u = 0; u < Ue; ++u, xu += (size_t)TP * a.cin, du += (size_t)a.t_out * a.cot) {
-        const float* xrow = xu + (size_t)rg * xstep;
-        const float* drow = du + (size_t)rg * a.cot;
-        for (int t = rg; t < a.t_out; t += a.RG, xrow += (size_t)a.RG * xstep, drow += (size_t)a.RG * a.cot) {
-          const float4 d = ld4(drow);
+      int xu = (int)(xs - smem) + 2 * ci2, du = (int)(dys - smem) + 4 * co4;
+      for (int u = 0; u < Ue; ++u, xu += TP * a.cin, du += a.t_out * a.cot) {
+        int xrow = xu + rg * xstep, drow = du + rg * a.cot;
+        for (int t = rg; t < a.t_out; t += a.RG, xrow += a.RG * xstep, drow += a.RG * a.cot) {
+          const float4 d = ld4(smem + drow);
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            const float2 x = ld2(xrow + k * a.cin);
+            const float2 x = ld2(smem + xrow + k * a.cin);
             acc[k][0].x = fmaf(x.x, d.x, acc[k][0].x); acc[k][0].y = fmaf(x.x, d.y, acc[k][0].y);
             acc[k][0].z = fmaf(x.x, d.z, acc[k][0].z); acc[k][0].w = fmaf(x.x, d.w, acc[k][0].w);
             acc[k][1].x = fmaf(x.y, d.x, acc[k][1].x); acc[k][1].y = fmaf(x.y, d.y, acc[k][1].y);
@@ -513,9 +535,9 @@ int build_dw_table(tcr_handle* h) {
   return 0;
 }
 
-template <int K>
+template <int K, bool WSMEM>
 static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
-  auto kfn = conv_bwd_data_kernel<K>;
+  auto kfn = conv_bwd_data_kernel<K, WSMEM>;
 #ifndef TCR_EMU
   static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
   if (smem > smem_limit) {
@@ -545,8 +567,8 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   const int groups = (n + U - 1) / U;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
   switch (cv.k) {
-    case 3: return launch_bwd_data<3>(("dx:" + cv.name).c_str(), a, groups, smem, s);
-    case 9: return launch_bwd_data<9>(("dx:" + cv.name).c_str(), a, groups, smem, s);
+    case 9: return wsm ? launch_bwd_data<9, true>(("dx:" + cv.name).c_str(), a, groups, smem, s)
+                       : launch_bwd_data<9, false>(("dx:" + cv.name).c_str(), a, groups, smem, s);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }

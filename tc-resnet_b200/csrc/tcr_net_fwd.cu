@@ -18,7 +18,7 @@ constexpr int TM = 4;   // output rows per thread task
 // ------------------------------------------------------------------------------------------------
 // conv forward
 // ------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool WSMEM>
 __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -32,17 +32,18 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   // shared memory: [mbarrier | W (TMA bulk destination) | W_down | x tile | y tiles | scratch]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float* ws = smem + 4;                               // [K][cin][cout]   (only when a.w_smem)
-  const int wn = a.w_smem ? K * a.cin * a.cout : 0;
-  const int wdn = (a.w_smem && a.wd) ? a.cin * a.coutd : 0;
+  const int wn = WSMEM ? K * a.cin * a.cout : 0;
+  const int wdn = (WSMEM && a.wd) ? a.cin * a.coutd : 0;
   float* wsd = ws + wn;                               // [cin][coutd]
   float* xs = wsd + wdn;                              // [U][TP][CS]
   float* ys = xs + (size_t)a.U * TP * CS;             // [KS][Rmax][cout]
   float* ysd = ys + (size_t)a.KS * Rmax * a.cout;     // [Rmax][coutd]
   float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);
   float* smean = red + kThreads;
+  const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), xs_off = (int)(xs - smem);
 
   // ---- one TMA bulk copy brings the whole filter bank into shared memory while the tile is staged ----
-  if (a.w_smem) {
+  if (WSMEM) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
       }
     }
   }
-  if (a.w_smem) mbar_wait(bar, 0);
+  if (WSMEM) mbar_wait(bar, 0);
   __syncthreads();
 
   // ---- register-tiled conv: task = (k-slice, row tile of TM, 4 output channels) ----
@@ -107,42 +108,61 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     const int cg = tk % ncg;
     const int rt = (tk / ncg) % NRT;
     const int ks = is_down ? 0 : tk / (ncg * NRT);
-    const float* xr[TM];
+    // 32-bit float offsets from the shared-memory base: the inner loop is LDS.128 + FFMA with integer adds only
+    int xo[TM];
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
       const int r = imin(rt + i * NRT, R - 1);      // rows of a task are NRT apart: adjacent lanes -> adjacent rows
       const int u = r / a.t_out, t = r - u * a.t_out;
-      xr[i] = is_down ? xs + (size_t)(u * TP + a.pad_left + 2 * t) * CS : xs + (size_t)(u * TP + t * a.stride) * CS;
+      xo[i] = xs_off + (is_down ? (u * TP + a.pad_left + 2 * t) : (u * TP + t * a.stride)) * CS;
     }
     float4 acc[TM];
 #pragma unroll
     for (int i = 0; i < TM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int k_lo = is_down ? 0 : ks * KPS, k_hi = is_down ? 1 : k_lo + KPS;
     const int co_n = is_down ? a.coutd : a.cout;
-    const float* wbase = (a.w_smem ? (is_down ? wsd : ws) : (is_down ? a.wd : a.w)) + 4 * cg;
-    for (int k = k_lo; k < k_hi; ++k) {
-      const float* wk = wbase + (size_t)k * a.cin * co_n;
+    if (WSMEM) {
+      const int wb = (is_down ? wsd_off : ws_off) + 4 * cg;
+      for (int k = k_lo; k < k_hi; ++k) {
+        int wk = wb + k * a.cin * co_n;
+        const int xk = k * CS;
 #pragma unroll 2
-      for (int ci = 0; ci < a.cin; ci += 4) {
-        float4 w0, w1, w2, w3;
-        if (a.w_smem) {
-          w0 = ld4(wk + (ci + 0) * co_n); w1 = ld4(wk + (ci + 1) * co_n);
-          w2 = ld4(wk + (ci + 2) * co_n); w3 = ld4(wk + (ci + 3) * co_n);
-        } else {
-          w0 = ldg4(wk + (size_t)(ci + 0) * co_n); w1 = ldg4(wk + (size_t)(ci + 1) * co_n);
-          w2 = ldg4(wk + (size_t)(ci + 2) * co_n); w3 = ldg4(wk + (size_t)(ci + 3) * co_n);
-        }
+        for (int ci = 0; ci < a.cin; ci += 4, wk += 4 * co_n) {
+          const float4 w0 = ld4(smem + wk), w1 = ld4(smem + wk + co_n), w2 = ld4(smem + wk + 2 * co_n), w3 = ld4(smem + wk + 3 * co_n);
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          const float4 x = ld4(xr[i] + k * CS + ci);
-          acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y);
-          acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
-          acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y);
-          acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
-          acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y);
-          acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
-          acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y);
-          acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+          for (int i = 0; i < TM; ++i) {
+            const float4 x = ld4(smem + xo[i] + xk + ci);
+            acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y);
+            acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
+            acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y);
+            acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
+            acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y);
+            acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
+            acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y);
+            acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+          }
+        }
+      }
+    } else {
+      const float* wbase = (is_down ? a.wd : a.w) + 4 * cg;
+      for (int k = k_lo; k < k_hi; ++k) {
+        const float* wk = wbase + (size_t)k * a.cin * co_n;
+        const int xk = k * CS;
+#pragma unroll 2
+        for (int ci = 0; ci < a.cin; ci += 4, wk += 4 * co_n) {
+          const float4 w0 = ldg4(wk), w1 = ldg4(wk + co_n), w2 = ldg4(wk + 2 * co_n), w3 = ldg4(wk + 3 * co_n);
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            const float4 x = ld4(smem + xo[i] + xk + ci);
+            acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y);
+            acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
+            acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y);
+            acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
+            acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y);
+            acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
+            acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y);
+            acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+          }
         }
       }
     }
@@ -504,9 +524,9 @@ int net_alloc_workspace(tcr_handle* h) {
   return build_opt_segments(h);
 }
 
-template <int K>
+template <int K, bool WSMEM>
 static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
-  auto kfn = conv_fwd_kernel<K>;
+  auto kfn = conv_fwd_kernel<K, WSMEM>;
 #ifndef TCR_EMU
   static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
   if (smem > smem_limit) {
@@ -538,9 +558,10 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   const int groups = (n + U - 1) / U;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
   switch (cv.k) {
-    case 3: return launch_conv_fwd<3>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
-    case 9: return launch_conv_fwd<9>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
-    case 1: return launch_conv_fwd<1>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
+    case 3: return wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, groups, smem, s)
+                       : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
+    case 9: return wsm ? launch_conv_fwd<9, true>(("fwd:" + cv.name).c_str(), a, groups, smem, s)
+                       : launch_conv_fwd<9, false>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }
