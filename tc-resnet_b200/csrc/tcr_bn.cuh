@@ -126,91 +126,144 @@ __device__ __forceinline__ RowWalk row_walk(int tid, int nthreads, int c4n) {
   return w;
 }
 
-// "Last CTA finalises": returns true in exactly one CTA of the grid, after every other CTA's global
-// writes are visible.  The counter is reset for the next launch.
-__device__ __forceinline__ bool last_block_done(unsigned* counter, unsigned nblocks) {
-  __shared__ int s_last;
+// ---- two-level "last CTA finalises" tree -------------------------------------------------------------
+// A single CTA walking all G partials is a latency chain (measured: 22 us for G = 256).  Instead CTAs are
+// grouped by kFanIn: the last CTA of each group to finish combines that group's <= 16 partials into a level-2
+// record; the last group to finish combines the <= 16.. level-2 records into the table.  Every step reads at most
+// kFanIn (or ceil(G/kFanIn)) records per channel with independent loads; grouping and order are fixed, so the
+// result is deterministic.  counters: [0] = level-2 arrivals, [1 + g] = arrivals of group g (all self-resetting).
+constexpr int kFanIn = 16;
+
+// returns 0: nothing to do, 1: this CTA combines its group (level 1), then call tree_arrive_l2
+__device__ __forceinline__ int tree_arrive_l1(unsigned* counters, int cta, int ncta) {
+  __shared__ int s_flag;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(counter, 1u);
-    s_last = (prev == nblocks - 1);
-    if (s_last) *counter = 0;
+    const int grp = cta / kFanIn;
+    const int members = imin(kFanIn, ncta - grp * kFanIn);
+    const unsigned prev = atomicAdd(counters + 1 + grp, 1u);
+    s_flag = (prev == (unsigned)members - 1);
+    if (s_flag) counters[1 + grp] = 0;
   }
   __syncthreads();
-  if (s_last) __threadfence();
-  return s_last != 0;
+  const int f = s_flag;
+  if (f) __threadfence();
+  return f;
+}
+__device__ __forceinline__ int tree_arrive_l2(unsigned* counters, int ncta) {
+  __shared__ int s_flag2;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ngrp = (ncta + kFanIn - 1) / kFanIn;
+    const unsigned prev = atomicAdd(counters, 1u);
+    s_flag2 = (prev == (unsigned)ngrp - 1);
+    if (s_flag2) counters[0] = 0;
+  }
+  __syncthreads();
+  const int f = s_flag2;
+  if (f) __threadfence();
+  return f;
 }
 
-// Chan et al. combination of per-group (mean, M2) partials into the BN table (fp64, fixed order), spread over
-// the whole CTA: thread (seg, c) owns every ns-th group of channel c, so each thread issues a handful of
-// independent loads instead of one thread walking all groups (that serial chain was a 20-30 us kernel tail).
-// Requires C <= blockDim.x <= 512.
-__device__ __forceinline__ void bn_finalize(const BnFinalize& f, int groups, int U, int n, int t_out, float eps) {
-  __shared__ double s_part[512];
-  __shared__ double s_mean[128];
-  const int tid = threadIdx.x, C = f.c;
-  const int ns = imax(1, (int)blockDim.x / C);
-  const int seg = tid / C, c = tid - seg * C;
-  const bool act = seg < ns;
-  const double m_total = (double)n * t_out;
-  double s = 0.0;
-  if (act)
-    for (int g = seg; g < groups; g += ns)
-      s += (double)(imin(U, n - g * U) * t_out) * (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2);
-  if (act) s_part[seg * C + c] = s;
-  __syncthreads();
-  if (tid < C) {
-    double tot = 0.0;
-    for (int q = 0; q < ns; ++q) tot += s_part[q * C + tid];
-    s_mean[tid] = tot / m_total;
-  }
-  __syncthreads();
-  double m2 = 0.0;
-  if (act) {
-    const double mean = s_mean[c];
-    for (int g = seg; g < groups; g += ns) {
-      const double cnt = (double)(imin(U, n - g * U) * t_out);
-      const double d = (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2) - mean;
-      m2 += (double)__ldcg(f.fpart + ((size_t)g * C + c) * 2 + 1) + cnt * d * d;
+// Level 1: combine (mean, M2) partials of groups [g0, g1) of CTAs into l2[(grp*C + c)*3 + {cnt, mean, M2}] (fp64 math,
+// Chan et al.).  Level 2: combine the l2 records into the BN table.
+__device__ __forceinline__ void bn_combine_l1(const BnFinalize& f, int grp, int ncta, int U, int n, int t_out, float* l2) {
+  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
+  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
+    float mean_g[kFanIn], m2_g[kFanIn];
+#pragma unroll
+    for (int j = 0; j < kFanIn; ++j) {
+      const int g = imin(g0 + j, g1 - 1);
+      mean_g[j] = __ldcg(f.fpart + ((size_t)g * f.c + c) * 2);
+      m2_g[j] = __ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1);
     }
-    s_part[seg * C + c] = m2;
+    double cnt = 0.0, sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < kFanIn; ++j)
+      if (g0 + j < g1) {
+        const double k = (double)(imin(U, n - (g0 + j) * U) * t_out);
+        cnt += k;
+        sum += k * (double)mean_g[j];
+      }
+    const double mean = sum / cnt;
+    double m2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kFanIn; ++j)
+      if (g0 + j < g1) {
+        const double k = (double)(imin(U, n - (g0 + j) * U) * t_out);
+        const double d = (double)mean_g[j] - mean;
+        m2 += (double)m2_g[j] + k * d * d;
+      }
+    float* o = l2 + ((size_t)grp * f.c + c) * 3;
+    o[0] = (float)cnt; o[1] = (float)mean; o[2] = (float)m2;
   }
-  __syncthreads();
-  if (tid < C) {
-    double tot = 0.0;
-    for (int q = 0; q < ns; ++q) tot += s_part[q * C + tid];
-    const double var = tot / m_total;
+}
+__device__ __forceinline__ void bn_combine_l2(const BnFinalize& f, int ngrp, const float* l2, float eps) {
+  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
+    double cnt = 0.0, sum = 0.0;
+    for (int g = 0; g < ngrp; ++g) {
+      const double k = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3);
+      cnt += k;
+      sum += k * (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 1);
+    }
+    const double mean = sum / cnt;
+    double m2 = 0.0;
+    for (int g = 0; g < ngrp; ++g) {
+      const double k = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3);
+      const double d = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 1) - mean;
+      m2 += (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 2) + k * d * d;
+    }
+    const double var = m2 / cnt;
     const double rstd = 1.0 / sqrt(var + (double)eps);
-    f.bnf[tid] = (float)s_mean[tid];
-    f.bnf[C + tid] = (float)rstd;
-    f.bnf[2 * C + tid] = (float)((double)f.gamma[tid] * rstd);
-    f.bnf[3 * C + tid] = f.beta[tid];
-    f.var[tid] = (float)var;
+    f.bnf[c] = (float)mean;
+    f.bnf[f.c + c] = (float)rstd;
+    f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
+    f.bnf[3 * f.c + c] = f.beta[c];
+    f.var[c] = (float)var;
   }
-  __syncthreads();
+}
+// Sums of (sum dz, sum dz*xhat): level 1 -> l2[(grp*C + c)*2 + q], level 2 -> bsum[q*C + c]
+__device__ __forceinline__ void bwdsum_combine_l1(const BwdSumFinalize& f, int grp, int ncta, float* l2) {
+  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
+  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
+    float v[kFanIn];
+#pragma unroll
+    for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(f.bpart + (size_t)imin(g0 + j, g1 - 1) * f.c * 2 + i);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < kFanIn; ++j)
+      if (g0 + j < g1) s += (double)v[j];
+    l2[(size_t)grp * f.c * 2 + i] = (float)s;
+  }
+}
+__device__ __forceinline__ void bwdsum_combine_l2(const BwdSumFinalize& f, int ngrp, const float* l2) {
+  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
+    double s = 0.0;
+    for (int g = 0; g < ngrp; ++g) s += (double)__ldcg(l2 + (size_t)g * f.c * 2 + i);
+    f.bsum[(i & 1) * f.c + (i >> 1)] = (float)s;
+  }
 }
 
-// Sum of per-group (sum dz, sum dz*xhat) partials, same thread layout (2C columns).
-__device__ __forceinline__ void bwdsum_finalize(const BwdSumFinalize& f, int groups) {
-  __shared__ double s_part[512];
-  const int tid = threadIdx.x, C2 = 2 * f.c;
-  const int ns = imax(1, (int)blockDim.x / C2);
-  const int seg = tid / C2, i = tid - seg * C2;
-  const bool act = seg < ns;
-  if (act) {
-    const int c = i >> 1, q = i & 1;
+// Scalar (loss) variant of the tree: loss_part[G] -> l2[ngrp] -> *out
+__device__ __forceinline__ void scalar_combine_l1(const float* part, int grp, int ncta, float* l2) {
+  __shared__ float s_v[kFanIn];
+  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
+  if (threadIdx.x < kFanIn) s_v[threadIdx.x] = (g0 + (int)threadIdx.x < g1) ? __ldcg(part + g0 + threadIdx.x) : 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int g = seg; g < groups; g += ns) s += (double)__ldcg(f.bpart + ((size_t)g * f.c + c) * 2 + q);
-    s_part[seg * C2 + i] = s;
+    for (int j = 0; j < kFanIn; ++j) s += (double)s_v[j];
+    l2[grp] = (float)s;
   }
-  __syncthreads();
-  if (tid < C2) {
-    double tot = 0.0;
-    for (int q = 0; q < ns; ++q) tot += s_part[q * C2 + tid];
-    f.bsum[(tid & 1) * f.c + (tid >> 1)] = (float)tot;
+}
+__device__ __forceinline__ void scalar_combine_l2(const float* l2, int ngrp, float* out) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int g = 0; g < ngrp; ++g) s += (double)__ldcg(l2 + g);
+    *out = (float)s;
   }
-  __syncthreads();
 }
 
 // Per-channel (mean, M2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}].

@@ -78,6 +78,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 __device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncthreads(); }  // all threads call it
 #endif
 
+// Debug timeline: thread 0 of a CTA stamps %globaltimer (ns) into tl[cta * 8 + slot] when tl != nullptr.
+#ifndef TCR_EMU
+__device__ __forceinline__ void tl_stamp(long long* tl, int cta, int slot) {
+  if (tl && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[(size_t)cta * 8 + slot] = (long long)t;
+  }
+}
+#else
+__device__ __forceinline__ void tl_stamp(long long*, int, int) {}
+#endif
+
 // Counter-based RNG for dropout (TF's RNG is not reproducible; parity runs inject a mask instead).
 __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);

@@ -35,12 +35,14 @@ struct BnFinalize {         // what the last CTA of a producer kernel needs to f
   const float* fpart;       // [G][C][2] (mean, M2)
   float* bnf;               // [4][C]
   float* var;               // [C] biased batch variance (moving-average update reads it)
+  float* l2;                // [ceil(G/16)][C][3] level-2 records of the finalize tree
   int c;
 };
 
 struct BwdSumFinalize {     // last CTA: sum partial (sum dz, sum dz*xhat) over groups
   const float* bpart;       // [G][C][2]
   float* bsum;              // [2][C]
+  float* l2;                // [ceil(G/16)][C][2] level-2 records of the finalize tree
   int c;
 };
 
@@ -56,6 +58,7 @@ struct FwdArgs {
   const float* w; float* y; float* fpart;
   int cout, stride, t_out, pad_left, KS;
   int w_smem;               // 1: filter bank(s) staged in shared memory by one TMA bulk copy
+  long long* tl;            // debug timeline (nullptr in production)
   // optional down conv (k=1, stride 2, no padding, same t_out)
   const float* wd; float* yd; float* fpartd; int coutd;
   // training statistics
@@ -87,6 +90,7 @@ struct HeadArgs {
   unsigned* counter;
   BwdSumFinalize finb, find;
   float* loss_out;          // [1] sum over utterances of CE (finalised by the last CTA)
+  float* loss_l2;           // [ceil(Gh/16)] level-2 loss sums
 };
 
 // ---------------- backward-data kernel ----------------

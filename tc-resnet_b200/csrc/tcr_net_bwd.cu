@@ -251,9 +251,14 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     if (qd < 2) a.bpartp[((size_t)blockIdx.x * a.cin + c) * 2 + qd] = s;
     else a.bpartpd[((size_t)blockIdx.x * a.cin + c) * 2 + (qd - 2)] = s;
   }
-  if (last_block_done(a.counter, gridDim.x)) {
-    bwdsum_finalize(a.finp, gridDim.x);
-    if (nq == 4) bwdsum_finalize(a.finpd, gridDim.x);
+  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
+    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
+    bwdsum_combine_l1(a.finp, grp, gridDim.x, a.finp.l2);
+    if (nq == 4) bwdsum_combine_l1(a.finpd, grp, gridDim.x, a.finpd.l2);
+    if (tree_arrive_l2(a.counter, gridDim.x)) {
+      bwdsum_combine_l2(a.finp, ngrp, a.finp.l2);
+      if (nq == 4) bwdsum_combine_l2(a.finpd, ngrp, a.finpd.l2);
+    }
   }
 }
 
@@ -383,9 +388,10 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
 // All layers' weight gradients in ONE launch: virtual CTA -> (layer, output-channel tile, row chunk) through a
 // static table, so ~600 CTAs of 256 threads keep every SM busy instead of ten serial 64-CTA launches.
 __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
-                                                                const float* __restrict__ feat) {
+                                                                const float* __restrict__ feat, long long* tl) {
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
+  tl_stamp(tl, 4096 + blockIdx.x, 0);
   int l = 0;
   while (l + 1 < nlayers && (int)blockIdx.x >= layers[l + 1].cta_begin) ++l;
   const DwLayer L = layers[l];
@@ -398,9 +404,12 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer
   a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.stride = L.stride; a.t_in = L.t_in; a.t_out = L.t_out;
   a.pad_left = L.pad_left; a.cot = L.cot; a.RG = L.RG; a.R = L.R; a.UB = L.UB; a.dwpart = L.dwpart;
   const int bx = local % ncot, by = local / ncot;
+  tl_stamp(tl, 4096 + blockIdx.x, 1);
   if (L.k == 9) dw_body<9>(a, bx, by, smem);
   else if (L.k == 3) dw_body<3>(a, bx, by, smem);
   else dw_body<1>(a, bx, by, smem);
+  tl_stamp(tl, 4096 + blockIdx.x, 2);
+  if (tl && threadIdx.x == 0) { tl[(size_t)(4096 + blockIdx.x) * 8 + 3] = l; tl[(size_t)(4096 + blockIdx.x) * 8 + 4] = (long long)by; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,22 +478,21 @@ static size_t bwd_weight_smem(const ConvPlan& cv, int cot, int RG, int UB) {
 // the tile that keeps most threads busy, chunks of roughly equal work (~0.7 M MAC) so all layers together give a
 // few waves of CTAs.
 void plan_bwd_weight(tcr_handle* h) {
-  const double target_macs = 0.7e6;
+  // Measured (tools/timeline.py): tiny output-channel tiles re-stage the same x tile many times and need a huge cross-group
+  // reduction; long chunks of K=1 layers run for 150 us on a handful of CTAs.  So: the LARGEST tile that fits 256 threads, at
+  // most 4 row groups, and chunks bounded both in MACs and in utterances so that no CTA runs much longer than the others.
+  const double target_macs = 0.5e6;
   for (auto& cv : h->convs) {
-    int cot = 4, best_workers = 0;
-    for (int c = 4; c <= cv.cout; c += 4) {
-      if (cv.cout % c) continue;
-      const int np = (cv.cin / 2) * (c / 4);
-      if (np > kDwThreads) continue;
-      const int workers = (kDwThreads / np) * np;
-      if (workers >= best_workers) { best_workers = workers; cot = c; }
-    }
+    int cot = 4;
+    for (int c = 4; c <= cv.cout; c += 4)
+      if (cv.cout % c == 0 && (cv.cin / 2) * (c / 4) <= kDwThreads) cot = c;
     const int np = (cv.cin / 2) * (cot / 4);
-    int RG = std::max(1, kDwThreads / np);
+    int RG = std::max(1, std::min(4, kDwThreads / np));
     const double macs_per_utt = (double)cv.t_out * cv.k * cv.cin * cot;
-    int upc = std::max(1, (int)(target_macs / macs_per_utt));          // utterances per chunk
-    int R = std::max(1, std::min(64, (h->cfg.max_batch + upc - 1) / upc));
-    int UB = 16;
+    int upc = std::max(1, std::min(8, (int)(target_macs / macs_per_utt)));     // utterances per chunk
+    int R = std::max(1, (h->cfg.max_batch + upc - 1) / upc);
+    R = std::min(R, 128);
+    int UB = 8;
     while (UB > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudgetW) --UB;
     while (RG > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudget) --RG;
     cv.dw_cot = cot;
@@ -563,7 +571,7 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.has_down = dn ? 1 : 0;
   a.wd = dn ? dn->wT : nullptr;
   a.coutd = dn ? dn->cout : 0;
-  a.counter = h->d_counters + slot;
+  a.counter = h->d_counters + (size_t)slot * h->counter_stride;
   const int groups = (n + U - 1) / U;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
   switch (cv.k) {
@@ -599,7 +607,7 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       a.dy = make_dy(cb, b.gblk, 0, n);
       a.epi_kind = 1;
       a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
-      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.cout};
+      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.bl2, ca.cout};
       a.finpd = a.finp;
       int rc = bwd_data(h, cb, nullptr, a, params, n, slot++, s);
       if (rc) return rc;
@@ -617,19 +625,19 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
         a.epi_kind = 2;
         a.out_prev = pb.out;
         a.yp = pcb.y; a.bnfp = pcb.bnf; a.bpartp = pcb.bpart;
-        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.cout};
+        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.bl2, pcb.cout};
         a.finpd = a.finp;
         if (pb.down >= 0) {
           ConvPlan& pd = h->convs[pb.down];
           a.ypd = pd.y; a.bnfpd = pd.bnf; a.bpartpd = pd.bpart;
-          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.cout};
+          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.bl2, pd.cout};
         }
         a.gprev = pb.gblk;
       } else {
         ConvPlan& c0 = h->convs[0];
         a.epi_kind = 1;
         a.yp = c0.y; a.bnfp = c0.bnf; a.bpartp = c0.bpart; a.gprev = c0.g;
-        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.cout};
+        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.bl2, c0.cout};
         a.finpd = a.finp;
       }
       int rc = bwd_data(h, ca, dn, a, params, n, slot++, s);
@@ -646,7 +654,7 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       smem_limit = h->dw_smem;
     }
 #endif
-    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat);
+    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat, h->d_timeline);
   }
   return 0;
 }

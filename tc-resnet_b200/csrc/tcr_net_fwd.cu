@@ -8,6 +8,8 @@
 //   head_kernel         : residual + ReLU + global average pool + dropout + fc + softmax + cross-entropy and,
 //                         for training, dlogits -> gradient of the last block + fc weight-gradient partials.
 // A CTA owns U whole utterances, so SAME padding is a few zero rows of the shared-memory tile.
+#include <stdlib.h>
+
 #include "tcr_bn.cuh"
 #include "tcr_net.h"
 
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   float* smean = red + kThreads;
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), xs_off = (int)(xs - smem);
 
+  tl_stamp(a.tl, blockIdx.x, 0);
   // ---- one TMA bulk copy brings the whole filter bank into shared memory while the tile is staged ----
   if (WSMEM) {
     if (tid == 0) mbar_init(bar, 1);
@@ -90,8 +93,10 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
       }
     }
   }
+  tl_stamp(a.tl, blockIdx.x, 1);
   if (WSMEM) mbar_wait(bar, 0);
   __syncthreads();
+  tl_stamp(a.tl, blockIdx.x, 2);
 
   // ---- register-tiled conv: task = (k-slice, row tile of TM, 4 output channels) ----
   const int R = Ue * a.t_out;
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     }
   }
   __syncthreads();
+  tl_stamp(a.tl, blockIdx.x, 3);
 
   // ---- epilogue: sum k-slices in fixed order, coalesced store of the pre-BN output ----
   const size_t grow0 = (size_t)u0 * a.t_out;
@@ -187,12 +193,20 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     for (int idx = tid; idx < R * NCGD; idx += kThreads) st4(a.yd + grow0 * a.coutd + (size_t)idx * 4, ld4(ysd + (size_t)idx * 4));
   if (!a.train) return;
   __syncthreads();
+  tl_stamp(a.tl, blockIdx.x, 4);
   tile_stats(ys, R, a.cout, red, smean, a.fpart + (size_t)blockIdx.x * a.cout * 2);
   if (a.wd) tile_stats(ysd, R, a.coutd, red, smean, a.fpartd + (size_t)blockIdx.x * a.coutd * 2);
-  if (last_block_done(a.counter, gridDim.x)) {
-    bn_finalize(a.fin, gridDim.x, a.U, a.n, a.t_out, a.eps);
-    if (a.wd) bn_finalize(a.find, gridDim.x, a.U, a.n, a.t_out, a.eps);
+  tl_stamp(a.tl, blockIdx.x, 5);
+  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
+    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
+    bn_combine_l1(a.fin, grp, gridDim.x, a.U, a.n, a.t_out, a.fin.l2);
+    if (a.wd) bn_combine_l1(a.find, grp, gridDim.x, a.U, a.n, a.t_out, a.find.l2);
+    if (tree_arrive_l2(a.counter, gridDim.x)) {
+      bn_combine_l2(a.fin, ngrp, a.fin.l2, a.eps);
+      if (a.wd) bn_combine_l2(a.find, ngrp, a.find.l2, a.eps);
+    }
   }
+  tl_stamp(a.tl, blockIdx.x, 6);
 }
 
 // Eval mode: BN tables from the moving statistics (bn_forward with is_training=False).
@@ -306,10 +320,9 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
         for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
         a.loss_part[blockIdx.x] = s;
       }
-      if (last_block_done(a.counter, gridDim.x) && threadIdx.x == 0) {
-        double s = 0.0;
-        for (unsigned g = 0; g < gridDim.x; ++g) s += (double)__ldcg(a.loss_part + g);
-        *a.loss_out = (float)s;
+      if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
+        scalar_combine_l1(a.loss_part, blockIdx.x / kFanIn, gridDim.x, a.loss_l2);
+        if (tree_arrive_l2(a.counter, gridDim.x)) scalar_combine_l2(a.loss_l2, (gridDim.x + kFanIn - 1) / kFanIn, a.loss_out);
       }
     }
     return;
@@ -391,13 +404,15 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
     for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
     a.loss_part[blockIdx.x] = s;
   }
-  if (last_block_done(a.counter, gridDim.x)) {
-    bwdsum_finalize(a.finb, gridDim.x);
-    if (a.ydn) bwdsum_finalize(a.find, gridDim.x);
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (unsigned g = 0; g < gridDim.x; ++g) s += (double)__ldcg(a.loss_part + g);
-      *a.loss_out = (float)s;
+  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
+    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
+    bwdsum_combine_l1(a.finb, grp, gridDim.x, a.finb.l2);
+    if (a.ydn) bwdsum_combine_l1(a.find, grp, gridDim.x, a.find.l2);
+    scalar_combine_l1(a.loss_part, grp, gridDim.x, a.loss_l2);
+    if (tree_arrive_l2(a.counter, gridDim.x)) {
+      bwdsum_combine_l2(a.finb, ngrp, a.finb.l2);
+      if (a.ydn) bwdsum_combine_l2(a.find, ngrp, a.find.l2);
+      scalar_combine_l2(a.loss_l2, ngrp, a.loss_out);
     }
   }
 }
@@ -498,6 +513,8 @@ int net_alloc_workspace(tcr_handle* h) {
     WS(ws_alloc(h, &cv.fpart, (size_t)h->g_max * cv.cout * 2));
     WS(ws_alloc(h, &cv.bpart, (size_t)std::max(h->g_max, h->head_groups_max) * cv.cout * 2));
     WS(ws_alloc(h, &cv.bsum, 2 * (size_t)cv.cout));
+    WS(ws_alloc(h, &cv.fl2, (size_t)(h->g_max / kFanIn + 1) * cv.cout * 3));
+    WS(ws_alloc(h, &cv.bl2, (size_t)(h->g_max / kFanIn + 1) * cv.cout * 2));
     WS(ws_alloc(h, &cv.dwpart, (size_t)cv.dw_R * cv.wnumel()));
     WS(ws_alloc(h, &cv.wT, (size_t)cv.wnumel()));
   }
@@ -515,9 +532,15 @@ int net_alloc_workspace(tcr_handle* h) {
   WS(ws_alloc(h, &h->d_dwfc_part, (size_t)h->head_groups_max * h->c_last * h->cfg.num_classes));
   WS(ws_alloc(h, &h->d_grads, (size_t)h->n_train));
   WS(ws_alloc(h, &h->d_l2part, 4096));
-  WS(ws_alloc(h, &h->d_counters, 64));
-  if (cudaMemset(h->d_counters, 0, 64 * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
+  h->counter_stride = 2 + h->g_max / kFanIn;
+  WS(ws_alloc(h, &h->d_counters, (size_t)64 * h->counter_stride));
+  if (cudaMemset(h->d_counters, 0, (size_t)64 * h->counter_stride * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
+  WS(ws_alloc(h, &h->d_loss_l2, (size_t)h->head_groups_max / kFanIn + 2));
   WS(ws_alloc(h, &h->d_hyper, 1));
+  if (getenv("TCR_DEBUG_TIMELINE")) {
+    WS(ws_alloc(h, &h->d_timeline, (size_t)8 * 8192));
+    cudaMemset(h->d_timeline, 0, sizeof(long long) * 8 * 8192);
+  }
   if (cudaMallocHost((void**)&h->h_hyper, sizeof(Hyper)) != cudaSuccess) return TCR_ERR_CUDA;
   int rc = build_dw_table(h);
   if (rc) return rc;
@@ -547,13 +570,14 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.cout = cv.cout; a.stride = cv.stride; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
   a.train = training ? 1 : 0;
-  a.counter = h->d_counters + counter_slot;
+  a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline : nullptr;
+  a.counter = h->d_counters + (size_t)counter_slot * h->counter_stride;
   a.eps = h->cfg.bn_epsilon;
-  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.cout};
+  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.fl2, cv.cout};
   a.find = a.fin;
   if (dn) {
     a.wd = params + dn->w_off; a.yd = dn->y; a.fpartd = dn->fpart; a.coutd = dn->cout;
-    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->cout};
+    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->fl2, dn->cout};
   }
   const int groups = (n + U - 1) / U;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
@@ -642,9 +666,10 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.yb = cb.y; ha.bnfb = cb.bnf; ha.bpartb = cb.bpart;
       ha.ydn = dn ? dn->y : nullptr; ha.bnfd = dn ? dn->bnf : nullptr; ha.bpartd = dn ? dn->bpart : nullptr;
       ha.dwfc_part = h->d_dwfc_part;
-      ha.counter = h->d_counters + slot++;
-      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.cout};
-      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->cout} : ha.finb;
+      ha.counter = h->d_counters + (size_t)(slot++) * h->counter_stride;
+      ha.loss_l2 = h->d_loss_l2;
+      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.bl2, cb.cout};
+      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->bl2, dn->cout} : ha.finb;
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       const size_t smem = (size_t)(kHeadWarps * 4 * lb.c + kHeadWarps * lb.c + kHeadWarps * ha.classes + kHeadWarps) * 4;

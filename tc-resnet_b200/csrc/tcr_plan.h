@@ -22,6 +22,8 @@ struct ConvPlan {
   float* fpart = nullptr;      // [G][cout][2]
   float* bpart = nullptr;      // [G][cout][2]
   float* bsum = nullptr;       // [2][cout]
+  float* fl2 = nullptr;        // level-2 records of the forward-statistics tree
+  float* bl2 = nullptr;        // level-2 records of the backward-sum tree
   float* dwpart = nullptr;     // [R][k*cin*cout]
   float* wT = nullptr;         // [k][cout][cin] transposed filter bank (refreshed per backward pass)
   int dw_R = 1, dw_cot = 0, dw_RG = 1, dw_UB = 1;
@@ -58,7 +60,7 @@ struct tcr_handle {
   float* d_loss_part = nullptr; float* d_loss = nullptr; float* d_dwfc_part = nullptr;
   float* d_grads = nullptr;
   float* d_l2part = nullptr;
-  unsigned* d_counters = nullptr;
+  unsigned* d_counters = nullptr; int counter_stride = 0; float* d_loss_l2 = nullptr;
   tcr::Hyper* d_hyper = nullptr; tcr::Hyper* h_hyper = nullptr;
   tcr::OptSegment* d_segs = nullptr; int n_segs = 0;
   tcr::MovingSegment* d_msegs = nullptr; int n_msegs = 0;
@@ -68,4 +70,5 @@ struct tcr_handle {
   // data-parallel
   void* comm = nullptr; int rank = 0, world = 1;
   int last_n = 0;
+  long long* d_timeline = nullptr;   // TCR_DEBUG_TIMELINE=1: per-CTA phase stamps (fwd kernels: 8 slots per CTA; dw: after)
 };

@@ -76,10 +76,10 @@ class TorchBackend:
 
     def view(self, ptr, numel):
         out = self.torch.empty(numel, dtype=self.torch.float32, device=self.dev)
-        cudart = self.torch.cuda.cudart()
         self.torch.cuda.synchronize()
-        err = cudart.cudaMemcpy(out.data_ptr(), ptr, numel * 4, 3)   # device-to-device
-        assert int(err[0] if isinstance(err, tuple) else err) == 0
+        rt = C.CDLL("libcudart.so.12")                                # already mapped by torch
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        assert rt.cudaMemcpy(out.data_ptr(), ptr, numel * 4, 3) == 0   # device-to-device
         return out.cpu().numpy()
 
     def sync(self):
