@@ -457,13 +457,14 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
     TCR_TRY(tcr_mfcc_forward(h, a->input, h->d_feat, a->n, stream));
     feat = h->d_feat;
   }
+  if (persist_enabled(h)) rec_begin(h);      // record the step's phases; net_update launches the persistent kernel
   int rc = net_forward(h, feat, a->params, nullptr, a->n, true, a->dropout_seed, a->dropout_mask, a->onehot,
                        a->weight_decay, a->logits, a->probs, nullptr, /*backward=*/true, s);
-  if (rc) return fail(rc, "forward launch failed: %s", g_err);
+  if (rc) { rec_abort(h); return fail(rc, "forward launch failed: %s", g_err); }
   rc = net_backward(h, feat, a->params, a->n, s);
-  if (rc) return fail(rc, "backward launch failed: %s", g_err);
+  if (rc) { rec_abort(h); return fail(rc, "backward launch failed: %s", g_err); }
   rc = net_update(h, a, s);
-  if (rc) return fail(rc, "update launch failed: %s", g_err);
+  if (rc) { rec_abort(h); return fail(rc, "update launch failed: %s", g_err); }
   TCR_CUDA(cudaGetLastError());
   h->last_n = a->n;
   return TCR_OK;

@@ -13,16 +13,16 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 
 // z = (y - mean) * scale + beta
 __device__ __forceinline__ float4 bn_apply4(float4 y, const float* __restrict__ bnf, int C, int c) {
-  const float4 mean = ldg4(bnf + c), scale = ldg4(bnf + 2 * C + c), beta = ldg4(bnf + 3 * C + c);
+  const float4 mean = ldc4(bnf + c), scale = ldc4(bnf + 2 * C + c), beta = ldc4(bnf + 3 * C + c);
   return make_float4(fmaf(y.x - mean.x, scale.x, beta.x), fmaf(y.y - mean.y, scale.y, beta.y),
                      fmaf(y.z - mean.z, scale.z, beta.z), fmaf(y.w - mean.w, scale.w, beta.w));
 }
 __device__ __forceinline__ float bn_apply1(float y, const float* __restrict__ bnf, int C, int c) {
-  return fmaf(y - __ldg(bnf + c), __ldg(bnf + 2 * C + c), __ldg(bnf + 3 * C + c));
+  return fmaf(y - ldc1(bnf + c), ldc1(bnf + 2 * C + c), ldc1(bnf + 3 * C + c));
 }
 // xhat = (y - mean) * rstd
 __device__ __forceinline__ float4 bn_xhat4(float4 y, const float* __restrict__ bnf, int C, int c) {
-  const float4 mean = ldg4(bnf + c), rstd = ldg4(bnf + C + c);
+  const float4 mean = ldc4(bnf + c), rstd = ldc4(bnf + C + c);
   return make_float4((y.x - mean.x) * rstd.x, (y.y - mean.y) * rstd.y, (y.z - mean.z) * rstd.z, (y.w - mean.w) * rstd.w);
 }
 
@@ -37,15 +37,15 @@ __device__ __forceinline__ float4 act_load4(const ActSrc& s, size_t ofs, int C, 
 __device__ __forceinline__ float4 dy_load4(const DySrc& d, size_t ofs, int C, int c) {
   float4 dz = ld4(d.dz + ofs);
   const float4 y = ld4(d.y + ofs);
-  const float4 mean = ldg4(d.bnf + c), rstd = ldg4(d.bnf + C + c), scale = ldg4(d.bnf + 2 * C + c);
+  const float4 mean = ldc4(d.bnf + c), rstd = ldc4(d.bnf + C + c), scale = ldc4(d.bnf + 2 * C + c);
   if (d.mask_relu) {
-    const float4 beta = ldg4(d.bnf + 3 * C + c);
+    const float4 beta = ldc4(d.bnf + 3 * C + c);
     if (fmaf(y.x - mean.x, scale.x, beta.x) <= 0.f) dz.x = 0.f;
     if (fmaf(y.y - mean.y, scale.y, beta.y) <= 0.f) dz.y = 0.f;
     if (fmaf(y.z - mean.z, scale.z, beta.z) <= 0.f) dz.z = 0.f;
     if (fmaf(y.w - mean.w, scale.w, beta.w) <= 0.f) dz.w = 0.f;
   }
-  const float4 s1 = ldg4(d.bsum + c), s2 = ldg4(d.bsum + C + c);
+  const float4 s1 = ldc4(d.bsum + c), s2 = ldc4(d.bsum + C + c);
   const float im = d.inv_m;
   float4 r;
   r.x = scale.x * (dz.x - s1.x * im - (y.x - mean.x) * rstd.x * (s2.x * im));
@@ -61,7 +61,7 @@ __device__ __forceinline__ float4 dy_load4(const DySrc& d, size_t ofs, int C, in
 struct Chan4 { float4 mean, rstd, scale, beta; };
 __device__ __forceinline__ Chan4 chan4_load(const float* __restrict__ bnf, int C, int c) {
   Chan4 k;
-  k.mean = ldg4(bnf + c); k.rstd = ldg4(bnf + C + c); k.scale = ldg4(bnf + 2 * C + c); k.beta = ldg4(bnf + 3 * C + c);
+  k.mean = ldc4(bnf + c); k.rstd = ldc4(bnf + C + c); k.scale = ldc4(bnf + 2 * C + c); k.beta = ldc4(bnf + 3 * C + c);
   return k;
 }
 __device__ __forceinline__ float4 chan4_bn(const Chan4& k, float4 y) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ Dy4 dy4_make(const DySrc& d, int C, int c) {
   Dy4 r;
   r.dz = d.dz; r.y = d.y; r.mask = d.mask_relu;
   r.k = chan4_load(d.bnf, C, c);
-  const float4 s1 = ldg4(d.bsum + c), s2 = ldg4(d.bsum + C + c);
+  const float4 s1 = ldc4(d.bsum + c), s2 = ldc4(d.bsum + C + c);
   const float im = d.inv_m;
   r.s1m = make_float4(s1.x * im, s1.y * im, s1.z * im, s1.w * im);
   r.s2m = make_float4(s2.x * im, s2.y * im, s2.z * im, s2.w * im);

@@ -19,6 +19,14 @@ void prof_end(cudaStream_t s);
     tcr::prof_end((cudaStream_t)(stream));                                       \
   } while (0)
 #define TCR_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+// cooperative launch (all CTAs co-resident): kernel arguments are packed into an array of pointers
+#define TCR_LAUNCH_COOP(name, kernel, grid, block, smem, stream, arg)                                                  \
+  do {                                                                                                                 \
+    tcr::prof_begin((name), (cudaStream_t)(stream));                                                                   \
+    void* coop_args_[] = {(void*)&(arg)};                                                                              \
+    cudaLaunchCooperativeKernel((const void*)(kernel), (grid), (block), coop_args_, (smem), (cudaStream_t)(stream));   \
+    tcr::prof_end((cudaStream_t)(stream));                                                                             \
+  } while (0)
 #endif
 
 namespace tcr {
@@ -27,6 +35,9 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+// L2-coherent loads for per-channel tables written earlier in the SAME launch (persistent kernel): never the .nc path
+__device__ __forceinline__ float4 ldc4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ldc1(const float* p) { return __ldcg(p); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -76,6 +87,37 @@ __device__ __forceinline__ void mbar_init(uint64_t*, int) {}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncthreads(); }  // all threads call it
+#endif
+
+// mbarrier state carried across uses: a standalone kernel initialises it on first use; the persistent step kernel
+// initialises once and flips `parity` after every completed transaction phase.
+struct MbarCtx { uint64_t* bar; uint32_t parity; bool ready; };
+#ifndef TCR_EMU
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+__device__ __forceinline__ void fence_proxy_async() {}
+#endif
+
+// Grid-wide barrier for the cooperative (co-resident) persistent kernel: monotonically increasing arrival counter,
+// zeroed by the host before the launch.  Same fence/atomic/spin pattern as cooperative_groups::grid::sync().
+#ifndef TCR_EMU
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++epoch;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * nblocks;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+#else
+__device__ __forceinline__ void grid_barrier(unsigned*, unsigned, unsigned& epoch) { ++epoch; emu::gridsync(); }
 #endif
 
 // Debug timeline: thread 0 of a CTA stamps %globaltimer (ns) into tl[cta * 8 + slot] when tl != nullptr.

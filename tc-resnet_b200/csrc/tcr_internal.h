@@ -160,6 +160,33 @@ struct MovingSegment {      // one BN layer
   int t_out;                // rows per utterance: M = n * t_out, unbiased variance = var * M / (M - 1)
 };
 
+struct GradArgs {           // gradient finalisation (sum of partials + weight decay -> flat gradient)
+  const OptSegment* segs; int nsegs; int64_t total; int fc_seg; const float* fc_part; int fc_R;
+  const float* params; float weight_decay; float* grads; float* l2part;
+};
+struct WtLayer { int64_t w_off; float* wT; int k, cin, cout; int64_t begin; };
+struct WtArgs { WtLayer layer[kMaxConvs]; int nlayers; int64_t total; const float* params; };
+
+// ---------------- persistent step kernel: phase program ----------------
+enum { PH_TRANSPOSE = 0, PH_FWD, PH_FIN_FWD, PH_HEAD, PH_BWD, PH_FIN_BWD, PH_DW, PH_GRAD };
+struct Phase { int kind, idx, nvb, k, wsmem; };
+struct FinFwd { BnFinalize f[2]; int nf, G, U, n, t_out; float eps; };
+struct FinBwd { BwdSumFinalize f[2]; int nf, G; const float* loss_part; float* loss_out; };
+constexpr int kMaxFwdPh = 16, kMaxBwdPh = 16, kMaxPhases = 80;
+struct StepProgram {
+  int nphases, nfwd, nbwd, nfinb;
+  Phase phase[kMaxPhases];
+  FwdArgs fwd[kMaxFwdPh];
+  FinFwd finf[kMaxFwdPh];
+  HeadArgs head;
+  BwdDataArgs bwd[kMaxBwdPh];
+  FinBwd finb[kMaxBwdPh + 1];
+  WtArgs wt;
+  const DwLayer* dw_layers; int n_dw_layers; int n; const float* feat; long long* tl;
+  GradArgs grad;
+  unsigned* barrier;
+};
+
 struct Hyper {              // device-resident hyper-parameters (graph replays read fresh values)
   float lr, momentum, weight_decay, one_minus_decay;
   float grad_scale;         // 1 / world_size

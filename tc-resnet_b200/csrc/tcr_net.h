@@ -24,6 +24,18 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s);
 int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int n, float* losses, cudaStream_t s);
 int head_groups(int n);
 
+// Persistent step kernel (tcr_persist.cu): the launch sites record phases instead of launching while h->rec != nullptr.
+bool persist_enabled(tcr_handle* h);
+void rec_begin(tcr_handle* h);
+void rec_abort(tcr_handle* h);
+void rec_fwd(tcr_handle* h, const FwdArgs& a, int k, int wsm, int groups, size_t smem);
+void rec_head(tcr_handle* h, const HeadArgs& a, int groups, size_t smem);
+void rec_bwd(tcr_handle* h, const BwdDataArgs& a, int k, int wsm, int groups, size_t smem);
+void rec_transpose(tcr_handle* h, const WtArgs& w);
+void rec_dw(tcr_handle* h, int n, const float* feat);
+void rec_grad(tcr_handle* h, const GradArgs& g, int blocks);
+int rec_launch(tcr_handle* h, cudaStream_t s);
+
 int measure_fp32_peak(tcr_handle* h, double* tflops, cudaStream_t s);
 
 // NCCL through dlopen (tcr_comm.cu): no link-time dependency, the torch-bundled libnccl is reused when loaded.

@@ -29,12 +29,12 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(
 // backward data
 // ------------------------------------------------------------------------------------------------
 template <int K, bool WSMEM>
-__global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) {
-  TCR_DYNAMIC_SMEM(smem_raw);
+__device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const int vb, const int nvb, unsigned char* smem_raw,
+                                                   MbarCtx& mb, const bool tree) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
   const int S = a.stride;
-  const int u0 = blockIdx.x * a.U;
+  const int u0 = vb * a.U;
   const int Ue = imin(a.U, a.n - u0);
   const int COS = chan_stride(a.cout);
   const int PLd = (K - 1) / S;
@@ -43,15 +43,19 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   const int COSD = a.has_down ? chan_stride(a.coutd) : 0;
   const int Rin_max = a.U * a.t_in;
   // shared memory: [mbarrier | W | W_down | dy tile | dy_down tile | dx planes | scratch]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* bar = mb.bar;
   float* ws = smem + 4;
   const int wn = WSMEM ? K * a.cin * a.cout : 0;
   const int wdn = (WSMEM && a.has_down) ? a.cin * a.coutd : 0;
   float* wsd = ws + wn;
   if (WSMEM) {
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    if (!mb.ready) {
+      if (tid == 0) mbar_init(bar, 1);
+      __syncthreads();
+      mb.ready = true;
+    }
     if (tid == 0) {
+      fence_proxy_async();
       mbar_expect_tx(bar, (uint32_t)(wn + wdn) * 4u);
       tma_load_1d(ws, a.w, (uint32_t)wn * 4u, bar);
       if (wdn) tma_load_1d(wsd, a.wd, (uint32_t)wdn * 4u, bar);
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
       }
     }
   }
-  if (WSMEM) mbar_wait(bar, 0);
+  if (WSMEM) { mbar_wait(bar, mb.parity); mb.parity ^= 1u; }
   __syncthreads();
 
   // ---- transposed conv, one parity class of input rows at a time ----
@@ -248,27 +252,31 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
     const int qd = i / a.cin, c = i - qd * a.cin;
     float s = 0.f;
     for (int sg = 0; sg < nseg; ++sg) s += red[((size_t)qd * nseg + sg) * a.cin + c];
-    if (qd < 2) a.bpartp[((size_t)blockIdx.x * a.cin + c) * 2 + qd] = s;
-    else a.bpartpd[((size_t)blockIdx.x * a.cin + c) * 2 + (qd - 2)] = s;
+    if (qd < 2) a.bpartp[((size_t)vb * a.cin + c) * 2 + qd] = s;
+    else a.bpartpd[((size_t)vb * a.cin + c) * 2 + (qd - 2)] = s;
   }
-  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
-    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
-    bwdsum_combine_l1(a.finp, grp, gridDim.x, a.finp.l2);
-    if (nq == 4) bwdsum_combine_l1(a.finpd, grp, gridDim.x, a.finpd.l2);
-    if (tree_arrive_l2(a.counter, gridDim.x)) {
+  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
+    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
+    bwdsum_combine_l1(a.finp, grp, nvb, a.finp.l2);
+    if (nq == 4) bwdsum_combine_l1(a.finpd, grp, nvb, a.finpd.l2);
+    if (tree_arrive_l2(a.counter, nvb)) {
       bwdsum_combine_l2(a.finp, ngrp, a.finp.l2);
       if (nq == 4) bwdsum_combine_l2(a.finpd, ngrp, a.finpd.l2);
     }
   }
 }
 
+template <int K, bool WSMEM>
+__global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
+  conv_bwd_data_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
+}
+
 // Transposed filter banks wT[k][co][ci] for the backward-data kernels (all conv layers, one launch).  `params`
 // is caller-owned and may change between calls, so the copy is refreshed at the start of every backward pass
 // (65 K - 300 K floats: a few microseconds).
-struct WtLayer { int64_t w_off; float* wT; int k, cin, cout; int64_t begin; };
-struct WtArgs { WtLayer layer[kMaxConvs]; int nlayers; int64_t total; const float* params; };
-__global__ void __launch_bounds__(256) weight_transpose_kernel(WtArgs a) {
-  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+__device__ __forceinline__ void weight_transpose_body(const WtArgs& a, const int64_t p) {
   if (p >= a.total) return;
   int l = 0;
   while (l + 1 < a.nlayers && p >= a.layer[l + 1].begin) ++l;
@@ -278,6 +286,9 @@ __global__ void __launch_bounds__(256) weight_transpose_kernel(WtArgs a) {
   const int co = (int)((i / L.cin) % L.cout);
   const int k = (int)(i / ((int64_t)L.cin * L.cout));
   L.wT[i] = a.params[L.w_off + ((int64_t)k * L.cin + ci) * L.cout + co];
+}
+__global__ void __launch_bounds__(256) weight_transpose_kernel(WtArgs a) {
+  weight_transpose_body(a, (int64_t)blockIdx.x * 256 + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -387,15 +398,14 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
 
 // All layers' weight gradients in ONE launch: virtual CTA -> (layer, output-channel tile, row chunk) through a
 // static table, so ~600 CTAs of 256 threads keep every SM busy instead of ten serial 64-CTA launches.
-__global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
-                                                                const float* __restrict__ feat, long long* tl) {
-  TCR_DYNAMIC_SMEM(smem_raw);
+__device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ layers, int nlayers, int n, const float* __restrict__ feat,
+                                                long long* tl, const int vb, unsigned char* smem_raw) {
   float* smem = reinterpret_cast<float*>(smem_raw);
-  tl_stamp(tl, 4096 + blockIdx.x, 0);
+  tl_stamp(tl, 4096 + vb, 0);
   int l = 0;
-  while (l + 1 < nlayers && (int)blockIdx.x >= layers[l + 1].cta_begin) ++l;
+  while (l + 1 < nlayers && vb >= layers[l + 1].cta_begin) ++l;
   const DwLayer L = layers[l];
-  const int local = (int)blockIdx.x - L.cta_begin;
+  const int local = vb - L.cta_begin;
   const int ncot = L.cout / L.cot;
   BwdWeightArgs a;
   a.n = n;
@@ -404,18 +414,22 @@ __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer
   a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.stride = L.stride; a.t_in = L.t_in; a.t_out = L.t_out;
   a.pad_left = L.pad_left; a.cot = L.cot; a.RG = L.RG; a.R = L.R; a.UB = L.UB; a.dwpart = L.dwpart;
   const int bx = local % ncot, by = local / ncot;
-  tl_stamp(tl, 4096 + blockIdx.x, 1);
+  tl_stamp(tl, 4096 + vb, 1);
   if (L.k == 9) dw_body<9>(a, bx, by, smem);
   else if (L.k == 3) dw_body<3>(a, bx, by, smem);
   else dw_body<1>(a, bx, by, smem);
-  tl_stamp(tl, 4096 + blockIdx.x, 2);
-  if (tl && threadIdx.x == 0) { tl[(size_t)(4096 + blockIdx.x) * 8 + 3] = l; tl[(size_t)(4096 + blockIdx.x) * 8 + 4] = (long long)by; }
+  tl_stamp(tl, 4096 + vb, 2);
+  if (tl && threadIdx.x == 0) { tl[(size_t)(4096 + vb) * 8 + 3] = l; tl[(size_t)(4096 + vb) * 8 + 4] = (long long)by; }
+}
+__global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
+                                                                const float* __restrict__ feat, long long* tl) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static constexpr size_t kSmemBudget = 100 * 1024;
 static constexpr size_t kSmemBudgetW = 64 * 1024;
 
 static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int KS, bool w_smem) {
@@ -430,8 +444,6 @@ static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int K
   f += 4 + (w_smem ? (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0) : 0);
   return f * 4;
 }
-
-static constexpr size_t kSmemMax = 200 * 1024;
 
 static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
   const size_t wbytes = ((size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0)) * 4;
@@ -574,6 +586,10 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.counter = h->d_counters + (size_t)slot * h->counter_stride;
   const int groups = (n + U - 1) / U;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
+  if (h->rec) {
+    rec_bwd(h, a, cv.k, wsm, groups, smem);
+    return 0;
+  }
   switch (cv.k) {
     case 9: return wsm ? launch_bwd_data<9, true>(("dx:" + cv.name).c_str(), a, groups, smem, s)
                        : launch_bwd_data<9, false>(("dx:" + cv.name).c_str(), a, groups, smem, s);
@@ -593,7 +609,8 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       w.layer[w.nlayers++] = WtLayer{cv.w_off, cv.wT, cv.k, cv.cin, cv.cout, w.total};
       w.total += cv.wnumel();
     }
-    TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
+    if (h->rec) rec_transpose(h, w);
+    else TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
   }
   for (int i = (int)h->blocks.size() - 1; i >= 0; --i) {
     BlockPlan& b = h->blocks[i];
@@ -645,7 +662,9 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
     }
   }
   // weight gradients: every layer's inputs are final now -> one grouped launch over all layers
-  {
+  if (h->rec) {
+    rec_dw(h, n, feat);
+  } else {
     auto kfn = dw_grouped_kernel;
 #ifndef TCR_EMU
     static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default

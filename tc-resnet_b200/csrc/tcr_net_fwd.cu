@@ -21,18 +21,18 @@ constexpr int TM = 4;   // output rows per thread task
 // conv forward
 // ------------------------------------------------------------------------------------------------
 template <int K, bool WSMEM>
-__global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
-  TCR_DYNAMIC_SMEM(smem_raw);
+__device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, const int nvb, unsigned char* smem_raw, MbarCtx& mb,
+                                              const bool tree) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
-  const int u0 = blockIdx.x * a.U;
+  const int u0 = vb * a.U;
   const int Ue = imin(a.U, a.n - u0);
   const int CS = chan_stride(a.cin);
   const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
   const int TP = a.pad_left + a.t_in + pad_right;
   const int Rmax = a.U * a.t_out;
   // shared memory: [mbarrier | W (TMA bulk destination) | W_down | x tile | y tiles | scratch]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* bar = mb.bar;
   float* ws = smem + 4;                               // [K][cin][cout]   (only when a.w_smem)
   const int wn = WSMEM ? K * a.cin * a.cout : 0;
   const int wdn = (WSMEM && a.wd) ? a.cin * a.coutd : 0;
@@ -44,12 +44,16 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   float* smean = red + kThreads;
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), xs_off = (int)(xs - smem);
 
-  tl_stamp(a.tl, blockIdx.x, 0);
+  tl_stamp(a.tl, vb, 0);
   // ---- one TMA bulk copy brings the whole filter bank into shared memory while the tile is staged ----
   if (WSMEM) {
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    if (!mb.ready) {
+      if (tid == 0) mbar_init(bar, 1);
+      __syncthreads();
+      mb.ready = true;
+    }
     if (tid == 0) {
+      fence_proxy_async();          // earlier generic-proxy reads of this buffer are ordered before the async write
       mbar_expect_tx(bar, (uint32_t)(wn + wdn) * 4u);
       tma_load_1d(ws, a.w, (uint32_t)wn * 4u, bar);
       if (wdn) tma_load_1d(wsd, a.wd, (uint32_t)wdn * 4u, bar);
@@ -93,10 +97,10 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
       }
     }
   }
-  tl_stamp(a.tl, blockIdx.x, 1);
-  if (WSMEM) mbar_wait(bar, 0);
+  tl_stamp(a.tl, vb, 1);
+  if (WSMEM) { mbar_wait(bar, mb.parity); mb.parity ^= 1u; }
   __syncthreads();
-  tl_stamp(a.tl, blockIdx.x, 2);
+  tl_stamp(a.tl, vb, 2);
 
   // ---- register-tiled conv: task = (k-slice, row tile of TM, 4 output channels) ----
   const int R = Ue * a.t_out;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     }
   }
   __syncthreads();
-  tl_stamp(a.tl, blockIdx.x, 3);
+  tl_stamp(a.tl, vb, 3);
 
   // ---- epilogue: sum k-slices in fixed order, coalesced store of the pre-BN output ----
   const size_t grow0 = (size_t)u0 * a.t_out;
@@ -193,20 +197,27 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
     for (int idx = tid; idx < R * NCGD; idx += kThreads) st4(a.yd + grow0 * a.coutd + (size_t)idx * 4, ld4(ysd + (size_t)idx * 4));
   if (!a.train) return;
   __syncthreads();
-  tl_stamp(a.tl, blockIdx.x, 4);
-  tile_stats(ys, R, a.cout, red, smean, a.fpart + (size_t)blockIdx.x * a.cout * 2);
-  if (a.wd) tile_stats(ysd, R, a.coutd, red, smean, a.fpartd + (size_t)blockIdx.x * a.coutd * 2);
-  tl_stamp(a.tl, blockIdx.x, 5);
-  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
-    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
-    bn_combine_l1(a.fin, grp, gridDim.x, a.U, a.n, a.t_out, a.fin.l2);
-    if (a.wd) bn_combine_l1(a.find, grp, gridDim.x, a.U, a.n, a.t_out, a.find.l2);
-    if (tree_arrive_l2(a.counter, gridDim.x)) {
+  tl_stamp(a.tl, vb, 4);
+  tile_stats(ys, R, a.cout, red, smean, a.fpart + (size_t)vb * a.cout * 2);
+  if (a.wd) tile_stats(ysd, R, a.coutd, red, smean, a.fpartd + (size_t)vb * a.coutd * 2);
+  tl_stamp(a.tl, vb, 5);
+  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
+    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
+    bn_combine_l1(a.fin, grp, nvb, a.U, a.n, a.t_out, a.fin.l2);
+    if (a.wd) bn_combine_l1(a.find, grp, nvb, a.U, a.n, a.t_out, a.find.l2);
+    if (tree_arrive_l2(a.counter, nvb)) {
       bn_combine_l2(a.fin, ngrp, a.fin.l2, a.eps);
       if (a.wd) bn_combine_l2(a.find, ngrp, a.find.l2, a.eps);
     }
   }
-  tl_stamp(a.tl, blockIdx.x, 6);
+  tl_stamp(a.tl, vb, 6);
+}
+
+template <int K, bool WSMEM>
+__global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
+  conv_fwd_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
 }
 
 // Eval mode: BN tables from the moving statistics (bn_forward with is_training=False).
@@ -238,8 +249,7 @@ __global__ void bn_table_eval_kernel(EvalBnArgs a) {
 constexpr int kHeadWarps = 8;
 constexpr int kHeadSlots = 4;   // channels per lane: c = lane + 32 j, C <= 128
 
-__global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
-  TCR_DYNAMIC_SMEM(smem_raw);
+__device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw, const bool tree) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int C = a.c, T = a.t, NC = a.classes;
   float* s_sum = smem;                                   // [warps][4][C]
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
   float* s_dl = s_drop + kHeadWarps * C;                 // [warps][NC]
   float* s_loss = s_dl + kHeadWarps * NC;                // [warps]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * kHeadWarps + warp;
+  const int n = vb * kHeadWarps + warp;
   const bool valid = n < a.n;
 
   float pooled[kHeadSlots], mk[kHeadSlots], dropped[kHeadSlots];
@@ -318,11 +328,11 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
       if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
-        a.loss_part[blockIdx.x] = s;
+        a.loss_part[vb] = s;
       }
-      if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
-        scalar_combine_l1(a.loss_part, blockIdx.x / kFanIn, gridDim.x, a.loss_l2);
-        if (tree_arrive_l2(a.counter, gridDim.x)) scalar_combine_l2(a.loss_l2, (gridDim.x + kFanIn - 1) / kFanIn, a.loss_out);
+      if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
+        scalar_combine_l1(a.loss_part, vb / kFanIn, nvb, a.loss_l2);
+        if (tree_arrive_l2(a.counter, nvb)) scalar_combine_l2(a.loss_l2, (nvb + kFanIn - 1) / kFanIn, a.loss_out);
       }
     }
     return;
@@ -360,13 +370,13 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
           a.gout[ofs] = g;
           const float yb = a.yb[ofs];
           sb1[j] += g;
-          sb2[j] = fmaf(g, (yb - __ldg(a.bnfb + c)) * __ldg(a.bnfb + C + c), sb2[j]);
+          sb2[j] = fmaf(g, (yb - ldc1(a.bnfb + c)) * ldc1(a.bnfb + C + c), sb2[j]);
           if (a.ydn) {
             const float yd = a.ydn[ofs];
             const float zd = bn_apply1(yd, a.bnfd, C, c);
             const float gs = zd > 0.f ? g : 0.f;
             sd1[j] += gs;
-            sd2[j] = fmaf(gs, (yd - __ldg(a.bnfd + c)) * __ldg(a.bnfd + C + c), sd2[j]);
+            sd2[j] = fmaf(gs, (yd - ldc1(a.bnfd + c)) * ldc1(a.bnfd + C + c), sd2[j]);
           }
         }
       }
@@ -390,31 +400,36 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
     const int q = i / C, c = i - q * C;
     float s = 0.f;
     for (int w = 0; w < kHeadWarps; ++w) s += s_sum[(w * 4 + q) * C + c];
-    if (q < 2) a.bpartb[((size_t)blockIdx.x * C + c) * 2 + q] = s;
-    else if (a.ydn) a.bpartd[((size_t)blockIdx.x * C + c) * 2 + (q - 2)] = s;
+    if (q < 2) a.bpartb[((size_t)vb * C + c) * 2 + q] = s;
+    else if (a.ydn) a.bpartd[((size_t)vb * C + c) * 2 + (q - 2)] = s;
   }
   for (int i = threadIdx.x; i < C * NC; i += blockDim.x) {
     const int c = i / NC, k = i - c * NC;
     float s = 0.f;
     for (int w = 0; w < kHeadWarps; ++w) s = fmaf(s_drop[w * C + c], s_dl[w * NC + k], s);
-    a.dwfc_part[(size_t)blockIdx.x * C * NC + i] = s;
+    a.dwfc_part[(size_t)vb * C * NC + i] = s;
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
-    a.loss_part[blockIdx.x] = s;
+    a.loss_part[vb] = s;
   }
-  if (tree_arrive_l1(a.counter, blockIdx.x, gridDim.x)) {
-    const int grp = blockIdx.x / kFanIn, ngrp = (gridDim.x + kFanIn - 1) / kFanIn;
-    bwdsum_combine_l1(a.finb, grp, gridDim.x, a.finb.l2);
-    if (a.ydn) bwdsum_combine_l1(a.find, grp, gridDim.x, a.find.l2);
-    scalar_combine_l1(a.loss_part, grp, gridDim.x, a.loss_l2);
-    if (tree_arrive_l2(a.counter, gridDim.x)) {
+  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
+    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
+    bwdsum_combine_l1(a.finb, grp, nvb, a.finb.l2);
+    if (a.ydn) bwdsum_combine_l1(a.find, grp, nvb, a.find.l2);
+    scalar_combine_l1(a.loss_part, grp, nvb, a.loss_l2);
+    if (tree_arrive_l2(a.counter, nvb)) {
       bwdsum_combine_l2(a.finb, ngrp, a.finb.l2);
       if (a.ydn) bwdsum_combine_l2(a.find, ngrp, a.find.l2);
       scalar_combine_l2(a.loss_l2, ngrp, a.loss_out);
     }
   }
+}
+
+__global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  head_body(a, blockIdx.x, gridDim.x, smem_raw, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -537,6 +552,7 @@ int net_alloc_workspace(tcr_handle* h) {
   if (cudaMemset(h->d_counters, 0, (size_t)64 * h->counter_stride * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
   WS(ws_alloc(h, &h->d_loss_l2, (size_t)h->head_groups_max / kFanIn + 2));
   WS(ws_alloc(h, &h->d_hyper, 1));
+  WS(ws_alloc(h, &h->d_gridbar, 4));
   if (getenv("TCR_DEBUG_TIMELINE")) {
     WS(ws_alloc(h, &h->d_timeline, (size_t)8 * 8192));
     cudaMemset(h->d_timeline, 0, sizeof(long long) * 8 * 8192);
@@ -581,6 +597,10 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   }
   const int groups = (n + U - 1) / U;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
+  if (h->rec) {
+    rec_fwd(h, a, cv.k, wsm, groups, smem);
+    return 0;
+  }
   switch (cv.k) {
     case 3: return wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, groups, smem, s)
                        : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
@@ -673,7 +693,8 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       const size_t smem = (size_t)(kHeadWarps * 4 * lb.c + kHeadWarps * lb.c + kHeadWarps * ha.classes + kHeadWarps) * 4;
-      TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+      if (h->rec) rec_head(h, ha, groups, smem);
+      else TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next
     // block's first kernel, so `prev` is updated at the top of the next iteration.

@@ -24,12 +24,16 @@ __device__ __forceinline__ int find_segment(const OptSegment* segs, int nsegs, i
   return lo;
 }
 
-__global__ void __launch_bounds__(kOptThreads) grad_finalize_kernel(const OptSegment* __restrict__ segs, int nsegs, int64_t total,
-                                                                   int fc_seg, const float* __restrict__ fc_part, int fc_R,
-                                                                   const float* __restrict__ params, float weight_decay,
-                                                                   float* __restrict__ grads, float* __restrict__ l2part) {
-  __shared__ float s_red[kOptThreads / 32];
-  const int64_t p = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
+__device__ __forceinline__ void grad_finalize_body(const GradArgs& a, const int vb, float* s_red) {
+  const OptSegment* __restrict__ segs = a.segs;
+  const int nsegs = a.nsegs, fc_seg = a.fc_seg, fc_R = a.fc_R;
+  const int64_t total = a.total;
+  const float* __restrict__ fc_part = a.fc_part;
+  const float* __restrict__ params = a.params;
+  const float weight_decay = a.weight_decay;
+  float* __restrict__ grads = a.grads;
+  float* __restrict__ l2part = a.l2part;
+  const int64_t p = (int64_t)vb * kOptThreads + threadIdx.x;
   float w2 = 0.f;
   if (p < total) {
     const int si = find_segment(segs, nsegs, p);
@@ -61,8 +65,12 @@ __global__ void __launch_bounds__(kOptThreads) grad_finalize_kernel(const OptSeg
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < kOptThreads / 32; ++i) s += s_red[i];
-    l2part[blockIdx.x] = s;
+    l2part[vb] = s;
   }
+}
+__global__ void __launch_bounds__(kOptThreads) grad_finalize_kernel(GradArgs a) {
+  __shared__ float s_red[kOptThreads / 32];
+  grad_finalize_body(a, (int)blockIdx.x, s_red);
 }
 
 struct UpdateArgs {
@@ -145,7 +153,6 @@ __global__ void __launch_bounds__(1024) loss_only_kernel(const OptSegment* __res
   }
 }
 
-int head_groups(int n);   // tcr_net_fwd.cu
 
 int build_opt_segments(tcr_handle* h) {
   std::vector<OptSegment> segs;
@@ -177,8 +184,15 @@ static int fc_segment(const tcr_handle* h) { return (int)h->convs.size() * 3; }
 int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   const int blocks = (int)((h->n_train + kOptThreads - 1) / kOptThreads);
   if (blocks > 4096) { set_error("parameter count too large for the l2 partial buffer"); return TCR_ERR_UNSUPPORTED; }
-  TCR_LAUNCH("grad_finalize", grad_finalize_kernel, dim3(blocks), dim3(kOptThreads), 0, s, h->d_segs, h->n_segs, h->n_train, fc_segment(h),
-             h->d_dwfc_part, head_groups(a->n), a->params, a->weight_decay, h->d_grads, h->d_l2part);
+  GradArgs ga{h->d_segs, h->n_segs, h->n_train, fc_segment(h), h->d_dwfc_part, head_groups(a->n), a->params, a->weight_decay,
+              h->d_grads, h->d_l2part};
+  if (h->rec) {
+    rec_grad(h, ga, blocks);
+    int rc0 = rec_launch(h, s);
+    if (rc0) return rc0;
+  } else {
+    TCR_LAUNCH("grad_finalize", grad_finalize_kernel, dim3(blocks), dim3(kOptThreads), 0, s, ga);
+  }
   if (h->comm && h->world > 1) {
     int rc = comm_allreduce_sum(h, h->d_grads, h->n_train, s);
     if (rc) return rc;

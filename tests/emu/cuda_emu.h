@@ -27,6 +27,7 @@
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
+#define __grid_constant__
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -152,5 +153,5 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 #define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().cur->smem
-#define TCR_LAUNCH_COOP(name, kernel, grid, block, smem, stream, ...) \
-  emu::launch_cooperative((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define TCR_LAUNCH_COOP(name, kernel, grid, block, smem, stream, arg) \
+  emu::launch_cooperative((grid), (block), (smem), [&]() { kernel(arg); })
