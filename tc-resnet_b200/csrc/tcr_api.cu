@@ -479,7 +479,7 @@ extern "C" int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr
     *numel = k;
     return TCR_OK;
   };
-  if (s == "timeline" && h->d_timeline) return ret((float*)h->d_timeline, 2 * 8 * 8192);   // int64 viewed as float pairs
+  if (s == "timeline" && h->d_timeline) return ret((float*)h->d_timeline, 2 * 16 * 8192);   // int64 viewed as float pairs
   if (s == "features") return ret(h->d_feat, n * h->frames * h->features);
   if (s == "grads") return ret(h->d_grads, h->n_train);
   if (s == "logits") return ret(h->d_logits, n * h->cfg.num_classes);

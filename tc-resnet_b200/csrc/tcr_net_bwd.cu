@@ -64,7 +64,8 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
   float* dys = wsd + wdn;                                            // [U][TPd][COS]
   float* dysd = dys + (size_t)a.U * TPd * COS;                       // [U][t_out][COSD]
   float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
-  float* red = dxs + (size_t)a.KS * Rin_max * a.cin;                 // [4][nseg][cin]
+  float* red = ws;                                                   // [4][nseg][cin]: aliases the filter bank / dy tiles,
+                                                                     // which are dead once the transposed conv is done
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), dys_off = (int)(dys - smem), dysd_off = (int)(dysd - smem);
 
   // ---- stage dy (BatchNorm backward applied on load) ----
@@ -440,8 +441,9 @@ static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int K
   const int ncig = cv.cin / 4;
   const int nseg = std::max(1, kThreads / ncig);
   size_t f = (size_t)U * TPd * chan_stride(cv.cout) + (dn ? (size_t)U * cv.t_out * chan_stride(dn->cout) : 0);
-  f += (size_t)KS * U * cv.t_in * cv.cin + (size_t)4 * nseg * cv.cin;
-  f += 4 + (w_smem ? (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0) : 0);
+  f += (w_smem ? (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0) : 0);
+  f = std::max(f, (size_t)4 * nseg * cv.cin);            // epilogue scratch aliases the filter bank + dy tiles
+  f += 4 + (size_t)KS * U * cv.t_in * cv.cin;
   return f * 4;
 }
 

@@ -249,46 +249,71 @@ __global__ void bn_table_eval_kernel(EvalBnArgs a) {
 constexpr int kHeadWarps = 8;
 constexpr int kHeadSlots = 4;   // channels per lane: c = lane + 32 j, C <= 128
 
+// Shared-memory layout (floats): tables tb[4][C] (conv_b), td[4][C] (down), then per CTA
+// s_sum[W][4][C], s_drop[W][C], s_dl[W][NC], s_loss[W], then per warp 3 tiles of T*C: so (block output), syb (raw y_b),
+// ssh (raw shortcut).  Every global read of the step happens once, as batched float4 loads into these tiles.
+__host__ __device__ inline size_t head_smem_floats(int T, int C, int NC) {
+  return (size_t)8 * C + (size_t)kHeadWarps * (4 * C + C + NC + 1) + 4 + (size_t)kHeadWarps * 3 * T * C;
+}
+
 __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw, const bool tree) {
-  float* smem = reinterpret_cast<float*>(smem_raw);
-  const int C = a.c, T = a.t, NC = a.classes;
-  float* s_sum = smem;                                   // [warps][4][C]
+  float* smem = reinterpret_cast<float*>(smem_raw) + 4;          // first 16 bytes: the persistent kernel's mbarrier
+  const int C = a.c, T = a.t, NC = a.classes, TC = T * C;
+  float* tb = smem;                                      // [4][C]
+  float* td = tb + 4 * C;                                // [4][C]
+  float* s_sum = td + 4 * C;                             // [warps][4][C]
   float* s_drop = s_sum + kHeadWarps * 4 * C;            // [warps][C]
   float* s_dl = s_drop + kHeadWarps * C;                 // [warps][NC]
   float* s_loss = s_dl + kHeadWarps * NC;                // [warps]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* so = s_loss + kHeadWarps + ((4 - (kHeadWarps * (5 * C + NC + 1)) % 4) % 4) + (size_t)warp * 3 * TC;   // 16-byte aligned
+  float* syb = so + TC;
+  float* ssh = syb + TC;
   const int n = vb * kHeadWarps + warp;
   const bool valid = n < a.n;
+  const bool sh_bn = a.shortcut.kind == 1;
+
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    tb[i] = ldc1(a.in.bnf + i);
+    td[i] = sh_bn ? ldc1(a.shortcut.bnf + i) : 0.f;
+  }
+  if (valid) {                                            // raw tiles: all loads issued before any use (latency overlapped)
+    const size_t base = (size_t)n * TC;
+    for (int e = 4 * lane; e < TC; e += 128) {
+      st4(syb + e, ld4(a.in.data + base + e));
+      st4(ssh + e, ld4(a.shortcut.data + base + e));
+    }
+  }
+  __syncthreads();
 
   float pooled[kHeadSlots], mk[kHeadSlots], dropped[kHeadSlots];
 #pragma unroll
   for (int j = 0; j < kHeadSlots; ++j) { pooled[j] = 0.f; mk[j] = 1.f; dropped[j] = 0.f; }
   float loss_n = 0.f, dl = 0.f;
   if (valid) {
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-      for (int j = 0; j < kHeadSlots; ++j) {
-        const int c = lane + 32 * j;
-        if (c < C) {
-          const size_t ofs = ((size_t)n * T + t) * C + c;
-          const float zb = bn_apply1(a.in.data[ofs], a.in.bnf, C, c);
-          float sh = a.shortcut.data[ofs];
-          if (a.shortcut.kind == 1) sh = fmaxf(bn_apply1(sh, a.shortcut.bnf, C, c), 0.f);
-          const float o = fmaxf(zb + sh, 0.f);
-          if (a.out_write) a.out_write[ofs] = o;
-          pooled[j] += o;
-        }
-      }
-    }
 #pragma unroll
     for (int j = 0; j < kHeadSlots; ++j) {
       const int c = lane + 32 * j;
-      pooled[j] = pooled[j] / (float)T;
-      if (a.use_dropout && c < C) {
-        mk[j] = a.mask ? a.mask[(size_t)n * C + c] : floorf(a.keep + uniform01(a.seed, (uint64_t)n * C + c));
-        dropped[j] = pooled[j] / a.keep * mk[j];        // tf.nn.dropout: x / keep_prob * floor(keep_prob + U)
-      } else {
-        dropped[j] = pooled[j];
+      if (c < C) {
+        const float mb_ = tb[c], sb_ = tb[2 * C + c], bb_ = tb[3 * C + c];
+        const float md_ = td[c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+          const float zb = fmaf(syb[t * C + c] - mb_, sb_, bb_);
+          float sh = ssh[t * C + c];
+          if (sh_bn) sh = fmaxf(fmaf(sh - md_, sd_, bd_), 0.f);
+          const float o = fmaxf(zb + sh, 0.f);
+          so[t * C + c] = o;
+          if (a.out_write) a.out_write[(size_t)n * TC + t * C + c] = o;
+          acc += o;
+        }
+        pooled[j] = acc / (float)T;
+        if (a.use_dropout) {
+          mk[j] = a.mask ? a.mask[(size_t)n * C + c] : floorf(a.keep + uniform01(a.seed, (uint64_t)n * C + c));
+          dropped[j] = pooled[j] / a.keep * mk[j];        // tf.nn.dropout: x / keep_prob * floor(keep_prob + U)
+        } else {
+          dropped[j] = pooled[j];
+        }
       }
     }
     // fc (no bias): logits[k] = sum_c dropped[c] W[c,k]; lane k keeps logits[k]
@@ -338,7 +363,7 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
     return;
   }
 
-  // ---- head backward: d pooled -> gradient at the block output, BN-backward partial sums ----
+  // ---- head backward: d pooled -> gradient at the block output, BN-backward partial sums (all from shared memory) ----
   float sb1[kHeadSlots], sb2[kHeadSlots], sd1[kHeadSlots], sd2[kHeadSlots];
 #pragma unroll
   for (int j = 0; j < kHeadSlots; ++j) sb1[j] = sb2[j] = sd1[j] = sd2[j] = 0.f;
@@ -358,25 +383,20 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
     for (int j = 0; j < kHeadSlots; ++j) {
       if (a.use_dropout) dnet[j] = dnet[j] / a.keep * mk[j];
       dnet[j] = dnet[j] / (float)T;                       // AvgPoolGrad
-    }
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-      for (int j = 0; j < kHeadSlots; ++j) {
-        const int c = lane + 32 * j;
-        if (c < C) {
-          const size_t ofs = ((size_t)n * T + t) * C + c;
-          const float o = a.out_write[ofs];
-          const float g = o > 0.f ? dnet[j] : 0.f;
-          a.gout[ofs] = g;
-          const float yb = a.yb[ofs];
+      const int c = lane + 32 * j;
+      if (c < C) {
+        const float mb_ = tb[c], rb_ = tb[C + c];
+        const float md_ = td[c], rd_ = td[C + c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
+        for (int t = 0; t < T; ++t) {
+          const float g = so[t * C + c] > 0.f ? dnet[j] : 0.f;
+          a.gout[(size_t)n * TC + t * C + c] = g;
           sb1[j] += g;
-          sb2[j] = fmaf(g, (yb - ldc1(a.bnfb + c)) * ldc1(a.bnfb + C + c), sb2[j]);
+          sb2[j] = fmaf(g, (syb[t * C + c] - mb_) * rb_, sb2[j]);
           if (a.ydn) {
-            const float yd = a.ydn[ofs];
-            const float zd = bn_apply1(yd, a.bnfd, C, c);
-            const float gs = zd > 0.f ? g : 0.f;
+            const float yd = ssh[t * C + c];
+            const float gs = fmaf(yd - md_, sd_, bd_) > 0.f ? g : 0.f;
             sd1[j] += gs;
-            sd2[j] = fmaf(gs, (yd - ldc1(a.bnfd + c)) * ldc1(a.bnfd + C + c), sd2[j]);
+            sd2[j] = fmaf(gs, (yd - md_) * rd_, sd2[j]);
           }
         }
       }
@@ -435,7 +455,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static constexpr size_t kSmemBudget = 100 * 1024;   // keeps two CTAs resident per SM
+static constexpr size_t kSmemBudget = 110 * 1024;   // two CTAs per SM: 2 x (110 + 1 static + 1 reserved) KB <= 227 KB
 
 int head_groups(int n) { return (n + kHeadWarps - 1) / kHeadWarps; }
 
@@ -554,8 +574,8 @@ int net_alloc_workspace(tcr_handle* h) {
   WS(ws_alloc(h, &h->d_hyper, 1));
   WS(ws_alloc(h, &h->d_gridbar, 4));
   if (getenv("TCR_DEBUG_TIMELINE")) {
-    WS(ws_alloc(h, &h->d_timeline, (size_t)8 * 8192));
-    cudaMemset(h->d_timeline, 0, sizeof(long long) * 8 * 8192);
+    WS(ws_alloc(h, &h->d_timeline, (size_t)16 * 8192));
+    cudaMemset(h->d_timeline, 0, sizeof(long long) * 16 * 8192);
   }
   if (cudaMallocHost((void**)&h->h_hyper, sizeof(Hyper)) != cudaSuccess) return TCR_ERR_CUDA;
   int rc = build_dw_table(h);
@@ -586,7 +606,7 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.cout = cv.cout; a.stride = cv.stride; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
   a.train = training ? 1 : 0;
-  a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline : nullptr;
+  a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline + (h->rec ? 12 * 8192 : 0) : nullptr;
   a.counter = h->d_counters + (size_t)counter_slot * h->counter_stride;
   a.eps = h->cfg.bn_epsilon;
   a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.fl2, cv.cout};
@@ -692,9 +712,20 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->bl2, dn->cout} : ha.finb;
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
-      const size_t smem = (size_t)(kHeadWarps * 4 * lb.c + kHeadWarps * lb.c + kHeadWarps * ha.classes + kHeadWarps) * 4;
-      if (h->rec) rec_head(h, ha, groups, smem);
-      else TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+      const size_t smem = (head_smem_floats(lb.t, lb.c, ha.classes) + 8) * 4;
+      if (smem > kSmemBudget) { set_error("head tile does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
+      if (h->rec) {
+        rec_head(h, ha, groups, smem);
+      } else {
+        static size_t head_lim = 32 * 1024;
+#ifndef TCR_EMU
+        if (smem > head_lim) {
+          if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
+          head_lim = smem;
+        }
+#endif
+        TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+      }
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next
     // block's first kernel, so `prev` is updated at the top of the next iteration.

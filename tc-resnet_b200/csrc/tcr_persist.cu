@@ -20,6 +20,9 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Distributed finalize: one warp per channel; lanes stride the per-CTA partials in batches of kFinB independent loads
+// (the unbatched version was a 7 us latency chain per phase), fp64 Chan combination, fixed order -> deterministic.
+constexpr int kFinB = 8;
 __device__ __forceinline__ void fin_fwd_phase(const FinFwd& F, int b, int nb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int total = F.f[0].c + (F.nf > 1 ? F.f[1].c : 0);
@@ -28,19 +31,44 @@ __device__ __forceinline__ void fin_fwd_phase(const FinFwd& F, int b, int nb) {
     const int c = item - (fi ? F.f[0].c : 0);
     const BnFinalize& f = F.f[fi];
     double cnt = 0.0, sum = 0.0;
-    for (int g = lane; g < F.G; g += 32) {
-      const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
-      cnt += k;
-      sum += k * (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2);
+    for (int g0 = lane; g0 < F.G; g0 += 32 * kFinB) {
+      float m[kFinB];
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) {
+        const int g = g0 + 32 * j;
+        m[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) {
+        const int g = g0 + 32 * j;
+        if (g < F.G) {
+          const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
+          cnt += k;
+          sum += k * (double)m[j];
+        }
+      }
     }
     cnt = warp_sum_d(cnt);
     sum = warp_sum_d(sum);
     const double mean = sum / cnt;
     double m2 = 0.0;
-    for (int g = lane; g < F.G; g += 32) {
-      const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
-      const double d = (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2) - mean;
-      m2 += (double)__ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) + k * d * d;
+    for (int g0 = lane; g0 < F.G; g0 += 32 * kFinB) {
+      float m[kFinB], q[kFinB];
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) {
+        const int g = g0 + 32 * j;
+        m[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2) : 0.f;
+        q[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) {
+        const int g = g0 + 32 * j;
+        if (g < F.G) {
+          const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
+          const double d = (double)m[j] - mean;
+          m2 += (double)q[j] + k * d * d;
+        }
+      }
     }
     m2 = warp_sum_d(m2);
     if (lane == 0) {
@@ -60,19 +88,34 @@ __device__ __forceinline__ void fin_bwd_phase(const FinBwd& F, int b, int nb) {
   const int n0 = 2 * F.f[0].c, n1 = F.nf > 1 ? 2 * F.f[1].c : 0;
   const int total = n0 + n1 + (F.loss_part ? 1 : 0);
   for (int item = b * wpb + warp; item < total; item += nb * wpb) {
-    double s = 0.0;
+    const float* src;
+    size_t stride;
+    float* dst;
     if (item < n0 + n1) {
       const int fi = item >= n0 ? 1 : 0;
       const int i = item - (fi ? n0 : 0);
       const BwdSumFinalize& f = F.f[fi];
-      for (int g = lane; g < F.G; g += 32) s += (double)__ldcg(f.bpart + (size_t)g * f.c * 2 + i);
-      s = warp_sum_d(s);
-      if (lane == 0) f.bsum[(i & 1) * f.c + (i >> 1)] = (float)s;
+      src = f.bpart + i;
+      stride = (size_t)f.c * 2;
+      dst = f.bsum + (i & 1) * f.c + (i >> 1);
     } else {
-      for (int g = lane; g < F.G; g += 32) s += (double)__ldcg(F.loss_part + g);
-      s = warp_sum_d(s);
-      if (lane == 0) *F.loss_out = (float)s;
+      src = F.loss_part;
+      stride = 1;
+      dst = F.loss_out;
     }
+    double s = 0.0;
+    for (int g0 = lane; g0 < F.G; g0 += 32 * kFinB) {
+      float v[kFinB];
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) {
+        const int g = g0 + 32 * j;
+        v[j] = g < F.G ? __ldcg(src + (size_t)g * stride) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kFinB; ++j) s += (double)v[j];
+    }
+    s = warp_sum_d(s);
+    if (lane == 0) *dst = (float)s;
   }
 }
 
@@ -87,6 +130,15 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
   float* scratch = reinterpret_cast<float*>(smem_raw) + 8;
   for (int ph = 0; ph < P.nphases; ++ph) {
     const Phase p = P.phase[ph];
+    if (P.tl && threadIdx.x == 0 && ph < 64) {          // debug timeline: [phase][cta][start, work done]
+      unsigned long long t;
+#ifndef TCR_EMU
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#else
+      t = 0;
+#endif
+      P.tl[((size_t)ph * 512 + b) * 2] = (long long)t;
+    }
     switch (p.kind) {
       case PH_TRANSPOSE:
         for (int64_t i = (int64_t)b * kThreads + threadIdx.x; i < P.wt.total; i += (int64_t)nb * kThreads) weight_transpose_body(P.wt, i);
@@ -126,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
         break;
       case PH_DW:
         for (int vb = b; vb < p.nvb; vb += nb) {
-          dw_grouped_body(P.dw_layers, P.n_dw_layers, P.n, P.feat, P.tl, vb, smem_raw);
+          dw_grouped_body(P.dw_layers, P.n_dw_layers, P.n, P.feat, nullptr, vb, smem_raw);
           __syncthreads();
         }
         break;
@@ -136,6 +188,18 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
           __syncthreads();
         }
         break;
+    }
+    if (P.tl && ph < 64) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long t;
+#ifndef TCR_EMU
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#else
+        t = 0;
+#endif
+        P.tl[((size_t)ph * 512 + b) * 2 + 1] = (long long)t;
+      }
     }
     if (ph + 1 < P.nphases) grid_barrier(P.barrier, (unsigned)nb, epoch);
   }
@@ -261,6 +325,7 @@ int rec_launch(tcr_handle* h, cudaStream_t s) {
   grid = h->persist_grid;
 #endif
   P.barrier = h->d_gridbar;
+  P.tl = h->d_timeline;
   if (cudaMemsetAsync(h->d_gridbar, 0, sizeof(unsigned), s) != cudaSuccess) { rec_abort(h); return TCR_ERR_CUDA; }
   TCR_LAUNCH_COOP("step_persistent", kfn, dim3(grid), dim3(kThreads), smem, s, P);
   delete h->rec;
