@@ -109,9 +109,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks
     atomicAdd(counter, 1u);
     const unsigned target = epoch * nblocks;
     unsigned v;
-    do {
+    for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    } while (v < target);
+      if (v >= target) break;
+      __nanosleep(200);          // back off: hundreds of CTAs polling one L2 line starve the CTAs that still work
+    }
     __threadfence();
   }
   __syncthreads();

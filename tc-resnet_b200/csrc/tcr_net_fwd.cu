@@ -253,7 +253,7 @@ constexpr int kHeadSlots = 4;   // channels per lane: c = lane + 32 j, C <= 128
 // s_sum[W][4][C], s_drop[W][C], s_dl[W][NC], s_loss[W], then per warp 3 tiles of T*C: so (block output), syb (raw y_b),
 // ssh (raw shortcut).  Every global read of the step happens once, as batched float4 loads into these tiles.
 __host__ __device__ inline size_t head_smem_floats(int T, int C, int NC) {
-  return (size_t)8 * C + (size_t)kHeadWarps * (4 * C + C + NC + 1) + 4 + (size_t)kHeadWarps * 3 * T * C;
+  return (size_t)8 * C + (size_t)C * NC + (size_t)kHeadWarps * (4 * C + C + NC + 1) + 8 + (size_t)kHeadWarps * 3 * T * C;
 }
 
 __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw, const bool tree) {
@@ -261,12 +261,13 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
   const int C = a.c, T = a.t, NC = a.classes, TC = T * C;
   float* tb = smem;                                      // [4][C]
   float* td = tb + 4 * C;                                // [4][C]
-  float* s_sum = td + 4 * C;                             // [warps][4][C]
+  float* s_wfc = td + 4 * C;                             // [C][NC] fc weights
+  float* s_sum = s_wfc + C * NC;                         // [warps][4][C]
   float* s_drop = s_sum + kHeadWarps * 4 * C;            // [warps][C]
   float* s_dl = s_drop + kHeadWarps * C;                 // [warps][NC]
   float* s_loss = s_dl + kHeadWarps * NC;                // [warps]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* so = s_loss + kHeadWarps + ((4 - (kHeadWarps * (5 * C + NC + 1)) % 4) % 4) + (size_t)warp * 3 * TC;   // 16-byte aligned
+  float* so = s_loss + kHeadWarps + ((4 - (C * NC + kHeadWarps * (5 * C + NC + 1)) % 4) % 4) + (size_t)warp * 3 * TC;   // 16-byte aligned
   float* syb = so + TC;
   float* ssh = syb + TC;
   const int n = vb * kHeadWarps + warp;
@@ -277,6 +278,7 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
     tb[i] = ldc1(a.in.bnf + i);
     td[i] = sh_bn ? ldc1(a.shortcut.bnf + i) : 0.f;
   }
+  for (int i = threadIdx.x; i < C * NC; i += blockDim.x) s_wfc[i] = __ldg(a.wfc + i);
   if (valid) {                                            // raw tiles: all loads issued before any use (latency overlapped)
     const size_t base = (size_t)n * TC;
     for (int e = 4 * lane; e < TC; e += 128) {
@@ -323,7 +325,7 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
 #pragma unroll
       for (int j = 0; j < kHeadSlots; ++j) {
         const int c = lane + 32 * j;
-        if (c < C) p = fmaf(dropped[j], __ldg(a.wfc + (size_t)c * NC + k), p);
+        if (c < C) p = fmaf(dropped[j], s_wfc[c * NC + k], p);
       }
       p = warp_sum(p);
       if (lane == k) logit = p;
@@ -376,7 +378,7 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
 #pragma unroll
       for (int j = 0; j < kHeadSlots; ++j) {
         const int c = lane + 32 * j;
-        if (c < C) dnet[j] = fmaf(dlk, __ldg(a.wfc + (size_t)c * NC + k), dnet[j]);
+        if (c < C) dnet[j] = fmaf(dlk, s_wfc[c * NC + k], dnet[j]);
       }
     }
 #pragma unroll

@@ -69,6 +69,7 @@ int lane_id();
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::syncwarp(); }
 static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}
 static inline void __threadfence_block() {}
 
 template <class T> static inline uint64_t emu_bits(T v) { uint64_t b = 0; std::memcpy(&b, &v, sizeof(T)); return b; }
