@@ -167,61 +167,44 @@ __device__ __forceinline__ int tree_arrive_l2(unsigned* counters, int ncta) {
   return f;
 }
 
-// Level 1: combine (mean, M2) partials of groups [g0, g1) of CTAs into l2[(grp*C + c)*3 + {cnt, mean, M2}] (fp64 math,
-// Chan et al.).  Level 2: combine the l2 records into the BN table.
-__device__ __forceinline__ void bn_combine_l1(const BnFinalize& f, int grp, int ncta, int U, int n, int t_out, float* l2) {
+// Level 1: sum the (sum y, sum y^2) partials of CTAs [g0, g1) into l2[(grp*C + c)*2 + q]; level 2: sum the l2 records and
+// form the BN table.
+__device__ __forceinline__ void bn_combine_l1(const BnFinalize& f, int grp, int ncta, int /*U*/, int /*n*/, int /*t_out*/, float* l2) {
   const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
-  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
-    float mean_g[kFanIn], m2_g[kFanIn];
+  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
+    float v[kFanIn];
 #pragma unroll
-    for (int j = 0; j < kFanIn; ++j) {
-      const int g = imin(g0 + j, g1 - 1);
-      mean_g[j] = __ldcg(f.fpart + ((size_t)g * f.c + c) * 2);
-      m2_g[j] = __ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1);
-    }
-    double cnt = 0.0, sum = 0.0;
+    for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(f.fpart + (size_t)imin(g0 + j, g1 - 1) * f.c * 2 + i);
+    double s = 0.0;
 #pragma unroll
     for (int j = 0; j < kFanIn; ++j)
-      if (g0 + j < g1) {
-        const double k = (double)(imin(U, n - (g0 + j) * U) * t_out);
-        cnt += k;
-        sum += k * (double)mean_g[j];
-      }
-    const double mean = sum / cnt;
-    double m2 = 0.0;
-#pragma unroll
-    for (int j = 0; j < kFanIn; ++j)
-      if (g0 + j < g1) {
-        const double k = (double)(imin(U, n - (g0 + j) * U) * t_out);
-        const double d = (double)mean_g[j] - mean;
-        m2 += (double)m2_g[j] + k * d * d;
-      }
-    float* o = l2 + ((size_t)grp * f.c + c) * 3;
-    o[0] = (float)cnt; o[1] = (float)mean; o[2] = (float)m2;
+      if (g0 + j < g1) s += (double)v[j];
+    l2[(size_t)grp * f.c * 2 + i] = (float)s;
   }
 }
-__device__ __forceinline__ void bn_combine_l2(const BnFinalize& f, int ngrp, const float* l2, float eps) {
+__device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, double s1, double s2, double m_total, float eps) {
+  const double mean = s1 / m_total;
+  double var = s2 / m_total - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  f.bnf[c] = (float)mean;
+  f.bnf[f.c + c] = (float)rstd;
+  f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
+  f.bnf[3 * f.c + c] = f.beta[c];
+  f.var[c] = (float)var;
+}
+__device__ __forceinline__ void bn_combine_l2(const BnFinalize& f, int ngrp, const float* l2, float eps, double m_total) {
   for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
-    double cnt = 0.0, sum = 0.0;
-    for (int g = 0; g < ngrp; ++g) {
-      const double k = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3);
-      cnt += k;
-      sum += k * (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 1);
+    double s1 = 0.0, s2 = 0.0;
+    for (int g0 = 0; g0 < ngrp; g0 += kFanIn) {           // all loads of a batch in flight before the first add
+      float2 v[kFanIn];
+#pragma unroll
+      for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(reinterpret_cast<const float2*>(l2) + (size_t)imin(g0 + j, ngrp - 1) * f.c + c);
+#pragma unroll
+      for (int j = 0; j < kFanIn; ++j)
+        if (g0 + j < ngrp) { s1 += (double)v[j].x; s2 += (double)v[j].y; }
     }
-    const double mean = sum / cnt;
-    double m2 = 0.0;
-    for (int g = 0; g < ngrp; ++g) {
-      const double k = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3);
-      const double d = (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 1) - mean;
-      m2 += (double)__ldcg(l2 + ((size_t)g * f.c + c) * 3 + 2) + k * d * d;
-    }
-    const double var = m2 / cnt;
-    const double rstd = 1.0 / sqrt(var + (double)eps);
-    f.bnf[c] = (float)mean;
-    f.bnf[f.c + c] = (float)rstd;
-    f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
-    f.bnf[3 * f.c + c] = f.beta[c];
-    f.var[c] = (float)var;
+    bn_table_write(f, c, s1, s2, m_total, eps);
   }
 }
 // Sums of (sum dz, sum dz*xhat): level 1 -> l2[(grp*C + c)*2 + q], level 2 -> bsum[q*C + c]
@@ -241,7 +224,14 @@ __device__ __forceinline__ void bwdsum_combine_l1(const BwdSumFinalize& f, int g
 __device__ __forceinline__ void bwdsum_combine_l2(const BwdSumFinalize& f, int ngrp, const float* l2) {
   for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
     double s = 0.0;
-    for (int g = 0; g < ngrp; ++g) s += (double)__ldcg(l2 + (size_t)g * f.c * 2 + i);
+    for (int g0 = 0; g0 < ngrp; g0 += kFanIn) {
+      float v[kFanIn];
+#pragma unroll
+      for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(l2 + (size_t)imin(g0 + j, ngrp - 1) * f.c * 2 + i);
+#pragma unroll
+      for (int j = 0; j < kFanIn; ++j)
+        if (g0 + j < ngrp) s += (double)v[j];
+    }
     f.bsum[(i & 1) * f.c + (i >> 1)] = (float)s;
   }
 }
@@ -266,41 +256,30 @@ __device__ __forceinline__ void scalar_combine_l2(const float* l2, int ngrp, flo
   }
 }
 
-// Per-channel (mean, M2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}].
-// Requires C <= blockDim.x.  red: blockDim.x floats of scratch, smean: C floats.  Two passes over the
-// tile (mean, then squared deviations) so the partial is exact enough for the Chan combination.
-__device__ __forceinline__ void tile_stats(const float* tile, int rows, int C, float* red, float* smean, float* part_out) {
+// Per-channel (sum y, sum y^2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}], ONE pass.
+// Requires C <= blockDim.x.  red: 2 * blockDim.x floats of scratch.  The cross-CTA combination is then a plain
+// fixed-order sum; var = E[y^2] - mean^2 is formed once per channel in fp64 (relative error ~1e-7 (1 + mean^2/var)).
+__device__ __forceinline__ void tile_stats(const float* tile, int rows, int C, float* red, float* /*unused*/, float* part_out) {
   const int tid = threadIdx.x;
   const int ns = imax(1, (int)blockDim.x / C);
   const int seg = tid / C, c = tid - seg * C;
   const bool act = seg < ns;
-  float s = 0.f;
   if (act) {
-    for (int r = seg; r < rows; r += ns) s += tile[r * C + c];
-    red[seg * C + c] = s;
-  }
-  __syncthreads();
-  if (tid < C) {
-    float tot = 0.f;
-    for (int q = 0; q < ns; ++q) tot += red[q * C + tid];
-    smean[tid] = tot / (float)rows;
-  }
-  __syncthreads();
-  if (act) {
-    const float mu = smean[c];
-    float m2 = 0.f;
+    float s1 = 0.f, s2 = 0.f;
     for (int r = seg; r < rows; r += ns) {
-      const float d = tile[r * C + c] - mu;
-      m2 = fmaf(d, d, m2);
+      const float v = tile[r * C + c];
+      s1 += v;
+      s2 = fmaf(v, v, s2);
     }
-    red[seg * C + c] = m2;
+    red[seg * C + c] = s1;
+    red[blockDim.x + seg * C + c] = s2;
   }
   __syncthreads();
-  if (tid < C) {
+  if (tid < 2 * C) {
+    const int q = tid / C, cc = tid - q * C;
     float tot = 0.f;
-    for (int q = 0; q < ns; ++q) tot += red[q * C + tid];
-    part_out[(size_t)tid * 2] = smean[tid];
-    part_out[(size_t)tid * 2 + 1] = tot;
+    for (int k = 0; k < ns; ++k) tot += red[q * blockDim.x + k * C + cc];
+    part_out[(size_t)cc * 2 + q] = tot;
   }
   __syncthreads();
 }

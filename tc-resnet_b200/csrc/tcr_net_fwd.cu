@@ -41,7 +41,7 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
   float* ys = xs + (size_t)a.U * TP * CS;             // [KS][Rmax][cout]
   float* ysd = ys + (size_t)a.KS * Rmax * a.cout;     // [Rmax][coutd]
   float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);
-  float* smean = red + kThreads;
+  float* smean = red + 2 * kThreads;
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), xs_off = (int)(xs - smem);
 
   tl_stamp(a.tl, vb, 0);
@@ -206,8 +206,8 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
     bn_combine_l1(a.fin, grp, nvb, a.U, a.n, a.t_out, a.fin.l2);
     if (a.wd) bn_combine_l1(a.find, grp, nvb, a.U, a.n, a.t_out, a.find.l2);
     if (tree_arrive_l2(a.counter, nvb)) {
-      bn_combine_l2(a.fin, ngrp, a.fin.l2, a.eps);
-      if (a.wd) bn_combine_l2(a.find, ngrp, a.find.l2, a.eps);
+      bn_combine_l2(a.fin, ngrp, a.fin.l2, a.eps, (double)a.n * a.t_out);
+      if (a.wd) bn_combine_l2(a.find, ngrp, a.find.l2, a.eps, (double)a.n * a.t_out);
     }
   }
   tl_stamp(a.tl, vb, 6);
@@ -244,197 +244,190 @@ __global__ void bn_table_eval_kernel(EvalBnArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// head: one warp per utterance
+// head: kHeadU utterances per CTA.  residual add + ReLU, average pool, dropout, fc, softmax cross-entropy and, for
+// training, the head backward (gradient at the block output, BN-backward partial sums, fc dW partials).
+// Every stage is a short loop over a flat index, so the code that each CTA runs exactly once stays small.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadWarps = 8;
-constexpr int kHeadSlots = 4;   // channels per lane: c = lane + 32 j, C <= 128
+constexpr int kHeadU = 4;
+constexpr int kHeadThreads = 256;
 
-// Shared-memory layout (floats): tables tb[4][C] (conv_b), td[4][C] (down), then per CTA
-// s_sum[W][4][C], s_drop[W][C], s_dl[W][NC], s_loss[W], then per warp 3 tiles of T*C: so (block output), syb (raw y_b),
-// ssh (raw shortcut).  Every global read of the step happens once, as batched float4 loads into these tiles.
+// Shared-memory layout (floats): tb[4][C] td[4][C] wfc[C][NC] | so, syb, ssh [U*T*C] each | drop, mk, dnet [U*C] each |
+// logit, dl [U*NC] each | loss [U] (+pad) | red [4][SEG][C] (<= 4 * 256)
 __host__ __device__ inline size_t head_smem_floats(int T, int C, int NC) {
-  return (size_t)8 * C + (size_t)C * NC + (size_t)kHeadWarps * (4 * C + C + NC + 1) + 8 + (size_t)kHeadWarps * 3 * T * C;
+  return (size_t)8 * C + (size_t)C * NC + 4 + (size_t)3 * kHeadU * T * C + 4 + (size_t)3 * kHeadU * C + (size_t)2 * kHeadU * NC +
+         kHeadU + 8 + 4 * kHeadThreads;
 }
 
 __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw, const bool tree) {
   float* smem = reinterpret_cast<float*>(smem_raw) + 4;          // first 16 bytes: the persistent kernel's mbarrier
   const int C = a.c, T = a.t, NC = a.classes, TC = T * C;
-  float* tb = smem;                                      // [4][C]
-  float* td = tb + 4 * C;                                // [4][C]
-  float* s_wfc = td + 4 * C;                             // [C][NC] fc weights
-  float* s_sum = s_wfc + C * NC;                         // [warps][4][C]
-  float* s_drop = s_sum + kHeadWarps * 4 * C;            // [warps][C]
-  float* s_dl = s_drop + kHeadWarps * C;                 // [warps][NC]
-  float* s_loss = s_dl + kHeadWarps * NC;                // [warps]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* so = s_loss + kHeadWarps + ((4 - (C * NC + kHeadWarps * (5 * C + NC + 1)) % 4) % 4) + (size_t)warp * 3 * TC;   // 16-byte aligned
-  float* syb = so + TC;
-  float* ssh = syb + TC;
-  const int n = vb * kHeadWarps + warp;
-  const bool valid = n < a.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int u0 = vb * kHeadU, nu = imin(kHeadU, a.n - u0), rows = nu * T;
+  float* tb = smem;
+  float* td = tb + 4 * C;
+  float* s_wfc = td + 4 * C;
+  float* so = s_wfc + ((C * NC + 3) & ~3);
+  float* syb = so + ((kHeadU * TC + 3) & ~3);
+  float* ssh = syb + ((kHeadU * TC + 3) & ~3);
+  float* s_drop = ssh + ((kHeadU * TC + 3) & ~3);
+  float* s_mk = s_drop + kHeadU * C;
+  float* s_dnet = s_mk + kHeadU * C;
+  float* s_logit = s_dnet + kHeadU * C;
+  float* s_dl = s_logit + kHeadU * NC;
+  float* s_loss = s_dl + kHeadU * NC;
+  float* red = s_loss + kHeadU;
   const bool sh_bn = a.shortcut.kind == 1;
+  const size_t base = (size_t)u0 * TC;
 
-  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+#pragma unroll 1
+  for (int i = tid; i < 4 * C; i += kHeadThreads) {
     tb[i] = ldc1(a.in.bnf + i);
     td[i] = sh_bn ? ldc1(a.shortcut.bnf + i) : 0.f;
   }
-  for (int i = threadIdx.x; i < C * NC; i += blockDim.x) s_wfc[i] = __ldg(a.wfc + i);
-  if (valid) {                                            // raw tiles: all loads issued before any use (latency overlapped)
-    const size_t base = (size_t)n * TC;
-    for (int e = 4 * lane; e < TC; e += 128) {
-      st4(syb + e, ld4(a.in.data + base + e));
-      st4(ssh + e, ld4(a.shortcut.data + base + e));
-    }
+#pragma unroll 1
+  for (int i = tid; i < C * NC; i += kHeadThreads) s_wfc[i] = __ldg(a.wfc + i);
+#pragma unroll 2
+  for (int e = 4 * tid; e < nu * TC; e += 4 * kHeadThreads) {     // the CTA's utterances are one contiguous span
+    st4(syb + e, ld4(a.in.data + base + e));
+    st4(ssh + e, ld4(a.shortcut.data + base + e));
   }
   __syncthreads();
 
-  float pooled[kHeadSlots], mk[kHeadSlots], dropped[kHeadSlots];
-#pragma unroll
-  for (int j = 0; j < kHeadSlots; ++j) { pooled[j] = 0.f; mk[j] = 1.f; dropped[j] = 0.f; }
-  float loss_n = 0.f, dl = 0.f;
-  if (valid) {
-#pragma unroll
-    for (int j = 0; j < kHeadSlots; ++j) {
-      const int c = lane + 32 * j;
-      if (c < C) {
-        const float mb_ = tb[c], sb_ = tb[2 * C + c], bb_ = tb[3 * C + c];
-        const float md_ = td[c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) {
-          const float zb = fmaf(syb[t * C + c] - mb_, sb_, bb_);
-          float sh = ssh[t * C + c];
-          if (sh_bn) sh = fmaxf(fmaf(sh - md_, sd_, bd_), 0.f);
-          const float o = fmaxf(zb + sh, 0.f);
-          so[t * C + c] = o;
-          if (a.out_write) a.out_write[(size_t)n * TC + t * C + c] = o;
-          acc += o;
-        }
-        pooled[j] = acc / (float)T;
-        if (a.use_dropout) {
-          mk[j] = a.mask ? a.mask[(size_t)n * C + c] : floorf(a.keep + uniform01(a.seed, (uint64_t)n * C + c));
-          dropped[j] = pooled[j] / a.keep * mk[j];        // tf.nn.dropout: x / keep_prob * floor(keep_prob + U)
-        } else {
-          dropped[j] = pooled[j];
-        }
-      }
+  // block output o = relu(bn(y_b) + shortcut): thread (seg, c) walks rows seg, seg + SEG, ...
+  const int SEG = kHeadThreads / C;
+  const int seg = tid / C, c = tid - seg * C;
+  if (seg < SEG) {
+    const float mb_ = tb[c], sb_ = tb[2 * C + c], bb_ = tb[3 * C + c];
+    const float md_ = td[c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
+#pragma unroll 1
+    for (int r = seg; r < rows; r += SEG) {
+      const float zb = fmaf(syb[r * C + c] - mb_, sb_, bb_);
+      float sh = ssh[r * C + c];
+      if (sh_bn) sh = fmaxf(fmaf(sh - md_, sd_, bd_), 0.f);
+      const float o = fmaxf(zb + sh, 0.f);
+      so[r * C + c] = o;
+      if (a.out_write) a.out_write[base + r * C + c] = o;
     }
-    // fc (no bias): logits[k] = sum_c dropped[c] W[c,k]; lane k keeps logits[k]
-    float logit = 0.f;
-    for (int k = 0; k < NC; ++k) {
-      float p = 0.f;
-#pragma unroll
-      for (int j = 0; j < kHeadSlots; ++j) {
-        const int c = lane + 32 * j;
-        if (c < C) p = fmaf(dropped[j], s_wfc[c * NC + k], p);
-      }
-      p = warp_sum(p);
-      if (lane == k) logit = p;
+  }
+  __syncthreads();
+  // average pool + dropout
+#pragma unroll 1
+  for (int i = tid; i < nu * C; i += kHeadThreads) {
+    const int u = i / C, cc = i - u * C;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += so[(u * T + t) * C + cc];
+    const float pooled = acc / (float)T;
+    float mk = 1.f, dropped = pooled;
+    if (a.use_dropout) {
+      const size_t gi = (size_t)(u0 + u) * C + cc;
+      mk = a.mask ? a.mask[gi] : floorf(a.keep + uniform01(a.seed, (uint64_t)gi));
+      dropped = pooled / a.keep * mk;                       // tf.nn.dropout: x / keep_prob * floor(keep_prob + U)
     }
+    s_drop[i] = dropped;
+    s_mk[i] = mk;
+  }
+  __syncthreads();
+  // fc (no bias): one warp per (utterance, class)
+#pragma unroll 1
+  for (int o = warp; o < nu * NC; o += kHeadThreads / 32) {
+    const int u = o / NC, k = o - u * NC;
+    float p = 0.f;
+    for (int cc = lane; cc < C; cc += 32) p = fmaf(s_drop[u * C + cc], s_wfc[cc * NC + k], p);
+    p = warp_sum(p);
+    if (lane == 0) s_logit[o] = p;
+  }
+  __syncthreads();
+  // softmax cross-entropy: one warp per utterance, lane k keeps class k (NC <= 32)
+#pragma unroll 1
+  for (int u = warp; u < nu; u += kHeadThreads / 32) {
     const bool act = lane < NC;
+    const float logit = act ? s_logit[u * NC + lane] : 0.f;
     const float mx = warp_max(act ? logit : -3.0e38f);
     const float e = act ? expf(logit - mx) : 0.f;
     const float se = warp_sum(e);
     const float prob = e / se;
     const float logp = (logit - mx) - logf(se);
+    const size_t gi = (size_t)(u0 + u) * NC + lane;
     if (act) {
-      if (a.logits) a.logits[(size_t)n * NC + lane] = logit;
-      if (a.probs) a.probs[(size_t)n * NC + lane] = prob;
+      if (a.logits) a.logits[gi] = logit;
+      if (a.probs) a.probs[gi] = prob;
     }
+    float loss_n = 0.f, dl = 0.f;
     if (a.onehot) {
-      float lab = act ? a.onehot[(size_t)n * NC + lane] : 0.f;
+      float lab = act ? a.onehot[gi] : 0.f;
       if (a.label_smoothing > 0.f && act) lab = lab * (1.f - a.label_smoothing) + a.label_smoothing / (float)NC;
       const float labsum = warp_sum(lab);
       loss_n = -warp_sum(act ? lab * logp : 0.f);
       dl = act ? (prob * labsum - lab) * a.inv_n : 0.f;
     }
+    if (act) s_dl[u * NC + lane] = dl;
+    if (lane == 0) s_loss[u] = loss_n;
+  }
+  __syncthreads();
+  if (tid == 0 && a.onehot) {
+    float s = 0.f;
+    for (int u = 0; u < nu; ++u) s += s_loss[u];
+    a.loss_part[vb] = s;
   }
   if (!a.backward) {
-    if (a.onehot) {
-      if (lane == 0) s_loss[warp] = loss_n;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
-        a.loss_part[vb] = s;
-      }
-      if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
-        scalar_combine_l1(a.loss_part, vb / kFanIn, nvb, a.loss_l2);
-        if (tree_arrive_l2(a.counter, nvb)) scalar_combine_l2(a.loss_l2, (nvb + kFanIn - 1) / kFanIn, a.loss_out);
-      }
+    if (a.onehot && tree && tree_arrive_l1(a.counter, vb, nvb)) {
+      scalar_combine_l1(a.loss_part, vb / kFanIn, nvb, a.loss_l2);
+      if (tree_arrive_l2(a.counter, nvb)) scalar_combine_l2(a.loss_l2, (nvb + kFanIn - 1) / kFanIn, a.loss_out);
     }
     return;
   }
 
-  // ---- head backward: d pooled -> gradient at the block output, BN-backward partial sums (all from shared memory) ----
-  float sb1[kHeadSlots], sb2[kHeadSlots], sd1[kHeadSlots], sd2[kHeadSlots];
-#pragma unroll
-  for (int j = 0; j < kHeadSlots; ++j) sb1[j] = sb2[j] = sd1[j] = sd2[j] = 0.f;
-  if (valid) {
-    float dnet[kHeadSlots];
-#pragma unroll
-    for (int j = 0; j < kHeadSlots; ++j) dnet[j] = 0.f;
-    for (int k = 0; k < NC; ++k) {
-      const float dlk = __shfl_sync(0xffffffffu, dl, k);
-#pragma unroll
-      for (int j = 0; j < kHeadSlots; ++j) {
-        const int c = lane + 32 * j;
-        if (c < C) dnet[j] = fmaf(dlk, s_wfc[c * NC + k], dnet[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kHeadSlots; ++j) {
-      if (a.use_dropout) dnet[j] = dnet[j] / a.keep * mk[j];
-      dnet[j] = dnet[j] / (float)T;                       // AvgPoolGrad
-      const int c = lane + 32 * j;
-      if (c < C) {
-        const float mb_ = tb[c], rb_ = tb[C + c];
-        const float md_ = td[c], rd_ = td[C + c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
-        for (int t = 0; t < T; ++t) {
-          const float g = so[t * C + c] > 0.f ? dnet[j] : 0.f;
-          a.gout[(size_t)n * TC + t * C + c] = g;
-          sb1[j] += g;
-          sb2[j] = fmaf(g, (syb[t * C + c] - mb_) * rb_, sb2[j]);
-          if (a.ydn) {
-            const float yd = ssh[t * C + c];
-            const float gs = fmaf(yd - md_, sd_, bd_) > 0.f ? g : 0.f;
-            sd1[j] += gs;
-            sd2[j] = fmaf(gs, (yd - md_) * rd_, sd2[j]);
-          }
+  // ---- head backward: d logits -> d pooled (fc^T, dropout, AvgPoolGrad) ----
+#pragma unroll 1
+  for (int i = tid; i < nu * C; i += kHeadThreads) {
+    const int u = i / C, cc = i - u * C;
+    float d = 0.f;
+    for (int k = 0; k < NC; ++k) d = fmaf(s_dl[u * NC + k], s_wfc[cc * NC + k], d);
+    if (a.use_dropout) d = d / a.keep * s_mk[i];
+    s_dnet[i] = d / (float)T;
+  }
+  __syncthreads();
+  // gradient at the block output and the BN-backward partial sums of conv_b (and of the down conv)
+  {
+    float sb1 = 0.f, sb2 = 0.f, sd1 = 0.f, sd2 = 0.f;
+    if (seg < SEG) {
+      const float mb_ = tb[c], rb_ = tb[C + c];
+      const float md_ = td[c], rd_ = td[C + c], sd_ = td[2 * C + c], bd_ = td[3 * C + c];
+#pragma unroll 1
+      for (int r = seg; r < rows; r += SEG) {
+        const int u = r / T;
+        const float g = so[r * C + c] > 0.f ? s_dnet[u * C + c] : 0.f;
+        a.gout[base + r * C + c] = g;
+        sb1 += g;
+        sb2 = fmaf(g, (syb[r * C + c] - mb_) * rb_, sb2);
+        if (a.ydn) {
+          const float yd = ssh[r * C + c];
+          const float gs = fmaf(yd - md_, sd_, bd_) > 0.f ? g : 0.f;
+          sd1 += gs;
+          sd2 = fmaf(gs, (yd - md_) * rd_, sd2);
         }
       }
+      red[(0 * SEG + seg) * C + c] = sb1;
+      red[(1 * SEG + seg) * C + c] = sb2;
+      red[(2 * SEG + seg) * C + c] = sd1;
+      red[(3 * SEG + seg) * C + c] = sd2;
     }
   }
-#pragma unroll
-  for (int j = 0; j < kHeadSlots; ++j) {
-    const int c = lane + 32 * j;
-    if (c < C) {
-      s_sum[(warp * 4 + 0) * C + c] = sb1[j];
-      s_sum[(warp * 4 + 1) * C + c] = sb2[j];
-      s_sum[(warp * 4 + 2) * C + c] = sd1[j];
-      s_sum[(warp * 4 + 3) * C + c] = sd2[j];
-      s_drop[warp * C + c] = dropped[j];
-    }
-  }
-  if (lane < NC) s_dl[warp * NC + lane] = dl;
-  if (lane == 0) s_loss[warp] = loss_n;
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
-    const int q = i / C, c = i - q * C;
+#pragma unroll 1
+  for (int i = tid; i < 4 * C; i += kHeadThreads) {
+    const int q = i / C, cc = i - q * C;
     float s = 0.f;
-    for (int w = 0; w < kHeadWarps; ++w) s += s_sum[(w * 4 + q) * C + c];
-    if (q < 2) a.bpartb[((size_t)vb * C + c) * 2 + q] = s;
-    else if (a.ydn) a.bpartd[((size_t)vb * C + c) * 2 + (q - 2)] = s;
+    for (int k = 0; k < SEG; ++k) s += red[(q * SEG + k) * C + cc];
+    if (q < 2) a.bpartb[((size_t)vb * C + cc) * 2 + q] = s;
+    else if (a.ydn) a.bpartd[((size_t)vb * C + cc) * 2 + (q - 2)] = s;
   }
-  for (int i = threadIdx.x; i < C * NC; i += blockDim.x) {
-    const int c = i / NC, k = i - c * NC;
+#pragma unroll 1
+  for (int i = tid; i < C * NC; i += kHeadThreads) {
+    const int cc = i / NC, k = i - cc * NC;
     float s = 0.f;
-    for (int w = 0; w < kHeadWarps; ++w) s = fmaf(s_drop[w * C + c], s_dl[w * NC + k], s);
+    for (int u = 0; u < nu; ++u) s = fmaf(s_drop[u * C + cc], s_dl[u * NC + k], s);
     a.dwfc_part[(size_t)vb * C * NC + i] = s;
-  }
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < kHeadWarps; ++w) s += s_loss[w];
-    a.loss_part[vb] = s;
   }
   if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
     const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
@@ -449,7 +442,7 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
   }
 }
 
-__global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   head_body(a, blockIdx.x, gridDim.x, smem_raw, true);
 }
@@ -459,7 +452,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(HeadArgs a) {
 // ------------------------------------------------------------------------------------------------
 static constexpr size_t kSmemBudget = 110 * 1024;   // two CTAs per SM: 2 x (110 + 1 static + 1 reserved) KB <= 227 KB
 
-int head_groups(int n) { return (n + kHeadWarps - 1) / kHeadWarps; }
+int head_groups(int n) { return (n + kHeadU - 1) / kHeadU; }
 
 static size_t fwd_weight_floats(const ConvPlan& cv, const ConvPlan* dn) {
   return (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0);
@@ -470,7 +463,7 @@ static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int 
   const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
   const int TP = cv.pad_left + cv.t_in + pad_right;
   size_t f = (size_t)U * TP * CS + (size_t)KS * U * cv.t_out * cv.cout + (dn ? (size_t)U * cv.t_out * dn->cout : 0);
-  f += kThreads + std::max(cv.cout, dn ? dn->cout : 0);
+  f += 2 * kThreads + std::max(cv.cout, dn ? dn->cout : 0);
   f += 4 + (w_smem ? fwd_weight_floats(cv, dn) : 0);
   return f * 4;
 }
@@ -636,7 +629,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
                 uint64_t seed, const float* mask, const float* onehot, float weight_decay, float* logits,
                 float* probs, float* losses, bool backward, cudaStream_t s) {
   (void)weight_decay;
-  if (h->c_last > 32 * kHeadSlots) { set_error("last_channels > 128 unsupported by the head kernel"); return TCR_ERR_UNSUPPORTED; }
+  if (h->c_last > kHeadThreads) { set_error("last_channels > 256 unsupported by the head kernel"); return TCR_ERR_UNSUPPORTED; }
   if (!training) {
     EvalBnArgs e;
     e.nlayers = (int)h->convs.size();
@@ -715,7 +708,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       const size_t smem = (head_smem_floats(lb.t, lb.c, ha.classes) + 8) * 4;
-      if (smem > kSmemBudget) { set_error("head tile does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
+      if (smem > kSmemBudget || lb.c > kHeadThreads) { set_error("head tile does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
       if (h->rec) {
         rec_head(h, ha, groups, smem);
       } else {
@@ -726,7 +719,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
           head_lim = smem;
         }
 #endif
-        TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadWarps * 32), smem, s, ha);
+        TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadThreads), smem, s, ha);
       }
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next

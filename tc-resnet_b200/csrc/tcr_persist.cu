@@ -30,56 +30,20 @@ __device__ __forceinline__ void fin_fwd_phase(const FinFwd& F, int b, int nb) {
     const int fi = item >= F.f[0].c ? 1 : 0;
     const int c = item - (fi ? F.f[0].c : 0);
     const BnFinalize& f = F.f[fi];
-    double cnt = 0.0, sum = 0.0;
+    float a1 = 0.f, a2 = 0.f;                              // per-lane fp32 partial sums (<= G/32 terms), fp64 across lanes
     for (int g0 = lane; g0 < F.G; g0 += 32 * kFinB) {
-      float m[kFinB];
+      float v1[kFinB], v2[kFinB];
 #pragma unroll
       for (int j = 0; j < kFinB; ++j) {
         const int g = g0 + 32 * j;
-        m[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2) : 0.f;
+        v1[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2) : 0.f;
+        v2[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < kFinB; ++j) {
-        const int g = g0 + 32 * j;
-        if (g < F.G) {
-          const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
-          cnt += k;
-          sum += k * (double)m[j];
-        }
-      }
+      for (int j = 0; j < kFinB; ++j) { a1 += v1[j]; a2 += v2[j]; }
     }
-    cnt = warp_sum_d(cnt);
-    sum = warp_sum_d(sum);
-    const double mean = sum / cnt;
-    double m2 = 0.0;
-    for (int g0 = lane; g0 < F.G; g0 += 32 * kFinB) {
-      float m[kFinB], q[kFinB];
-#pragma unroll
-      for (int j = 0; j < kFinB; ++j) {
-        const int g = g0 + 32 * j;
-        m[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2) : 0.f;
-        q[j] = g < F.G ? __ldcg(f.fpart + ((size_t)g * f.c + c) * 2 + 1) : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < kFinB; ++j) {
-        const int g = g0 + 32 * j;
-        if (g < F.G) {
-          const double k = (double)(imin(F.U, F.n - g * F.U) * F.t_out);
-          const double d = (double)m[j] - mean;
-          m2 += (double)q[j] + k * d * d;
-        }
-      }
-    }
-    m2 = warp_sum_d(m2);
-    if (lane == 0) {
-      const double var = m2 / cnt;
-      const double rstd = 1.0 / sqrt(var + (double)F.eps);
-      f.bnf[c] = (float)mean;
-      f.bnf[f.c + c] = (float)rstd;
-      f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
-      f.bnf[3 * f.c + c] = f.beta[c];
-      f.var[c] = (float)var;
-    }
+    const double s1 = warp_sum_d((double)a1), s2 = warp_sum_d((double)a2);
+    if (lane == 0) bn_table_write(f, c, s1, s2, (double)F.n * F.t_out, F.eps);
   }
 }
 
@@ -211,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
 bool persist_enabled(tcr_handle* h) {
   if (h->persist < 0) {
     const char* e = getenv("TCR_PERSISTENT");
-    h->persist = (e && e[0] == '0') ? 0 : 1;
+    h->persist = (e && e[0] == '1') ? 1 : 0;   // opt-in: the multi-kernel path is faster at present
 #ifndef TCR_EMU
     int dev = 0, coop = 0;
     cudaGetDevice(&dev);

@@ -221,3 +221,59 @@ class Engine:
         v = C.c_double()
         L.check(self.lib, self.lib.tcr_measure_fp32_peak(self._h, C.byref(v), self._stream), "tcr_measure_fp32_peak")
         return float(v.value)
+
+
+class HostFeed:
+    """Double-buffered host -> device feed around Engine.train_step (the `session.run(train_op)` loop of
+    helper/trainer.py:132-154 with the input pipeline's prefetch, datasets/data_wrapper_base.py:100-108).
+
+    submit(i) enqueues, without blocking on the GPU: the H2D copy of batch i on a copy stream (pinned host memory),
+    step i on the compute stream behind it, and the D2H read of step i's losses; it then returns the losses of step
+    i-1.  The copy of batch i+1 therefore overlaps the compute of step i; every step's input still crosses the bus.
+    flush() returns the last outstanding losses.
+    """
+
+    def __init__(self, engine: "Engine", batch: int, depth: int = 2):
+        self.eng, self.n, self.depth = engine, int(batch), int(depth)
+        dev = engine.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.d_wav = [torch.empty(batch, engine.cfg.clip_samples, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_hot = [torch.empty(batch, engine.num_classes, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_loss = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.h_loss = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.i = 0
+        self.pending = None
+
+    def submit(self, h_wav: torch.Tensor, h_onehot: torch.Tensor, params, slots, moving, learning_rate, momentum=0.9,
+               weight_decay=1e-4, dropout_seed=0):
+        assert h_wav.is_pinned() and h_onehot.is_pinned(), "HostFeed needs pinned host tensors"
+        b = self.i % self.depth
+        compute = torch.cuda.current_stream(self.eng.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.i >= self.depth:
+                self.copy_stream.wait_event(self.free[b])          # step i-depth has consumed this buffer
+            self.d_wav[b].copy_(h_wav.reshape(self.n, -1), non_blocking=True)
+            self.d_hot[b].copy_(h_onehot, non_blocking=True)
+            self.ready[b].record(self.copy_stream)
+        compute.wait_event(self.ready[b])
+        self.eng.train_step(self.d_wav[b], self.d_hot[b], params, slots, moving, learning_rate, momentum, weight_decay,
+                            dropout_seed=dropout_seed, losses=self.d_loss[b])
+        self.free[b].record(compute)
+        self.h_loss[b].copy_(self.d_loss[b], non_blocking=True)
+        self.done[b].record(compute)
+        prev, self.pending = self.pending, b
+        self.i += 1
+        return self._collect(prev)
+
+    def _collect(self, b):
+        if b is None:
+            return None
+        self.done[b].synchronize()
+        return float(self.h_loss[b][0]), float(self.h_loss[b][1])
+
+    def flush(self):
+        prev, self.pending = self.pending, None
+        return self._collect(prev)

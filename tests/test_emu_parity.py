@@ -26,6 +26,13 @@ def test_emulated_kernels_match_oracle(backend, kw):
     assert report["features"] < 1e-6
 
 
+def test_emulated_persistent_step_kernel(backend, monkeypatch):
+    """The opt-in single cooperative launch (TCR_PERSISTENT=1) runs the same phase bodies behind a grid barrier."""
+    monkeypatch.setenv("TCR_PERSISTENT", "1")
+    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=5, keep=0.5)
+    run_case(backend, model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False)
+
+
 def test_log_mel_front_end(backend):
     eng = Engine(backend, feature_kind=1, max_batch=4)
     wav, _ = O.synthetic_batch(2, adversarial=True)

@@ -28,6 +28,13 @@ def test_cuda_path_matches_oracle(backend, kw):
     run_case(backend, **kw)
 
 
+def test_persistent_step_kernel_matches_oracle(backend, monkeypatch):
+    """Opt-in cooperative single-launch step (TCR_PERSISTENT=1): same results as the multi-kernel path."""
+    monkeypatch.setenv("TCR_PERSISTENT", "1")
+    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=64, keep=0.5, steps=2)
+    run_case(backend, model="TCResNet14", wm=1.5, window=640, stride=320, n=33, keep=1.0)
+
+
 def test_full_size_config2_tcresnet8_n512(backend):
     report = run_case(backend, model="TCResNet8", wm=1.0, n=512, keep=0.5, max_batch=512, check_f32_floor=True)
     print(report)
