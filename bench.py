@@ -193,7 +193,15 @@ def kernel_work(plan, name, n):
         return bytes_, 2.0 * n * macs
     if name == "head":
         return n * (3 * 4 * plan.t_last * plan.c_last), 2.0 * n * plan.c_last * plan.num_classes * 2
-    return 12.0 * plan.num_trainable, 4.0 * plan.num_trainable
+    if name == "dw_grouped":          # every layer's weight gradient in one launch: reads x, dz, y of each layer once
+        b = sum(n * (4 * c.t_in * c.cin + 8 * c.t_out * c.cout) + 4 * c.weights for c in plan.convs())
+        return b, 2.0 * n * sum(c.macs for c in plan.convs())
+    if name == "weight_transpose":
+        w = sum(c.weights for c in plan.convs())
+        return 8.0 * w, 0.0
+    if name == "step_persistent":     # the whole step behind the front-end in one cooperative launch
+        return n * (plan.min_bytes(n) - 4 * plan.clip), n * (plan.train_flops() - plan.frontend_flops())
+    return 12.0 * plan.num_trainable, 4.0 * plan.num_trainable      # grad_finalize / update: params, slots, grads
 
 
 def run_ours(a):
@@ -291,8 +299,22 @@ def run_ours(a):
             dur = tms / cnt * 1e-3
             kernels.append({"name": name, "us": dur * 1e6, "share": tms / total_ms, "GBps": b / dur / 1e9, "TFLOPs": f / dur / 1e12})
         dom = kernels[0]
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/, same workload)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_tcresnet8_b512.json")))
+            if a.model == "TCResNet8" and a.width == 1.0 and n == 512:
+                ncu_name = {"mfcc": "mfcc_kernel", "dw_grouped": "dw_grouped_kernel", "head": "head_kernel",
+                            "step_persistent": "step_kernel"}.get(dom["name"])
+                for k, v in tj["bytes_per_launch"].items():
+                    if ncu_name and k.startswith(ncu_name):
+                        traffic, traffic_src = v, f"profiles/ncu_traffic_tcresnet8_b512.json ({tj['source']})"
+        except Exception:
+            pass
+        alg_bytes = kernel_work(plan, dom["name"], n)[0]
         out["roofline"] = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                           "frac": dom["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                           "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                           "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                            "kernel_share_of_step": dom["share"],
                            "fp32": {"achieved_tflops": dom["TFLOPs"], "peak_tflops": fp32_peak, "frac": dom["TFLOPs"] / max(fp32_peak, 1e-9),
                                     "peak_source": "measured in this run (tcr_measure_fp32_peak, FMA loop on all SMs)"},
