@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCR_ABI_VERSION 1
+#define TCR_ABI_VERSION 2
 
 enum {
   TCR_OK = 0,
@@ -38,6 +38,14 @@ enum {
 
 enum { TCR_MODEL_TCRESNET8 = 8, TCR_MODEL_TCRESNET14 = 14 };
 enum { TCR_FEATURE_MFCC = 0, TCR_FEATURE_LOG_MEL = 1 };
+/* What `input` points at (the `input_is_features` argument / field):
+ *   TCR_INPUT_WAV_F32   fp32 samples in [-1,1], the output of contrib_audio.decode_wav + augmentation
+ *                       (datasets/audio_data_wrapper.py:57-112);
+ *   TCR_INPUT_FEATURES  precomputed features [n,T,F];
+ *   TCR_INPUT_WAV_PCM16 int16 PCM samples as stored in the wav files; the kernel applies decode_wav's 1/32768 scaling
+ *                       (exact in fp32), so the result is bit-identical to TCR_INPUT_WAV_F32 on the decoded samples.
+ *                       Halves the host->device bytes of an un-augmented (evaluation / inference) batch. */
+enum { TCR_INPUT_WAV_F32 = 0, TCR_INPUT_FEATURES = 1, TCR_INPUT_WAV_PCM16 = 2 };
 
 typedef struct tcr_handle tcr_handle;
 typedef void* tcr_stream;   /* cudaStream_t */
@@ -101,8 +109,8 @@ typedef struct tcr_param_desc {
 
 /* Arguments of one training step == one `session.run(train_op)` of helper/trainer.py:312-321. */
 typedef struct tcr_step_args {
-  const float* input;        /* wav [n, clip_samples] in [-1,1], or features [n,T,F] if input_is_features */
-  int32_t      input_is_features;
+  const float* input;        /* wav [n, clip_samples] in [-1,1], features [n,T,F], or (cast) int16 PCM: see TCR_INPUT_* */
+  int32_t      input_is_features;   /* TCR_INPUT_WAV_F32 | TCR_INPUT_FEATURES | TCR_INPUT_WAV_PCM16 */
   const float* onehot;       /* [n, num_classes] fp32 (datasets/audio_data_wrapper.py:113-118) */
   int32_t      n;            /* utterances on THIS rank */
   float*       params;       /* flat trainables, updated in place */
@@ -143,6 +151,8 @@ int tcr_init_variables(tcr_handle* h, float* params, float* slots, float* moving
  * Replaces MFCCPreprocessor._preprocess / LogMelSpectrogramPreprocessor._preprocess
  * (datasets/preprocessors.py:64-96, 162-170, 183-194). */
 int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream);
+/* Same front-end on int16 PCM samples [n, clip_samples] (decode_wav's 1/32768 scaling fused into the framing). */
+int tcr_mfcc_forward_pcm16(tcr_handle* h, const int16_t* pcm, float* features, int32_t n, tcr_stream stream);
 
 /* Forward pass.  is_training == 0: evaluate_audio.py path (BN moving statistics, dropout identity;
  * helper/base.py:52-125).  is_training == 1: the training graph's forward (batch statistics, dropout)

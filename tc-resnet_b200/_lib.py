@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtcr_b200.so")
 
 TCR_MODEL_TCRESNET8 = 8
 TCR_MODEL_TCRESNET14 = 14
+TCR_INPUT_WAV_F32, TCR_INPUT_FEATURES, TCR_INPUT_WAV_PCM16 = 0, 1, 2
 TCR_FEATURE_MFCC = 0
 TCR_FEATURE_LOG_MEL = 1
 KIND_NAMES = {0: "weight", 1: "beta", 2: "gamma", 3: "moving_mean", 4: "moving_variance"}
@@ -80,6 +81,7 @@ SYMBOLS = {
     "tcr_param_table": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(TcrParamDesc)), C.POINTER(C.c_int32)]),
     "tcr_init_variables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tcr_mfcc_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tcr_mfcc_forward_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "tcr_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                               C.c_uint64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
@@ -112,8 +114,8 @@ def load(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the export is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.tcr_abi_version() != 1:
-        raise TcrError(f"ABI version mismatch: library {lib.tcr_abi_version()}, binding 1")
+    if lib.tcr_abi_version() != 2:
+        raise TcrError(f"ABI version mismatch: library {lib.tcr_abi_version()}, binding 2")
     return lib
 
 

@@ -157,9 +157,10 @@ static int build_frontend_tables(tcr_handle* h) {
   return TCR_OK;
 }
 
-static MfccArgs mfcc_args(const tcr_handle* h, const float* wav, float* feat) {
+static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float* feat) {
   MfccArgs a;
   a.wav = wav;
+  a.pcm16 = pcm16;
   a.feat = feat;
   a.clip = h->cfg.clip_samples;
   a.window = h->cfg.window_size_samples;
@@ -416,14 +417,22 @@ static int check_n(const tcr_handle* h, int n) {
   return TCR_OK;
 }
 
-extern "C" int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream) {
+static int mfcc_run(tcr_handle* h, const void* wav, int pcm16, float* features, int32_t n, tcr_stream stream) {
   if (!h || !wav || !features) return fail(TCR_ERR_INVALID, "NULL argument");
   TCR_TRY(check_n(h, n));
   if (((uintptr_t)wav & 15) != 0) return fail(TCR_ERR_INVALID, "wav must be 16-byte aligned (TMA bulk copy)");
-  MfccArgs a = mfcc_args(h, wav, features);
+  if (pcm16 && (h->cfg.window_size_samples % 8 || h->cfg.window_stride_samples % 8 || h->cfg.clip_samples % 8))
+    return fail(TCR_ERR_UNSUPPORTED, "int16 input needs window, stride and clip lengths that are multiples of 8 samples");
+  MfccArgs a = mfcc_args(h, wav, pcm16, features);
   if (mfcc_launch(a, n, h->fft, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc launch configuration failed");
   TCR_CUDA(cudaGetLastError());
   return TCR_OK;
+}
+extern "C" int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream) {
+  return mfcc_run(h, wav, 0, features, n, stream);
+}
+extern "C" int tcr_mfcc_forward_pcm16(tcr_handle* h, const int16_t* pcm, float* features, int32_t n, tcr_stream stream) {
+  return mfcc_run(h, pcm, 1, features, n, stream);
 }
 
 extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, const float* params,
@@ -435,8 +444,9 @@ extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_f
   TCR_TRY(check_n(h, n));
   cudaStream_t s = (cudaStream_t)stream;
   const float* feat = input;
-  if (!input_is_features) {
-    TCR_TRY(tcr_mfcc_forward(h, input, h->d_feat, n, stream));
+  if (input_is_features != TCR_INPUT_FEATURES) {
+    if (input_is_features != TCR_INPUT_WAV_F32 && input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "unknown input kind %d", input_is_features);
+    TCR_TRY(mfcc_run(h, input, input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, n, stream));
     feat = h->d_feat;
   }
   int rc = net_forward(h, feat, params, moving, n, is_training != 0, dropout_seed, dropout_mask, onehot, weight_decay,
@@ -453,8 +463,9 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
   TCR_TRY(check_n(h, a->n));
   cudaStream_t s = (cudaStream_t)stream;
   const float* feat = a->input;
-  if (!a->input_is_features) {
-    TCR_TRY(tcr_mfcc_forward(h, a->input, h->d_feat, a->n, stream));
+  if (a->input_is_features != TCR_INPUT_FEATURES) {
+    if (a->input_is_features != TCR_INPUT_WAV_F32 && a->input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "unknown input kind %d", a->input_is_features);
+    TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, a->n, stream));
     feat = h->d_feat;
   }
   if (persist_enabled(h)) rec_begin(h);      // record the step's phases; net_update launches the persistent kernel

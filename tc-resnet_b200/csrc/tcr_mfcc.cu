@@ -90,27 +90,62 @@ __device__ __forceinline__ void fft_pass(float2* z, int N, int Ns, const float2*
   __syncwarp();
 }
 
-template <int NF2>
-__device__ __forceinline__ void fft_warp(float2* z, const float2* __restrict__ tw, int lane) {
+// First pass (Ns = 1: all twiddles are 1) fused with framing: the butterfly inputs are read straight from the staged
+// samples, multiplied by the window and packed as complex z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); n >= window/2 is the zero
+// padding up to the FFT length.  PCM: samples are int16 and scaled by 1/32768 like decode_wav (exact in fp32).
+template <bool PCM>
+__device__ __forceinline__ float2 frame_sample(const void* x, const float2* __restrict__ wtab, int n, int half_w) {
+  if (n >= half_w) return make_float2(0.f, 0.f);
+  float2 xs;
+  if (PCM) {
+    const uint32_t u = reinterpret_cast<const uint32_t*>(x)[n];
+    xs = make_float2((float)(short)(u & 0xffffu) * (1.0f / 32768.0f), (float)(short)(u >> 16) * (1.0f / 32768.0f));
+  } else {
+    xs = ld2(reinterpret_cast<const float*>(x) + 2 * n);
+  }
+  const float2 ws = __ldg(wtab + n);
+  return make_float2(xs.x * ws.x, xs.y * ws.y);
+}
+template <int R, int MAXQ, bool PCM>
+__device__ __forceinline__ void fft_first_pass(const void* x, const float2* __restrict__ wtab, int half_w, float2* z, int N, int lane) {
+  const int nb = N / R;
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int j = lane + 32 * q;
+    if (j < nb) {
+      float2 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = frame_sample<PCM>(x, wtab, j + r * nb, half_w);
+      dft_small<R>(v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) z[zi(j * R + r)] = v[r];
+    }
+  }
+  __syncwarp();
+}
+
+template <int NF2, bool PCM>
+__device__ __forceinline__ void fft_warp(const void* x, const float2* __restrict__ wtab, int half_w, float2* z,
+                                         const float2* __restrict__ tw, int lane) {
   if (NF2 == 1024) {
-    fft_pass<8, 4>(z, 1024, 1, tw, lane);
+    fft_first_pass<8, 4, PCM>(x, wtab, half_w, z, 1024, lane);
     fft_pass<8, 4>(z, 1024, 8, tw, lane);
     fft_pass<8, 4>(z, 1024, 64, tw, lane);
     fft_pass<2, 16>(z, 1024, 512, tw, lane);
   } else if (NF2 == 512) {
-    fft_pass<8, 2>(z, 512, 1, tw, lane);
+    fft_first_pass<8, 2, PCM>(x, wtab, half_w, z, 512, lane);
     fft_pass<8, 2>(z, 512, 8, tw, lane);
     fft_pass<8, 2>(z, 512, 64, tw, lane);
   } else if (NF2 == 256) {
-    fft_pass<8, 1>(z, 256, 1, tw, lane);
+    fft_first_pass<8, 1, PCM>(x, wtab, half_w, z, 256, lane);
     fft_pass<8, 1>(z, 256, 8, tw, lane);
     fft_pass<4, 2>(z, 256, 64, tw, lane);
   } else if (NF2 == 128) {
-    fft_pass<8, 1>(z, 128, 1, tw, lane);
+    fft_first_pass<8, 1, PCM>(x, wtab, half_w, z, 128, lane);
     fft_pass<4, 1>(z, 128, 8, tw, lane);
     fft_pass<4, 1>(z, 128, 32, tw, lane);
   } else {  // 64
-    fft_pass<8, 1>(z, 64, 1, tw, lane);
+    fft_first_pass<8, 1, PCM>(x, wtab, half_w, z, 64, lane);
     fft_pass<8, 1>(z, 64, 8, tw, lane);
   }
 }
@@ -120,7 +155,7 @@ __device__ __forceinline__ void fft_warp(float2* z, const float2* __restrict__ t
 //   wav   : span floats             (TMA destination, 16-byte aligned)
 //   tw    : NF2 float2              FFT twiddles exp(-2 pi i n / NF2)
 //   per warp: z   (NF2 + NF2/16) float2, pw (NF2 + 1 [+pad]) floats, lm (mel_bins) floats
-template <int NF2>
+template <int NF2, bool PCM>
 __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   TCR_DYNAMIC_SMEM(smem);
   const int lane = threadIdx.x & 31;
@@ -129,11 +164,12 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   const int utt = blockIdx.y;
   const int f0 = blockIdx.x * a.fpb;
   const int nf = min(a.fpb, a.frames - f0);
+  constexpr int SB = PCM ? 2 : 4;                         // bytes per staged sample
 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  float* s_wav = reinterpret_cast<float*>(smem + 16);
+  unsigned char* s_wav = smem + 16;
   const int span_max = (a.fpb - 1) * a.stride + a.window;
-  float2* s_tw = reinterpret_cast<float2*>(s_wav + span_max);
+  float2* s_tw = reinterpret_cast<float2*>(s_wav + (size_t)span_max * 4);
   const int z_elems = NF2 + (NF2 >> 4);
   const int pw_elems = ((NF2 + 1 + 3) / 4) * 4;
   const int per_warp_floats = 2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3);
@@ -142,12 +178,13 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   float* pw = s_warp + 2 * z_elems;
   float* lm = pw + pw_elems;
 
-  const int span = (nf - 1) * a.stride + a.window;   // floats actually needed (multiple of 4)
+  const int span = (nf - 1) * a.stride + a.window;   // samples actually needed (span * SB is a multiple of 16)
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)span * 4u);
-    tma_load_1d(s_wav, a.wav + (size_t)utt * a.clip + (size_t)f0 * a.stride, (uint32_t)span * 4u, bar);
+    mbar_expect_tx(bar, (uint32_t)span * SB);
+    tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB,
+                (uint32_t)span * SB, bar);
   }
   for (int i = threadIdx.x; i < NF2; i += blockDim.x) s_tw[i] = __ldg(&a.tw[i]);   // overlaps the bulk copy
   mbar_wait(bar, 0);
@@ -155,45 +192,62 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
 
   const int half_w = a.window >> 1;
   for (int f = warp; f < nf; f += nwarps) {
-    const float* x = s_wav + f * a.stride;
-    // windowed frame packed as complex: z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); zero padding to fft length
-    for (int n = lane; n < NF2; n += 32) {
-      float2 v = make_float2(0.f, 0.f);
-      if (n < half_w) {
-        const float2 xs = ld2(x + 2 * n);
-        const float2 ws = __ldg(reinterpret_cast<const float2*>(a.window_tab) + n);
-        v = make_float2(xs.x * ws.x, xs.y * ws.y);
-      }
-      z[zi(n)] = v;
-    }
-    __syncwarp();
-    fft_warp<NF2>(z, s_tw, lane);
-    // real-FFT post-processing: X[k] = E + (-i) e^{-2 pi i k / fft} O, E/O = (Z[k] +- conj(Z[NF2-k])) / 2
-    for (int k = lane; k <= NF2; k += 32) {
-      const float2 zk = z[zi(k & (NF2 - 1))];
+    fft_warp<NF2, PCM>(s_wav + (size_t)f * a.stride * SB, reinterpret_cast<const float2*>(a.window_tab), half_w, z, s_tw, lane);
+    // real-FFT post-processing, bins k and NF2-k from the same pair (Z[k], Z[NF2-k]):
+    //   E = (Z[k] + conj Z[NF2-k]) / 2, O = (Z[k] - conj Z[NF2-k]) / 2, T = e^{-2 pi i k / fft} O
+    //   X[k] = E - i T,  X[NF2-k] = conj(E) - i conj(T) ... written out below in components
+#pragma unroll 1
+    for (int k = lane; k <= NF2 / 2; k += 32) {
+      const float2 zk = z[zi(k)];
       const float2 zr = z[zi((NF2 - k) & (NF2 - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
       const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y + zr.y));
       const float2 t = cmul(__ldg(&a.tw2[k]), o);
-      const float xr = e.x + t.y, xi = e.y - t.x;
-      const float p = xr * xr + xi * xi;
-      pw[k] = a.magnitude ? sqrtf(p) : p;
+      const float ar = e.x + t.y, ai = e.y - t.x;          // X[k]
+      const float br = e.x - t.y, bi = e.y + t.x;          // X[NF2-k] (imaginary part negated: only |.|^2 is used)
+      const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+      pw[k] = a.magnitude ? sqrtf(pa) : pa;
+      pw[NF2 - k] = a.magnitude ? sqrtf(pb) : pb;
     }
     __syncwarp();
-    // banded mel + log
-    for (int m = lane; m < a.mel_bins; m += 32) {
-      const int start = __ldg(&a.mel_start[m]), len = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
-      float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(pw[start + i], __ldg(&a.mel_w[off + i]), acc);
-      lm[m] = logf(acc + 1e-6f);
+    // banded mel + log; a lane takes bins i and mel_bins-1-i so short and long bands pair up
+#pragma unroll 1
+    for (int i = lane; 2 * i < a.mel_bins; i += 32) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int m = h ? a.mel_bins - 1 - i : i;
+        if (h && m == i) break;
+        const int start = __ldg(&a.mel_start[m]), len = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
+        float acc = 0.f;
+        for (int q = 0; q < len; ++q) acc = fmaf(pw[start + q], __ldg(&a.mel_w[off + q]), acc);
+        lm[m] = logf(acc + 1e-6f);
+      }
     }
     __syncwarp();
     float* out = a.feat + ((size_t)utt * a.frames + (f0 + f)) * a.features;
     if (a.use_dct) {
-      for (int c = lane; c < a.features; c += 32) {
-        float acc = 0.f;
-        for (int m = 0; m < a.mel_bins; ++m) acc = fmaf(lm[m], __ldg(&a.dct[m * a.features + c]), acc);
-        out[c] = acc;
+      // DCT: lane (q, g) = (lane / 8, lane % 8) sums mel bins m = q, q + 4, ... for coefficients c = g, g + 8, ...; the four
+      // quarter sums meet through two shuffles.  All 32 lanes stay busy for any coefficient count <= 64.
+      const int q = lane >> 3, g = lane & 7;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      const int nj = (a.features + 7) >> 3;
+#pragma unroll 2
+      for (int m = q; m < a.mel_bins; m += 4) {
+        const float v = lm[m];
+        const float* row = a.dct + m * a.features + g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nj && g + 8 * j < a.features) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nj) {
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+          if (q == 0 && g + 8 * j < a.features) out[g + 8 * j] = acc[j];
+        }
       }
     } else {
       for (int c = lane; c < a.features; c += 32) out[c] = lm[c];
@@ -219,18 +273,19 @@ int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
 #ifndef TCR_EMU
 #define TCR_MFCC_CASE(NF2)                                                                                   \
   case NF2: {                                                                                                \
-    auto k = mfcc_kernel<NF2>;                                                                               \
-    static size_t smem_limit = 32 * 1024;                                                                    \
-    if (smem > smem_limit) {                                                                                 \
+    auto k = a.pcm16 ? mfcc_kernel<NF2, true> : mfcc_kernel<NF2, false>;                                     \
+    static size_t smem_limit[2] = {32 * 1024, 32 * 1024};                                                    \
+    size_t& lim = smem_limit[a.pcm16 ? 1 : 0];                                                               \
+    if (smem > lim) {                                                                                 \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-      smem_limit = smem;                                                                                     \
+      lim = smem;                                                                                            \
     }                                                                                                        \
     TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);                                                             \
   } break;
 #else
 #define TCR_MFCC_CASE(NF2)                         \
   case NF2: {                                      \
-    auto k = mfcc_kernel<NF2>;                     \
+    auto k = a.pcm16 ? mfcc_kernel<NF2, true> : mfcc_kernel<NF2, false>; \
     TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);   \
   } break;
 #endif

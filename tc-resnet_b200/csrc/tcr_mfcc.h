@@ -5,7 +5,8 @@
 namespace tcr {
 
 struct MfccArgs {
-  const float* wav;         // [N, clip]
+  const void* wav;          // [N, clip] fp32 samples, or int16 PCM when pcm16 != 0
+  int pcm16;
   float* feat;              // [N, frames, features]
   int clip, window, stride, frames, features, mel_bins;
   int fpb;                  // frames per CTA (== warps per CTA)

@@ -91,11 +91,21 @@ class Engine:
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
     @staticmethod
-    def _ptr(t):
+    def _ptr(t, dtype=torch.float32):
         if t is None:
             return None
-        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous fp32 CUDA tensor"
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"expected contiguous {dtype} CUDA tensor"
         return t.data_ptr()
+
+    def _input(self, inputs, input_is_features):
+        """(pointer, TCR_INPUT_* kind): fp32 wav, precomputed features, or int16 PCM (decode_wav scaling on device)."""
+        n = inputs.shape[0]
+        if input_is_features:
+            return self._ptr(inputs), L.TCR_INPUT_FEATURES
+        inputs = inputs.reshape(n, -1)
+        if inputs.dtype == torch.int16:
+            return self._ptr(inputs, torch.int16), L.TCR_INPUT_WAV_PCM16
+        return self._ptr(inputs), L.TCR_INPUT_WAV_F32
 
     # ------------------------------------------------------------------ variables
     def new_variables(self, seed: int = 0):
@@ -141,19 +151,22 @@ class Engine:
         wav = wav.reshape(wav.shape[0], -1)
         n = wav.shape[0]
         out = out if out is not None else self._f32(n, self.frames, self.features)
-        L.check(self.lib, self.lib.tcr_mfcc_forward(self._h, self._ptr(wav), self._ptr(out), n, self._stream),
-                "tcr_mfcc_forward")
+        if wav.dtype == torch.int16:
+            L.check(self.lib, self.lib.tcr_mfcc_forward_pcm16(self._h, self._ptr(wav, torch.int16), self._ptr(out), n, self._stream),
+                    "tcr_mfcc_forward_pcm16")
+        else:
+            L.check(self.lib, self.lib.tcr_mfcc_forward(self._h, self._ptr(wav), self._ptr(out), n, self._stream),
+                    "tcr_mfcc_forward")
         return out
 
     def forward(self, inputs: torch.Tensor, params: torch.Tensor, moving: Optional[torch.Tensor] = None,
                 is_training: bool = False, onehot: Optional[torch.Tensor] = None, weight_decay: float = 0.0,
                 dropout_seed: int = 0, dropout_mask: Optional[torch.Tensor] = None, input_is_features: bool = False):
         n = inputs.shape[0]
-        if not input_is_features:
-            inputs = inputs.reshape(n, -1)
+        in_ptr, in_kind = self._input(inputs, input_is_features)
         logits, probs = self._f32(n, self.num_classes), self._f32(n, self.num_classes)
         losses = self._f32(2) if onehot is not None else None
-        L.check(self.lib, self.lib.tcr_forward(self._h, self._ptr(inputs), int(input_is_features), self._ptr(params),
+        L.check(self.lib, self.lib.tcr_forward(self._h, in_ptr, in_kind, self._ptr(params),
                                                self._ptr(moving), n, int(is_training), int(dropout_seed),
                                                self._ptr(dropout_mask), self._ptr(onehot), float(weight_decay),
                                                self._ptr(logits), self._ptr(probs), self._ptr(losses), self._stream),
@@ -166,10 +179,9 @@ class Engine:
                    want_outputs: bool = False, want_grads: bool = False, apply_update: bool = True,
                    losses: Optional[torch.Tensor] = None):
         n = inputs.shape[0]
-        if not input_is_features:
-            inputs = inputs.reshape(n, -1)
         a = L.TcrStepArgs()
-        a.input, a.input_is_features, a.onehot, a.n = self._ptr(inputs), int(input_is_features), self._ptr(onehot), n
+        a.input, a.input_is_features = self._input(inputs, input_is_features)
+        a.onehot, a.n = self._ptr(onehot), n
         a.params, a.slots, a.moving = self._ptr(params), self._ptr(slots), self._ptr(moving)
         a.learning_rate, a.momentum, a.weight_decay = float(learning_rate), float(momentum), float(weight_decay)
         a.dropout_seed, a.dropout_mask = int(dropout_seed), self._ptr(dropout_mask)
@@ -233,11 +245,12 @@ class HostFeed:
     flush() returns the last outstanding losses.
     """
 
-    def __init__(self, engine: "Engine", batch: int, depth: int = 2):
+    def __init__(self, engine: "Engine", batch: int, depth: int = 2, pcm16: bool = False):
         self.eng, self.n, self.depth = engine, int(batch), int(depth)
         dev = engine.device
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.d_wav = [torch.empty(batch, engine.cfg.clip_samples, dtype=torch.float32, device=dev) for _ in range(depth)]
+        wav_dtype = torch.int16 if pcm16 else torch.float32     # int16: the wav files' own PCM, decoded on the device
+        self.d_wav = [torch.empty(batch, engine.cfg.clip_samples, dtype=wav_dtype, device=dev) for _ in range(depth)]
         self.d_hot = [torch.empty(batch, engine.num_classes, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.d_loss = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.h_loss = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(depth)]

@@ -34,7 +34,8 @@ class NumpyBackend:
         return np.full(shape, np.nan, np.float32)
 
     def upload(self, a):
-        return np.ascontiguousarray(a, dtype=np.float32).copy()
+        a = np.asarray(a)
+        return np.ascontiguousarray(a, dtype=np.int16 if a.dtype == np.int16 else np.float32).copy()
 
     def download(self, a):
         return np.array(a, copy=True)
@@ -66,7 +67,8 @@ class TorchBackend:
         return self.torch.full(shape, float("nan"), dtype=self.torch.float32, device=self.dev)
 
     def upload(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev)
+        a = np.asarray(a)
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.int16 if a.dtype == np.int16 else np.float32)).to(self.dev)
 
     def download(self, a):
         return a.detach().cpu().numpy()
@@ -127,7 +129,8 @@ class Engine:
         n = wav_np.shape[0]
         wav = b.upload(wav_np)
         feat = b.empty(n, self.info.frames, self.info.features)
-        L.check(self.lib, self.lib.tcr_mfcc_forward(self.h, b.ptr(wav), b.ptr(feat), n, b.stream), "tcr_mfcc_forward")
+        fn = self.lib.tcr_mfcc_forward_pcm16 if np.asarray(wav_np).dtype == np.int16 else self.lib.tcr_mfcc_forward
+        L.check(self.lib, fn(self.h, b.ptr(wav), b.ptr(feat), n, b.stream), "tcr_mfcc_forward")
         b.sync()
         return b.download(feat)
 
@@ -141,7 +144,8 @@ class Engine:
         onehot = b.upload(onehot_np) if onehot_np is not None else None
         nc = self.cfg.num_classes
         logits, probs, losses = b.empty(n, nc), b.empty(n, nc), b.empty(2)
-        L.check(self.lib, self.lib.tcr_forward(self.h, b.ptr(inp), int(is_features), b.ptr(params), b.ptr(moving), n,
+        kind = 1 if is_features else (2 if np.asarray(inp_np).dtype == np.int16 else 0)
+        L.check(self.lib, self.lib.tcr_forward(self.h, b.ptr(inp), kind, b.ptr(params), b.ptr(moving), n,
                                                int(is_training), seed, b.ptr(mask), b.ptr(onehot), weight_decay,
                                                b.ptr(logits), b.ptr(probs), b.ptr(losses) if onehot is not None else None,
                                                b.stream), "tcr_forward")
@@ -159,7 +163,8 @@ class Engine:
         logits, probs, losses = b.empty(n, nc), b.empty(n, nc), b.empty(2)
         grads = b.empty(self.info.num_trainable)
         a = L.TcrStepArgs()
-        a.input, a.input_is_features, a.onehot, a.n = b.ptr(inp), int(is_features), b.ptr(onehot), n
+        kind = 1 if is_features else (2 if np.asarray(inp_np).dtype == np.int16 else 0)
+        a.input, a.input_is_features, a.onehot, a.n = b.ptr(inp), kind, b.ptr(onehot), n
         a.params, a.slots, a.moving = b.ptr(params), b.ptr(slots), b.ptr(moving)
         a.learning_rate, a.momentum, a.weight_decay = lr, momentum, weight_decay
         a.dropout_seed, a.dropout_mask = seed, b.ptr(mask)

@@ -43,6 +43,27 @@ def test_log_mel_front_end(backend):
     eng.close()
 
 
+def test_pcm16_input_is_bit_identical_to_decoded_samples(backend):
+    """TCR_INPUT_WAV_PCM16: int16 samples scaled by 1/32768 in the framing stage == decode_wav then the fp32 path."""
+    eng = Engine(backend, max_batch=4)
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32768, size=(3, 16000), dtype=np.int16)
+    pcm[0, :700] = [-32768, 32767] * 350
+    got = eng.mfcc(pcm)
+    ref = eng.mfcc(pcm.astype(np.float32) / 32768.0)
+    assert np.array_equal(got, ref)
+    assert rel_err(got, O.mfcc(pcm.astype(np.float64) / 32768.0, 640, 320)) < 2e-5   # full-scale Nyquist square wave in clip 0
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    pv, mv = O.init_variables(spec, 3)
+    params, moving = O.flatten_vars(spec, pv).astype(np.float32), O.flatten_moving(spec, mv).astype(np.float32)
+    slots = np.zeros_like(params)
+    onehot = np.eye(12, dtype=np.float32)[[1, 5, 7]]
+    a = eng.train_step(pcm, onehot, params, slots, moving, seed=4)
+    b = eng.train_step(pcm.astype(np.float32) / 32768.0, onehot, params, slots, moving, seed=4)
+    assert np.array_equal(a["params"], b["params"]) and np.array_equal(a["losses"], b["losses"])
+    eng.close()
+
+
 def test_unsupported_width_is_an_error(backend):
     with pytest.raises(Exception, match="multiple of 4"):
         Engine(backend, width_multiplier=1.3)

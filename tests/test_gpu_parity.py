@@ -35,6 +35,25 @@ def test_persistent_step_kernel_matches_oracle(backend, monkeypatch):
     run_case(backend, model="TCResNet14", wm=1.5, window=640, stride=320, n=33, keep=1.0)
 
 
+def test_pcm16_input_matches_decoded_samples_bitwise(backend):
+    """TCR_INPUT_WAV_PCM16 == decode_wav (x / 32768) followed by the fp32 path, bit for bit, front-end and full step."""
+    eng = Engine(backend, max_batch=64)
+    rng = np.random.default_rng(11)
+    pcm = rng.integers(-32768, 32768, size=(64, 16000), dtype=np.int16)
+    dec = pcm.astype(np.float32) / 32768.0
+    got, ref = eng.mfcc(pcm), eng.mfcc(dec)
+    assert np.array_equal(got, ref)
+    assert rel_err(got, O.mfcc(pcm.astype(np.float64) / 32768.0, 640, 320)) < 1e-6
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    pv, mv = O.init_variables(spec, 3)
+    params, moving = O.flatten_vars(spec, pv).astype(np.float32), O.flatten_moving(spec, mv).astype(np.float32)
+    onehot = np.eye(12, dtype=np.float32)[rng.integers(0, 12, 64)]
+    a = eng.train_step(pcm, onehot, params, np.zeros_like(params), moving, seed=4)
+    b = eng.train_step(dec, onehot, params, np.zeros_like(params), moving, seed=4)
+    assert np.array_equal(a["params"], b["params"]) and np.array_equal(a["losses"], b["losses"])
+    eng.close()
+
+
 def test_full_size_config2_tcresnet8_n512(backend):
     report = run_case(backend, model="TCResNet8", wm=1.0, n=512, keep=0.5, max_batch=512, check_f32_floor=True)
     print(report)
