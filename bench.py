@@ -330,47 +330,52 @@ def run_ours(a):
         h_hots = [o.cpu().pin_memory() for o in onehots[:min(rot, 4)]]
         esteps = min(a.steps, 100)
 
-        def e2e_run(host_wavs, pcm16):
-            feed = HostFeed(eng, n, pcm16=pcm16)
+        def e2e_run(host_wavs):
+            feed = HostFeed(eng, lag=2)
+            seen = []
 
-            def e2e_step(i):                              # returns the (total, model) loss of step i-1
-                return feed.submit(host_wavs[i % len(host_wavs)], h_hots[i % len(h_hots)], params, slots, moving, lr, mom, wd,
-                                   dropout_seed=i)
+            def e2e_step(i):                              # returns (step, total, model) of the step submitted 2 calls earlier
+                r = feed.submit(host_wavs[i % len(host_wavs)], h_hots[i % len(h_hots)], params, slots, moving, lr, mom, wd,
+                                dropout_seed=i)
+                if r is not None:
+                    seen.append(r)
 
             for i in range(3):
                 e2e_step(i)
             feed.flush()
             barrier()
+            del seen[:]
             t0 = time.perf_counter()
             for i in range(esteps):
                 e2e_step(i)
-            last = feed.flush()                           # the last step's loss is on the host before the clock stops
+            seen.extend(feed.flush())                     # every step's loss is on the host before the clock stops
             barrier()
             el = torch.tensor([time.perf_counter() - t0], device=dev)
             if world > 1:
                 torch.distributed.all_reduce(el, op=torch.distributed.ReduceOp.MAX)
-            return n * world * esteps / float(el.item()), last, feed
+            assert len(seen) == esteps, (len(seen), esteps)
+            return n * world * esteps / float(el.item()), seen[-1]
 
-        e2e_value, last, feed = e2e_run(h_wavs, False)
+        e2e_value, last = e2e_run(h_wavs)
         # the same clips as the wav files store them (int16 PCM); decode_wav's 1/32768 scaling runs on the device
         h_pcm = [(w.clamp(-1, 1) * 32767.0).round().to(torch.int16).cpu().pin_memory() for w in wavs[:min(rot, 4)]]
-        pcm_value, _, _ = e2e_run(h_pcm, True)
+        pcm_value, _ = e2e_run(h_pcm)
         h2d = int(h_wavs[0].numel() * 4 + h_hots[0].numel() * 4)
         # serial H2D bandwidth of the same buffers, for context
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for i in range(10):
-            feed.d_wav[0].copy_(h_wavs[i % len(h_wavs)], non_blocking=True)
+            wavs[0].copy_(h_wavs[i % len(h_wavs)], non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
         out["e2e"] = {"value": e2e_value, "unit": "utterances/sec",
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "steps": esteps,
                       "h2d_GBps_measured": 10 * h_wavs[0].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9,
-                      "last_total_loss": last[0] if last else None,
+                      "last_total_loss": last[1] if last else None,
                       "pcm16": {"value": pcm_value, "unit": "utterances/sec", "h2d_bytes_per_step": int(h_pcm[0].numel() * 2 + h_hots[0].numel() * 4),
                                 "note": "same pipeline fed int16 PCM (TCR_INPUT_WAV_PCM16): for un-augmented evaluation/inference batches"},
-                      "api": "tcresnet_b200.engine.HostFeed.submit (double-buffered Engine.train_step): pinned host fp32 wav + "
-                             "one-hot -> H2D on a copy stream every step, loss of every step read back to the host"}
+                      "api": "C ABI tcr_train_step_host (tcresnet_b200.engine.HostFeed.submit, lag 2): pinned host fp32 wav + one-hot -> H2D on "
+                             "the library's copy stream every step, the step, both losses of every step read back to the host"}
 
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:

@@ -168,6 +168,18 @@ int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, co
  * averaged over ranks with one ncclAllReduce before the update. */
 int tcr_train_step(tcr_handle* h, const tcr_step_args* args, tcr_stream stream);
 
+/* The same step fed from PINNED HOST memory (the feed_dict / tf.data side of session.run(train_op): helper/trainer.py:312-321,
+ * datasets/data_wrapper_base.py:100-108).  `a->input` and `a->onehot` are host pointers (cudaHostAlloc / pin_memory);
+ * `a->losses` is ignored.  The batch is copied H2D on a private copy stream into one of 3 staging slots, the step runs on
+ * `stream` behind it and its two losses are copied back; the call does not wait for the step it submits.  It returns,
+ * in losses_out[0..1] and *losses_step, the losses of the step submitted `lag` calls earlier (*losses_step = -1 while
+ * fewer than lag+1 steps are outstanding).  lag in [0,2]: 0 = synchronous, 1 = copy/compute overlap, 2 = also keeps
+ * kernel launches ahead of the GPU.  The host buffers of a call may be reused once the call `lag`+1 later has
+ * returned (or after tcr_host_flush).  tcr_host_flush returns the oldest outstanding losses, *losses_step = -1 when none. */
+int tcr_train_step_host(tcr_handle* h, const tcr_step_args* a, int32_t lag, tcr_stream stream, float* losses_out,
+                        int64_t* losses_step);
+int tcr_host_flush(tcr_handle* h, float* losses_out, int64_t* losses_step);
+
 /* Debug / parity inspection: device pointer of a named workspace tensor after the last call, e.g.
  * "features", "y:conv0", "y:block0/conv0_0", "out:block1", "g:block0/down", "grads".
  * Returns TCR_ERR_INVALID for unknown names. */

@@ -86,6 +86,9 @@ SYMBOLS = {
                               C.c_uint64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
     "tcr_train_step": (C.c_int, [C.c_void_p, C.POINTER(TcrStepArgs), C.c_void_p]),
+    "tcr_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(TcrStepArgs), C.c_int32, C.c_void_p, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_int64)]),
+    "tcr_host_flush": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "tcr_workspace_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tcr_comm_unique_id": (C.c_int, [C.c_void_p]),
     "tcr_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

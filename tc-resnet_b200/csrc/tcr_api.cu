@@ -350,8 +350,11 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
   return TCR_OK;
 }
 
+static void hostfeed_destroy(tcr_handle* h);
+
 extern "C" int tcr_destroy(tcr_handle* h) {
   if (!h) return TCR_OK;
+  hostfeed_destroy(h);
   comm_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_hyper) cudaFreeHost(h->h_hyper);
@@ -479,6 +482,115 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
   TCR_CUDA(cudaGetLastError());
   h->last_n = a->n;
   return TCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer training step: the `feed_dict` / input-pipeline side of session.run(train_op)
+// (helper/trainer.py:312-321, datasets/data_wrapper_base.py:100-108 prefetch).  Pinned host batch -> H2D on a private
+// copy stream into one of kFeedDepth staging slots -> the step on the caller's stream -> D2H of the two losses.
+// Submission never waits for the step it submits: the losses handed back are those of the step `lag` calls earlier,
+// so the copy of batch i+1 overlaps the compute of batch i and kernel launches run ahead of the GPU.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kFeedDepth = 3;
+struct HostSlot {
+  void* d_in = nullptr; float* d_hot = nullptr; float* d_loss = nullptr; float* h_loss = nullptr;
+  cudaEvent_t ready = nullptr, consumed = nullptr, done = nullptr;
+};
+struct HostFeedState {
+  HostSlot slot[kFeedDepth];
+  cudaStream_t copy = nullptr;
+  int64_t submitted = 0, collected = 0;
+};
+}  // namespace
+
+static void hostfeed_destroy(tcr_handle* h) {
+  HostFeedState* f = (HostFeedState*)h->hostfeed;
+  if (!f) return;
+  for (auto& s : f->slot) {
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_hot) cudaFree(s.d_hot);
+    if (s.d_loss) cudaFree(s.d_loss);
+    if (s.h_loss) cudaFreeHost(s.h_loss);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (f->copy) cudaStreamDestroy(f->copy);
+  delete f;
+  h->hostfeed = nullptr;
+}
+
+static int hostfeed_get(tcr_handle* h, HostFeedState** out) {
+  if (!h->hostfeed) {
+    HostFeedState* f = new HostFeedState();
+    h->hostfeed = f;
+    TCR_CUDA(cudaStreamCreateWithFlags(&f->copy, cudaStreamNonBlocking));
+    const size_t in_bytes = (size_t)h->cfg.max_batch * std::max((size_t)h->cfg.clip_samples, (size_t)h->frames * h->features) * 4;
+    for (auto& s : f->slot) {
+      TCR_CUDA(cudaMalloc(&s.d_in, in_bytes));
+      TCR_CUDA(cudaMalloc((void**)&s.d_hot, (size_t)h->cfg.max_batch * h->cfg.num_classes * 4));
+      TCR_CUDA(cudaMalloc((void**)&s.d_loss, 2 * sizeof(float)));
+      TCR_CUDA(cudaMallocHost((void**)&s.h_loss, 2 * sizeof(float)));
+      TCR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+      TCR_CUDA(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+      TCR_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+  }
+  *out = (HostFeedState*)h->hostfeed;
+  return TCR_OK;
+}
+
+static int hostfeed_collect(HostFeedState* f, float* losses_out, int64_t* losses_step) {
+  HostSlot& s = f->slot[f->collected % kFeedDepth];
+  TCR_CUDA(cudaEventSynchronize(s.done));
+  if (losses_out) { losses_out[0] = s.h_loss[0]; losses_out[1] = s.h_loss[1]; }
+  if (losses_step) *losses_step = f->collected;
+  ++f->collected;
+  return TCR_OK;
+}
+
+extern "C" int tcr_train_step_host(tcr_handle* h, const tcr_step_args* a, int32_t lag, tcr_stream stream, float* losses_out,
+                                   int64_t* losses_step) {
+  if (!h || !a || !a->input || !a->onehot || !a->params) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (lag < 0 || lag >= kFeedDepth) return fail(TCR_ERR_INVALID, "lag must be in [0, %d]", kFeedDepth - 1);
+  TCR_TRY(check_n(h, a->n));
+  HostFeedState* f = nullptr;
+  TCR_TRY(hostfeed_get(h, &f));
+  if (losses_step) *losses_step = -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  HostSlot& sl = f->slot[f->submitted % kFeedDepth];
+  size_t in_bytes;
+  switch (a->input_is_features) {
+    case TCR_INPUT_WAV_F32: in_bytes = (size_t)a->n * h->cfg.clip_samples * 4; break;
+    case TCR_INPUT_WAV_PCM16: in_bytes = (size_t)a->n * h->cfg.clip_samples * 2; break;
+    case TCR_INPUT_FEATURES: in_bytes = (size_t)a->n * h->frames * h->features * 4; break;
+    default: return fail(TCR_ERR_INVALID, "unknown input kind %d", a->input_is_features);
+  }
+  if (f->submitted >= kFeedDepth) TCR_CUDA(cudaStreamWaitEvent(f->copy, sl.consumed, 0));   // the slot's previous step has read it
+  TCR_CUDA(cudaMemcpyAsync(sl.d_in, a->input, in_bytes, cudaMemcpyHostToDevice, f->copy));
+  TCR_CUDA(cudaMemcpyAsync(sl.d_hot, a->onehot, (size_t)a->n * h->cfg.num_classes * 4, cudaMemcpyHostToDevice, f->copy));
+  TCR_CUDA(cudaEventRecord(sl.ready, f->copy));
+  TCR_CUDA(cudaStreamWaitEvent(s, sl.ready, 0));
+  tcr_step_args d = *a;
+  d.input = (const float*)sl.d_in;
+  d.onehot = sl.d_hot;
+  d.losses = sl.d_loss;
+  TCR_TRY(tcr_train_step(h, &d, stream));
+  TCR_CUDA(cudaEventRecord(sl.consumed, s));
+  TCR_CUDA(cudaMemcpyAsync(sl.h_loss, sl.d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  TCR_CUDA(cudaEventRecord(sl.done, s));
+  ++f->submitted;
+  if (f->submitted - f->collected > lag) TCR_TRY(hostfeed_collect(f, losses_out, losses_step));
+  return TCR_OK;
+}
+
+extern "C" int tcr_host_flush(tcr_handle* h, float* losses_out, int64_t* losses_step) {
+  if (!h) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (losses_step) *losses_step = -1;
+  HostFeedState* f = (HostFeedState*)h->hostfeed;
+  if (!f || f->collected >= f->submitted) return TCR_OK;
+  return hostfeed_collect(f, losses_out, losses_step);
 }
 
 extern "C" int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr, int64_t* numel) {

@@ -70,6 +70,7 @@ struct tcr_handle {
   // data-parallel
   void* comm = nullptr; int rank = 0, world = 1;
   int last_n = 0;
+  void* hostfeed = nullptr;   // HostFeedState (tcr_api.cu): staging slots of tcr_train_step_host
   tcr::StepProgram* rec = nullptr;   // non-null while a training step is being recorded for the persistent kernel
   size_t rec_smem = 0; int persist = -1; int persist_grid = 0; unsigned* d_gridbar = nullptr;
   long long* d_timeline = nullptr;   // TCR_DEBUG_TIMELINE=1: per-CTA phase stamps (fwd kernels: 8 slots per CTA; dw: after)

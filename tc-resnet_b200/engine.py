@@ -236,57 +236,46 @@ class Engine:
 
 
 class HostFeed:
-    """Double-buffered host -> device feed around Engine.train_step (the `session.run(train_op)` loop of
+    """Host-buffer feed around the C ABI's tcr_train_step_host (the `session.run(train_op)` loop of
     helper/trainer.py:132-154 with the input pipeline's prefetch, datasets/data_wrapper_base.py:100-108).
 
-    submit(i) enqueues, without blocking on the GPU: the H2D copy of batch i on a copy stream (pinned host memory),
-    step i on the compute stream behind it, and the D2H read of step i's losses; it then returns the losses of step
-    i-1.  The copy of batch i+1 therefore overlaps the compute of step i; every step's input still crosses the bus.
-    flush() returns the last outstanding losses.
+    submit() hands one pinned host batch (fp32 wav, int16 PCM, or features) to the library, which copies it H2D on its
+    own copy stream into a staging slot, runs the step behind the copy and reads the two losses back.  The call does
+    not wait for the step it submits: it returns (step_index, total_loss, model_loss) of the step `lag` submissions
+    earlier (None while the pipeline fills), so copies, launches and compute of neighbouring steps overlap while every
+    step's input still crosses the bus and every step's loss reaches the host.  flush() drains what is outstanding.
     """
 
-    def __init__(self, engine: "Engine", batch: int, depth: int = 2, pcm16: bool = False):
-        self.eng, self.n, self.depth = engine, int(batch), int(depth)
-        dev = engine.device
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        wav_dtype = torch.int16 if pcm16 else torch.float32     # int16: the wav files' own PCM, decoded on the device
-        self.d_wav = [torch.empty(batch, engine.cfg.clip_samples, dtype=wav_dtype, device=dev) for _ in range(depth)]
-        self.d_hot = [torch.empty(batch, engine.num_classes, dtype=torch.float32, device=dev) for _ in range(depth)]
-        self.d_loss = [torch.zeros(2, dtype=torch.float32, device=dev) for _ in range(depth)]
-        self.h_loss = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.ready = [torch.cuda.Event() for _ in range(depth)]
-        self.free = [torch.cuda.Event() for _ in range(depth)]
-        self.done = [torch.cuda.Event() for _ in range(depth)]
-        self.i = 0
-        self.pending = None
+    def __init__(self, engine: "Engine", lag: int = 2):
+        self.eng, self.lag = engine, int(lag)
+        self._out = (C.c_float * 2)()
+        self._step = C.c_int64(-1)
 
-    def submit(self, h_wav: torch.Tensor, h_onehot: torch.Tensor, params, slots, moving, learning_rate, momentum=0.9,
-               weight_decay=1e-4, dropout_seed=0):
-        assert h_wav.is_pinned() and h_onehot.is_pinned(), "HostFeed needs pinned host tensors"
-        b = self.i % self.depth
-        compute = torch.cuda.current_stream(self.eng.device)
-        with torch.cuda.stream(self.copy_stream):
-            if self.i >= self.depth:
-                self.copy_stream.wait_event(self.free[b])          # step i-depth has consumed this buffer
-            self.d_wav[b].copy_(h_wav.reshape(self.n, -1), non_blocking=True)
-            self.d_hot[b].copy_(h_onehot, non_blocking=True)
-            self.ready[b].record(self.copy_stream)
-        compute.wait_event(self.ready[b])
-        self.eng.train_step(self.d_wav[b], self.d_hot[b], params, slots, moving, learning_rate, momentum, weight_decay,
-                            dropout_seed=dropout_seed, losses=self.d_loss[b])
-        self.free[b].record(compute)
-        self.h_loss[b].copy_(self.d_loss[b], non_blocking=True)
-        self.done[b].record(compute)
-        prev, self.pending = self.pending, b
-        self.i += 1
-        return self._collect(prev)
+    def _result(self):
+        return None if self._step.value < 0 else (int(self._step.value), float(self._out[0]), float(self._out[1]))
 
-    def _collect(self, b):
-        if b is None:
-            return None
-        self.done[b].synchronize()
-        return float(self.h_loss[b][0]), float(self.h_loss[b][1])
+    def submit(self, h_inputs: torch.Tensor, h_onehot: torch.Tensor, params, slots, moving, learning_rate, momentum=0.9,
+               weight_decay=1e-4, dropout_seed=0, input_is_features=False):
+        eng = self.eng
+        assert h_inputs.is_pinned() and h_onehot.is_pinned() and h_inputs.is_contiguous(), "HostFeed needs pinned host tensors"
+        a = L.TcrStepArgs()
+        a.input = h_inputs.data_ptr()
+        a.input_is_features = (L.TCR_INPUT_FEATURES if input_is_features else
+                               L.TCR_INPUT_WAV_PCM16 if h_inputs.dtype == torch.int16 else L.TCR_INPUT_WAV_F32)
+        a.onehot, a.n = h_onehot.data_ptr(), h_inputs.shape[0]
+        a.params, a.slots, a.moving = eng._ptr(params), eng._ptr(slots), eng._ptr(moving)
+        a.learning_rate, a.momentum, a.weight_decay = float(learning_rate), float(momentum), float(weight_decay)
+        a.dropout_seed, a.apply_update = int(dropout_seed), 1
+        L.check(eng.lib, eng.lib.tcr_train_step_host(eng._h, C.byref(a), self.lag, eng._stream, self._out, C.byref(self._step)),
+                "tcr_train_step_host")
+        return self._result()
 
     def flush(self):
-        prev, self.pending = self.pending, None
-        return self._collect(prev)
+        """Drain the pipeline: list of (step_index, total_loss, model_loss) for every outstanding step."""
+        out = []
+        while True:
+            L.check(self.eng.lib, self.eng.lib.tcr_host_flush(self.eng._h, self._out, C.byref(self._step)), "tcr_host_flush")
+            r = self._result()
+            if r is None:
+                return out
+            out.append(r)

@@ -64,6 +64,41 @@ def test_pcm16_input_is_bit_identical_to_decoded_samples(backend):
     eng.close()
 
 
+def test_host_buffer_step_and_its_loss_pipeline(backend):
+    """tcr_train_step_host: same update as the device-buffer step; losses come back `lag` submissions late, in order."""
+    import ctypes as C
+    from tcresnet_b200 import _lib as L
+    eng = Engine(backend, max_batch=4)
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    pv, mv = O.init_variables(spec, 3)
+    params0, moving0 = O.flatten_vars(spec, pv).astype(np.float32), O.flatten_moving(spec, mv).astype(np.float32)
+    wav, onehot = O.synthetic_batch(3, seed_wav=9)
+    ref = eng.train_step(wav, onehot, params0, np.zeros_like(params0), moving0, seed=4)
+
+    def host_step(params, slots, moving, lag, seed):
+        a = L.TcrStepArgs()
+        a.input, a.input_is_features, a.onehot, a.n = wav.ctypes.data, 0, onehot.ctypes.data, 3
+        a.params, a.slots, a.moving = params.ctypes.data, slots.ctypes.data, moving.ctypes.data
+        a.learning_rate, a.momentum, a.weight_decay, a.dropout_seed, a.apply_update = 0.1, 0.9, 1e-3, seed, 1
+        out, step = (C.c_float * 2)(), C.c_int64(-7)
+        L.check(eng.lib, eng.lib.tcr_train_step_host(eng.h, C.byref(a), lag, None, out, C.byref(step)), "tcr_train_step_host")
+        return step.value, (out[0], out[1])
+
+    p, sl, mvv = params0.copy(), np.zeros_like(params0), moving0.copy()
+    step, losses = host_step(p, sl, mvv, 0, 4)
+    assert step == 0 and np.array_equal(p, ref["params"]) and np.allclose(losses, ref["losses"], rtol=0, atol=0)
+    got = [host_step(p, sl, mvv, 2, 5 + i)[0] for i in range(4)]
+    assert got == [-1, -1, 1, 2]                     # step 0 was collected above; lag 2 keeps two in flight
+    out, stepv, rest = (C.c_float * 2)(), C.c_int64(0), []
+    while True:
+        L.check(eng.lib, eng.lib.tcr_host_flush(eng.h, out, C.byref(stepv)), "tcr_host_flush")
+        if stepv.value < 0:
+            break
+        rest.append(stepv.value)
+    assert rest == [3, 4]
+    eng.close()
+
+
 def test_unsupported_width_is_an_error(backend):
     with pytest.raises(Exception, match="multiple of 4"):
         Engine(backend, width_multiplier=1.3)

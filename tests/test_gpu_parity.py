@@ -54,6 +54,39 @@ def test_pcm16_input_matches_decoded_samples_bitwise(backend):
     eng.close()
 
 
+def test_host_feed_pipeline_matches_device_steps(backend):
+    """tcr_train_step_host through tcresnet_b200.engine.HostFeed: 6 pipelined steps from pinned host buffers (fp32 and int16)
+    leave exactly the parameters that 6 device-buffer steps leave, and every step's loss comes back once, in order."""
+    import torch
+    from tcresnet_b200.engine import Engine as PublicEngine, HostFeed
+    eng = PublicEngine(max_batch=32)
+    gen = torch.Generator().manual_seed(3)
+    pcm = [torch.randint(-30000, 30000, (32, 16000), generator=gen, dtype=torch.int16).pin_memory() for _ in range(3)]
+    dec = [(p.float() / 32768.0).pin_memory() for p in pcm]
+    hot = [torch.nn.functional.one_hot(torch.randint(0, 12, (32,), generator=gen), 12).float().pin_memory() for _ in range(3)]
+    results = {}
+    for kind, bufs in (("device", dec), ("host_f32", dec), ("host_pcm16", pcm)):
+        params, slots, moving = eng.new_variables(seed=1)
+        losses = []
+        if kind == "device":
+            for i in range(6):
+                out = eng.train_step(bufs[i % 3].cuda(), hot[i % 3].cuda(), params, slots, moving, 0.05, 0.9, 1e-3, dropout_seed=i)
+                losses.append(tuple(out["losses"].tolist()))
+        else:
+            feed = HostFeed(eng, lag=2)
+            got = [feed.submit(bufs[i % 3], hot[i % 3], params, slots, moving, 0.05, 0.9, 1e-3, dropout_seed=i) for i in range(6)]
+            assert got[0] is None and got[1] is None and [g[0] for g in got[2:]] == [0, 1, 2, 3]
+            rest = feed.flush()
+            assert [r[0] for r in rest] == [4, 5]
+            losses = [(g[1], g[2]) for g in got[2:] + rest]
+        torch.cuda.synchronize()
+        results[kind] = (params.cpu().numpy(), np.array(losses, np.float32))
+    for kind in ("host_f32", "host_pcm16"):
+        assert np.array_equal(results[kind][0], results["device"][0]), kind
+        assert np.array_equal(results[kind][1], results["device"][1]), kind
+    eng.close()
+
+
 def test_full_size_config2_tcresnet8_n512(backend):
     report = run_case(backend, model="TCResNet8", wm=1.0, n=512, keep=0.5, max_batch=512, check_f32_floor=True)
     print(report)
