@@ -328,7 +328,7 @@ def run_ours(a):
         from tcresnet_b200.engine import HostFeed
         h_wavs = [w.cpu().pin_memory() for w in wavs[:min(rot, 4)]]
         h_hots = [o.cpu().pin_memory() for o in onehots[:min(rot, 4)]]
-        esteps = min(a.steps, 100)
+        esteps = min(a.steps, 200)
 
         def e2e_run(host_wavs):
             feed = HostFeed(eng, lag=2)
