@@ -432,9 +432,11 @@ static int mfcc_run(tcr_handle* h, const void* wav, int pcm16, float* features, 
   return TCR_OK;
 }
 extern "C" int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n, tcr_stream stream) {
+  pdl_chain_reset();
   return mfcc_run(h, wav, 0, features, n, stream);
 }
 extern "C" int tcr_mfcc_forward_pcm16(tcr_handle* h, const int16_t* pcm, float* features, int32_t n, tcr_stream stream) {
+  pdl_chain_reset();
   return mfcc_run(h, pcm, 1, features, n, stream);
 }
 
@@ -442,6 +444,7 @@ extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_f
                            const float* moving, int32_t n, int32_t is_training, uint64_t dropout_seed,
                            const float* dropout_mask, const float* onehot, float weight_decay, float* logits,
                            float* probs, float* losses, tcr_stream stream) {
+  pdl_chain_reset();
   if (!h || !input || !params) return fail(TCR_ERR_INVALID, "NULL argument");
   if (!is_training && !moving) return fail(TCR_ERR_INVALID, "eval-mode forward needs the moving statistics");
   TCR_TRY(check_n(h, n));
@@ -461,6 +464,7 @@ extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_f
 }
 
 extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream stream) {
+  pdl_chain_reset();
   if (!h || !a || !a->input || !a->onehot || !a->params) return fail(TCR_ERR_INVALID, "NULL argument");
   if (a->apply_update && (!a->slots || !a->moving)) return fail(TCR_ERR_INVALID, "apply_update needs slots and moving");
   TCR_TRY(check_n(h, a->n));
@@ -472,6 +476,7 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
     feat = h->d_feat;
   }
   if (persist_enabled(h)) rec_begin(h);      // record the step's phases; net_update launches the persistent kernel
+  net_weight_transpose(h, a->params, s);
   int rc = net_forward(h, feat, a->params, nullptr, a->n, true, a->dropout_seed, a->dropout_mask, a->onehot,
                        a->weight_decay, a->logits, a->probs, nullptr, /*backward=*/true, s);
   if (rc) { rec_abort(h); return fail(rc, "forward launch failed: %s", g_err); }
@@ -645,6 +650,7 @@ extern "C" int tcr_comm_destroy(tcr_handle* h) {
 }
 
 extern "C" int tcr_measure_fp32_peak(tcr_handle* h, double* tflops, tcr_stream stream) {
+  pdl_chain_reset();
   if (!h || !tflops) return fail(TCR_ERR_INVALID, "NULL argument");
   int rc = measure_fp32_peak(h, tflops, (cudaStream_t)stream);
   return rc ? fail(rc, "fp32 peak measurement failed") : TCR_OK;

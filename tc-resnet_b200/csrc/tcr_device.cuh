@@ -12,11 +12,30 @@ namespace tcr {
 void prof_begin(const char* name, cudaStream_t s);   // tcr_prof.cu: launch counter + optional CUDA-event bracket
 void prof_end(cudaStream_t s);
 }
-#define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...)                 \
-  do {                                                                           \
-    tcr::prof_begin((name), (cudaStream_t)(stream));                             \
-    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);    \
-    tcr::prof_end((cudaStream_t)(stream));                                       \
+namespace tcr {
+bool pdl_enabled();                                   // tcr_prof.cu: env TCR_PDL (default on), false for the first launch of a call
+void pdl_chain_reset();                               // called at every API entry point
+// Every kernel of the library is launched with programmatic stream serialization: its CTAs may become resident and
+// run their producer-independent prologue (mbarrier init, filter-bank TMA, smem padding) while the previous kernel
+// drains; pdl_wait() (griddepcontrol.wait) is the point after which the previous kernel's results may be read.
+// Every kernel calls pdl_wait() exactly once on every path, so completion is transitive along the stream.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace tcr
+#define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...)                                          \
+  do {                                                                                                    \
+    tcr::prof_begin((name), (cudaStream_t)(stream));                                                      \
+    tcr::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__); \
+    tcr::prof_end((cudaStream_t)(stream));                                                                \
   } while (0)
 #define TCR_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 // cooperative launch (all CTAs co-resident): kernel arguments are packed into an array of pointers
@@ -30,6 +49,18 @@ void prof_end(cudaStream_t s);
 #endif
 
 namespace tcr {
+
+// programmatic dependent launch (see launch_pdl): no-ops in a kernel that was launched without the attribute
+__device__ __forceinline__ void pdl_wait() {
+#ifndef TCR_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef TCR_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

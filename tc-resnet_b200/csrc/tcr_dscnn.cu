@@ -43,6 +43,7 @@ __device__ __forceinline__ void fold_bn(const float* p, int64_t b, int64_t beta,
 // ---- first layer: cin == 1 ----
 __global__ void __launch_bounds__(256) dscnn_conv_kernel(DsLayerDev L, const float* __restrict__ params, const float* __restrict__ in,
                                                          float* __restrict__ out, float eps) {
+  pdl_wait();
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int hp = (L.hout - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw;      // padded input extent
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) dscnn_conv_kernel(DsLayerDev L, const flo
 constexpr int kDsTM = 4;
 __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH, const float* __restrict__ params,
                                                             const float* __restrict__ in, float* __restrict__ out, float eps) {
+  pdl_wait();
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int C = L.cin, CO = L.cout;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH
 __global__ void __launch_bounds__(256) dscnn_head_kernel(int npos, int C, int classes, int64_t fcw, int64_t fcb,
                                                          const float* __restrict__ params, const float* __restrict__ in,
                                                          float* __restrict__ logits, float* __restrict__ probs) {
+  pdl_wait();
   __shared__ float s_red[256];
   __shared__ float s_pool[320];
   __shared__ float s_logit[kMaxClasses];
@@ -343,6 +346,7 @@ extern "C" int tcr_dscnn_param_table(const tcr_dscnn* d, const tcr_param_desc** 
 
 extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const float* params, int32_t n, float* logits, float* probs,
                                  tcr_stream stream) {
+  pdl_chain_reset();
   if (!d || !features || !params) { set_error("NULL argument"); return TCR_ERR_INVALID; }
   if (n <= 0 || n > d->cfg.max_batch) { set_error("n outside [1, max_batch]"); return TCR_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;

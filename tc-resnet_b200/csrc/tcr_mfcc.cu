@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
 
   const int span = (nf - 1) * a.stride + a.window;   // samples actually needed (span * SB is a multiple of 16)
   if (threadIdx.x == 0) mbar_init(bar, 1);
+  pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)span * SB);

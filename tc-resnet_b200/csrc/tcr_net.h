@@ -16,6 +16,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
                 float* probs, float* losses, bool backward, cudaStream_t s);
 
 // Backward-data chain + all weight-gradient kernels; leaves per-layer partial sums in the workspace.
+int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s);
 
 // Gradient finalisation (+ weight decay), optional NCCL all-reduce, momentum update, BN moving averages, losses.

@@ -76,6 +76,7 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
       const int row = pr < PLd ? pr : a.t_out + pr;
       st4(dys + ((size_t)(u * TPd + row) * COS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    pdl_wait();                     // the transposed filter bank (TMA above) was written at the start of the step
     {
       const RowWalk w = row_walk(tid, kThreads, c4n);
       const int rows = Ue * a.t_out;
@@ -271,6 +272,7 @@ template <int K, bool WSMEM>
 __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
+  pdl_trigger();
   conv_bwd_data_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
 }
 
@@ -289,6 +291,7 @@ __device__ __forceinline__ void weight_transpose_body(const WtArgs& a, const int
   L.wT[i] = a.params[L.w_off + ((int64_t)k * L.cin + ci) * L.cout + co];
 }
 __global__ void __launch_bounds__(256) weight_transpose_kernel(WtArgs a) {
+  pdl_wait();
   weight_transpose_body(a, (int64_t)blockIdx.x * 256 + threadIdx.x);
 }
 
@@ -425,6 +428,7 @@ __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ laye
 __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
                                                                 const float* __restrict__ feat, long long* tl) {
   TCR_DYNAMIC_SMEM(smem_raw);
+  pdl_wait();
   dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw);
 }
 
@@ -599,21 +603,25 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   }
 }
 
+// Transposed filter banks for the backward-data kernels: launched at the START of the step (it only reads params), so the
+// first backward kernel can prefetch its bank before its programmatic-dependency wait.
+int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s) {
+  WtArgs w;
+  w.nlayers = 0;
+  w.total = 0;
+  w.params = params;
+  for (auto& cv : h->convs) {
+    if (&cv == &h->convs[0]) continue;               // conv0 needs no input gradient
+    w.layer[w.nlayers++] = WtLayer{cv.w_off, cv.wT, cv.k, cv.cin, cv.cout, w.total};
+    w.total += cv.wnumel();
+  }
+  if (h->rec) rec_transpose(h, w);
+  else TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
+  return 0;
+}
+
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s) {
   int slot = 32;
-  {
-    WtArgs w;
-    w.nlayers = 0;
-    w.total = 0;
-    w.params = params;
-    for (auto& cv : h->convs) {
-      if (&cv == &h->convs[0]) continue;               // conv0 needs no input gradient
-      w.layer[w.nlayers++] = WtLayer{cv.w_off, cv.wT, cv.k, cv.cin, cv.cout, w.total};
-      w.total += cv.wnumel();
-    }
-    if (h->rec) rec_transpose(h, w);
-    else TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
-  }
   for (int i = (int)h->blocks.size() - 1; i >= 0; --i) {
     BlockPlan& b = h->blocks[i];
     ConvPlan& ca = h->convs[b.a];

@@ -68,6 +68,7 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
     const int row = pr < a.pad_left ? pr : a.t_in + pr;
     st4(xs + ((size_t)(u * TP + row) * CS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
   }
+  pdl_wait();                       // everything above is independent of the producer kernel (filters: caller-owned params)
   {
     // c4 fixed per thread (per-channel constants in registers), rows advance incrementally: no div/mod per element
     const RowWalk w = row_walk(tid, kThreads, c4n);
@@ -217,6 +218,7 @@ template <int K, bool WSMEM>
 __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
+  pdl_trigger();                    // grid <= resident CTA slots: the next kernel's CTAs may take slots as ours retire
   conv_fwd_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
 }
 
@@ -231,6 +233,7 @@ struct EvalBnArgs {
   float* bnf[kMaxConvs];
 };
 __global__ void bn_table_eval_kernel(EvalBnArgs a) {
+  pdl_wait();
   const int l = blockIdx.x;
   const int C = a.c[l];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -444,6 +447,8 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
+  pdl_trigger();
+  pdl_wait();
   head_body(a, blockIdx.x, gridDim.x, smem_raw, true);
 }
 

@@ -69,6 +69,7 @@ __device__ __forceinline__ void grad_finalize_body(const GradArgs& a, const int 
   }
 }
 __global__ void __launch_bounds__(kOptThreads) grad_finalize_kernel(GradArgs a) {
+  pdl_wait();
   __shared__ float s_red[kOptThreads / 32];
   grad_finalize_body(a, (int)blockIdx.x, s_red);
 }
@@ -87,6 +88,7 @@ struct UpdateArgs {
 };
 
 __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
+  pdl_wait();
   const int64_t p = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
   if (p < a.total) {
     const float g = a.grads[p] * a.grad_scale;
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
 // Loss scalars for a forward-only call: sum of w^2 over the decayed variables in one CTA.
 __global__ void __launch_bounds__(1024) loss_only_kernel(const OptSegment* __restrict__ segs, int nsegs, const float* __restrict__ params,
                                                          float weight_decay, const float* ce_sum, float inv_n, float* losses) {
+  pdl_wait();
   __shared__ float s_red[32];
   float w2 = 0.f;
   for (int si = 0; si < nsegs; ++si) {
@@ -222,6 +225,7 @@ int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int
 // fp32 FMA peak (compute-roofline denominator): 8 independent FMA chains per thread, all SMs busy.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float seed) {
+  pdl_wait();
   float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f, a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f, a7 = seed + 7.f;
   const float b = 1.0000001f, c = 1e-7f;
   for (int i = 0; i < iters; ++i) {

@@ -2,6 +2,7 @@
 // bench.py uses it for `gpu_launches` and for the per-kernel durations of the roofline block; tests use the
 // counter to prove that the CUDA path (not a fallback) ran.  Disabled profiling costs one branch per launch.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -36,6 +37,20 @@ struct Profiler {
 }  // namespace
 
 #ifndef TCR_EMU
+// PDL only links the library's own kernels WITHIN one API call: the first launch of a call is an ordinary launch (fully
+// ordered behind whatever the caller put on the stream), later ones carry the programmatic-serialization attribute.
+static thread_local bool t_chain = false;
+void pdl_chain_reset() { t_chain = false; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCR_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool use = v != 0 && t_chain;
+  t_chain = true;
+  return use;
+}
 void prof_begin(const char* name, cudaStream_t s) {
   ++g_prof.launches;
   if (!g_prof.enabled) return;
@@ -60,6 +75,7 @@ static void drain() {
   g_prof.pool_next = 0;
 }
 #else
+void pdl_chain_reset() {}
 static void drain() {}
 #endif
 

@@ -160,6 +160,7 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 
+namespace tcr { void pdl_chain_reset(); }
 #define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().cur->smem
