@@ -64,6 +64,11 @@ __device__ __forceinline__ Chan4 chan4_load(const float* __restrict__ bnf, int C
   k.mean = ldc4(bnf + c); k.rstd = ldc4(bnf + C + c); k.scale = ldc4(bnf + 2 * C + c); k.beta = ldc4(bnf + 3 * C + c);
   return k;
 }
+__device__ __forceinline__ Chan4 chan4_load_s(const float* tbl, int C, int c) {       // table in shared memory
+  Chan4 k;
+  k.mean = ld4(tbl + c); k.rstd = ld4(tbl + C + c); k.scale = ld4(tbl + 2 * C + c); k.beta = ld4(tbl + 3 * C + c);
+  return k;
+}
 __device__ __forceinline__ float4 chan4_bn(const Chan4& k, float4 y) {
   return make_float4(fmaf(y.x - k.mean.x, k.scale.x, k.beta.x), fmaf(y.y - k.mean.y, k.scale.y, k.beta.y),
                      fmaf(y.z - k.mean.z, k.scale.z, k.beta.z), fmaf(y.w - k.mean.w, k.scale.w, k.beta.w));
@@ -73,10 +78,10 @@ __device__ __forceinline__ float4 chan4_xhat(const Chan4& k, float4 y) {
 }
 // activation source with hoisted constants
 struct Act4 { const float* data; Chan4 k; int kind; };
-__device__ __forceinline__ Act4 act4_make(const ActSrc& s, int C, int c) {
+__device__ __forceinline__ Act4 act4_make(const ActSrc& s, int C, int c, const float* tbl) {
   Act4 a;
   a.data = s.data; a.kind = s.kind;
-  if (s.kind == 1) a.k = chan4_load(s.bnf, C, c);
+  if (s.kind == 1) a.k = chan4_load_s(tbl, C, c);
   return a;
 }
 __device__ __forceinline__ float4 act4_load(const Act4& a, size_t ofs) {
@@ -86,11 +91,11 @@ __device__ __forceinline__ float4 act4_load(const Act4& a, size_t ofs) {
 }
 // dy = scale * (dz - s1/M - xhat * s2/M) with hoisted constants
 struct Dy4 { const float* dz; const float* y; Chan4 k; float4 s1m, s2m; int mask; };
-__device__ __forceinline__ Dy4 dy4_make(const DySrc& d, int C, int c) {
+__device__ __forceinline__ Dy4 dy4_make(const DySrc& d, int C, int c, const float* sb) {   // sb: [2][C] sums in shared memory
   Dy4 r;
   r.dz = d.dz; r.y = d.y; r.mask = d.mask_relu;
   r.k = chan4_load(d.bnf, C, c);
-  const float4 s1 = ldc4(d.bsum + c), s2 = ldc4(d.bsum + C + c);
+  const float4 s1 = ld4(sb + c), s2 = ld4(sb + C + c);
   const float im = d.inv_m;
   r.s1m = make_float4(s1.x * im, s1.y * im, s1.z * im, s1.w * im);
   r.s2m = make_float4(s2.x * im, s2.y * im, s2.z * im, s2.w * im);
@@ -126,62 +131,38 @@ __device__ __forceinline__ RowWalk row_walk(int tid, int nthreads, int c4n) {
   return w;
 }
 
-// ---- two-level "last CTA finalises" tree -------------------------------------------------------------
-// A single CTA walking all G partials is a latency chain (measured: 22 us for G = 256).  Instead CTAs are
-// grouped by kFanIn: the last CTA of each group to finish combines that group's <= 16 partials into a level-2
-// record; the last group to finish combines the <= 16.. level-2 records into the table.  Every step reads at most
-// kFanIn (or ceil(G/kFanIn)) records per channel with independent loads; grouping and order are fixed, so the
-// result is deterministic.  counters: [0] = level-2 arrivals, [1 + g] = arrivals of group g (all self-resetting).
-constexpr int kFanIn = 16;
-
-// returns 0: nothing to do, 1: this CTA combines its group (level 1), then call tree_arrive_l2
-__device__ __forceinline__ int tree_arrive_l1(unsigned* counters, int cta, int ncta) {
-  __shared__ int s_flag;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int grp = cta / kFanIn;
-    const int members = imin(kFanIn, ncta - grp * kFanIn);
-    const unsigned prev = atomicAdd(counters + 1 + grp, 1u);
-    s_flag = (prev == (unsigned)members - 1);
-    if (s_flag) counters[1 + grp] = 0;
+// ---- cross-CTA BatchNorm statistics: cluster reduce in the producer, table in the consumer -------------------------
+// Producer: every CTA leaves its per-channel partial sums in its OWN shared memory; the CTAs of a thread-block cluster add
+// them through distributed shared memory (rank order) and write one record per cluster, part[cluster][cols].  No atomics,
+// no fences, no "last CTA" tail: the kernel ends when its tiles are done.  (A launch without a cluster dimension is a
+// cluster of one: one record per CTA, which is what the persistent kernel's finalize phases read.)
+// Consumer: the next kernel sums the <= 32..64 records per channel in its prologue (every CTA, redundantly, from L2) and
+// keeps the finished table in shared memory; CTA 0 also publishes it for the kernels further down the stream.
+// Everything is summed in a fixed order, so the step stays bit-reproducible.
+struct PubSeg { const float* sp; int n; float* g; };   // shared-memory partials, column count, global records [cluster][n]
+template <int NSEG>
+__device__ __forceinline__ void cluster_publish(const PubSeg (&seg)[NSEG], int vb) {
+  cluster_sync_all();
+  const int CL = (int)cluster_nctarank(), r = (int)cluster_ctarank();
+  const int cid = vb / CL;
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < NSEG; ++k) total += seg[k].n;
+  for (int col = r + CL * (int)threadIdx.x; col < total; col += CL * (int)blockDim.x) {
+    int k = 0, c = col;
+#pragma unroll
+    for (int j = 0; j < NSEG - 1; ++j)
+      if (k == j && c >= seg[j].n) { c -= seg[j].n; k = j + 1; }
+    const float* sp = seg[k].sp + c;
+    float s = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < CL; ++q) s += ld_dsmem(sp, (unsigned)q);
+    seg[k].g[(size_t)cid * seg[k].n + c] = s;
   }
-  __syncthreads();
-  const int f = s_flag;
-  if (f) __threadfence();
-  return f;
-}
-__device__ __forceinline__ int tree_arrive_l2(unsigned* counters, int ncta) {
-  __shared__ int s_flag2;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ngrp = (ncta + kFanIn - 1) / kFanIn;
-    const unsigned prev = atomicAdd(counters, 1u);
-    s_flag2 = (prev == (unsigned)ngrp - 1);
-    if (s_flag2) counters[0] = 0;
-  }
-  __syncthreads();
-  const int f = s_flag2;
-  if (f) __threadfence();
-  return f;
+  cluster_sync_all();               // nobody exits (and releases its shared memory) while a peer may still read it
 }
 
-// Level 1: sum the (sum y, sum y^2) partials of CTAs [g0, g1) into l2[(grp*C + c)*2 + q]; level 2: sum the l2 records and
-// form the BN table.
-__device__ __forceinline__ void bn_combine_l1(const BnFinalize& f, int grp, int ncta, int /*U*/, int /*n*/, int /*t_out*/, float* l2) {
-  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
-  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
-    float v[kFanIn];
-#pragma unroll
-    for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(f.fpart + (size_t)imin(g0 + j, g1 - 1) * f.c * 2 + i);
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < kFanIn; ++j)
-      if (g0 + j < g1) s += (double)v[j];
-    l2[(size_t)grp * f.c * 2 + i] = (float)s;
-  }
-}
+// One channel of a BN table from its batch sums (used by the persistent kernel's finalize phase).
 __device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, double s1, double s2, double m_total, float eps) {
   const double mean = s1 / m_total;
   double var = s2 / m_total - mean * mean;
@@ -193,70 +174,83 @@ __device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, doubl
   f.bnf[3 * f.c + c] = f.beta[c];
   f.var[c] = (float)var;
 }
-__device__ __forceinline__ void bn_combine_l2(const BnFinalize& f, int ngrp, const float* l2, float eps, double m_total) {
-  for (int c = threadIdx.x; c < f.c; c += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int g0 = 0; g0 < ngrp; g0 += kFanIn) {           // all loads of a batch in flight before the first add
-      float2 v[kFanIn];
+
+// Sum `gc` records of `cols` floats each: thread i < cols * nch takes column i % cols and records i / cols, + nch, ...
+// (loads batched 8 deep); the nch chunk sums land in scratch[chunk * cols + col].  Needs cols <= blockDim.x.
+constexpr int kFanIn = 16;         // sizing unit of the legacy per-layer scratch records (workspace layout only)
+constexpr int kRecB = 8;
+__device__ __forceinline__ int records_sum(const float* part, int gc, int cols, float* scratch) {
+  const int nch = imax(1, (int)blockDim.x / cols);
+  const int i = threadIdx.x;
+  if (i < cols * nch) {
+    const int col = i % cols, ch = i / cols;
+    float s = 0.f;
+    for (int g0 = ch; g0 < gc; g0 += nch * kRecB) {
+      float v[kRecB];
 #pragma unroll
-      for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(reinterpret_cast<const float2*>(l2) + (size_t)imin(g0 + j, ngrp - 1) * f.c + c);
+      for (int j = 0; j < kRecB; ++j) {
+        const int g = g0 + j * nch;
+        v[j] = g < gc ? __ldcg(part + (size_t)g * cols + col) : 0.f;
+      }
 #pragma unroll
-      for (int j = 0; j < kFanIn; ++j)
-        if (g0 + j < ngrp) { s1 += (double)v[j].x; s2 += (double)v[j].y; }
+      for (int j = 0; j < kRecB; ++j) s += v[j];
     }
-    bn_table_write(f, c, s1, s2, m_total, eps);
+    scratch[ch * cols + col] = s;
   }
-}
-// Sums of (sum dz, sum dz*xhat): level 1 -> l2[(grp*C + c)*2 + q], level 2 -> bsum[q*C + c]
-__device__ __forceinline__ void bwdsum_combine_l1(const BwdSumFinalize& f, int grp, int ncta, float* l2) {
-  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
-  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
-    float v[kFanIn];
-#pragma unroll
-    for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(f.bpart + (size_t)imin(g0 + j, g1 - 1) * f.c * 2 + i);
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < kFanIn; ++j)
-      if (g0 + j < g1) s += (double)v[j];
-    l2[(size_t)grp * f.c * 2 + i] = (float)s;
-  }
-}
-__device__ __forceinline__ void bwdsum_combine_l2(const BwdSumFinalize& f, int ngrp, const float* l2) {
-  for (int i = threadIdx.x; i < 2 * f.c; i += blockDim.x) {
-    double s = 0.0;
-    for (int g0 = 0; g0 < ngrp; g0 += kFanIn) {
-      float v[kFanIn];
-#pragma unroll
-      for (int j = 0; j < kFanIn; ++j) v[j] = __ldcg(l2 + (size_t)imin(g0 + j, ngrp - 1) * f.c * 2 + i);
-#pragma unroll
-      for (int j = 0; j < kFanIn; ++j)
-        if (g0 + j < ngrp) s += (double)v[j];
-    }
-    f.bsum[(i & 1) * f.c + (i >> 1)] = (float)s;
-  }
+  return nch;
 }
 
-// Scalar (loss) variant of the tree: loss_part[G] -> l2[ngrp] -> *out
-__device__ __forceinline__ void scalar_combine_l1(const float* part, int grp, int ncta, float* l2) {
-  __shared__ float s_v[kFanIn];
-  const int g0 = grp * kFanIn, g1 = imin(ncta, g0 + kFanIn);
-  if (threadIdx.x < kFanIn) s_v[threadIdx.x] = (g0 + (int)threadIdx.x < g1) ? __ldcg(part + g0 + threadIdx.x) : 0.f;
+// BN table of one layer in shared memory tbl[4][C] (mean, rstd, scale, beta).  st.cpart == nullptr: the global table is
+// already final (persistent kernel / eval tables) and is only copied.  Block-wide; ends with __syncthreads().
+__device__ __forceinline__ void bn_table_build(const StatSrc& st, const float* bnf_global, int C, float* tbl, float* scratch, bool publish) {
+  if (!st.cpart) {
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) tbl[i] = ldc1(bnf_global + i);
+    __syncthreads();
+    return;
+  }
+  const int nch = records_sum(st.cpart, st.gc, 2 * C, scratch);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int j = 0; j < kFanIn; ++j) s += (double)s_v[j];
-    l2[grp] = (float)s;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int ch = 0; ch < nch; ++ch) {
+      s1 += (double)scratch[ch * 2 * C + 2 * c];
+      s2 += (double)scratch[ch * 2 * C + 2 * c + 1];
+    }
+    const double mean = s1 * (double)st.inv_m;
+    double var = s2 * (double)st.inv_m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)st.eps);
+    const float g = st.gamma[c], b = st.beta[c];
+    const float fm = (float)mean, fr = (float)rstd, fs = (float)((double)g * rstd);
+    tbl[c] = fm; tbl[C + c] = fr; tbl[2 * C + c] = fs; tbl[3 * C + c] = b;
+    if (publish) {
+      st.bnf[c] = fm; st.bnf[C + c] = fr; st.bnf[2 * C + c] = fs; st.bnf[3 * C + c] = b;
+      st.var[c] = (float)var;
+    }
   }
-}
-__device__ __forceinline__ void scalar_combine_l2(const float* l2, int ngrp, float* out) {
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int g = 0; g < ngrp; ++g) s += (double)__ldcg(l2 + g);
-    *out = (float)s;
-  }
+  __syncthreads();
 }
 
-// Per-channel (sum y, sum y^2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}], ONE pass.
+// BN-backward sums of one layer in shared memory sb[2][C] (sum dz, sum dz*xhat), same conventions.
+__device__ __forceinline__ void bsum_build(const BsumSrc& bs, const float* bsum_global, int C, float* sb, float* scratch, bool publish) {
+  if (!bs.cpart) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sb[i] = ldc1(bsum_global + i);
+    __syncthreads();
+    return;
+  }
+  const int nch = records_sum(bs.cpart, bs.gc, 2 * C, scratch);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double s = 0.0;
+    for (int ch = 0; ch < nch; ++ch) s += (double)scratch[ch * 2 * C + i];
+    const float f = (float)s;
+    sb[(i & 1) * C + (i >> 1)] = f;
+    if (publish) bs.bsum[(i & 1) * C + (i >> 1)] = f;
+  }
+  __syncthreads();
+}
+
+// Per-channel (sum y, sum y^2) of a [rows][C] shared-memory tile -> part_out[c*2 + {0,1}] (shared memory), ONE pass.
 // Requires C <= blockDim.x.  red: 2 * blockDim.x floats of scratch.  The cross-CTA combination is then a plain
 // fixed-order sum; var = E[y^2] - mean^2 is formed once per channel in fp64 (relative error ~1e-7 (1 + mean^2/var)).
 __device__ __forceinline__ void tile_stats(const float* tile, int rows, int C, float* red, float* /*unused*/, float* part_out) {

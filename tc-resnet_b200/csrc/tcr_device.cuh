@@ -20,21 +20,38 @@ void pdl_chain_reset();                               // called at every API ent
 // drains; pdl_wait() (griddepcontrol.wait) is the point after which the previous kernel's results may be read.
 // Every kernel calls pdl_wait() exactly once on every path, so completion is transitive along the stream.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {                // thread-block cluster along x: grid.x must be a multiple of `cluster`
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 }  // namespace tcr
+// cluster launch: CTAs of a cluster share partial BatchNorm sums through distributed shared memory
+#define TCR_LAUNCH_CLUSTER(name, kernel, grid, block, smem, stream, cluster, ...)                                   \
+  do {                                                                                                              \
+    tcr::prof_begin((name), (cudaStream_t)(stream));                                                                \
+    tcr::launch_ex(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), (unsigned)(cluster), __VA_ARGS__); \
+    tcr::prof_end((cudaStream_t)(stream));                                                                          \
+  } while (0)
 #define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...)                                          \
   do {                                                                                                    \
     tcr::prof_begin((name), (cudaStream_t)(stream));                                                      \
-    tcr::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__); \
+    tcr::launch_ex(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), 1u, __VA_ARGS__); \
     tcr::prof_end((cudaStream_t)(stream));                                                                \
   } while (0)
 #define TCR_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
@@ -61,6 +78,30 @@ __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+
+// ---- thread-block cluster primitives (a kernel launched without a cluster dimension is a cluster of one CTA) ----
+#ifndef TCR_EMU
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// all threads of all CTAs of the cluster; release/acquire: shared-memory writes before it are visible cluster-wide after it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float at the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+#else
+__device__ __forceinline__ unsigned cluster_ctarank() { return emu::cluster_rank(); }
+__device__ __forceinline__ unsigned cluster_nctarank() { return emu::cluster_size(); }
+__device__ __forceinline__ void cluster_sync_all() { emu::cluster_sync(); }
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) { return *reinterpret_cast<const float*>(emu::dsmem(local, rank)); }
+#endif
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

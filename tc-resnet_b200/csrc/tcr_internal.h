@@ -22,11 +22,27 @@ constexpr int kMaxBlocks = 8;
 constexpr int kThreads = 256;        // conv fwd / bwd-data CTAs
 constexpr int kMaxClasses = 32;
 
+// Forward statistics of a layer as its producer kernel left them (tcr_bn.cuh): per-cluster records that the consumer
+// sums, or nothing (cpart == nullptr) when the global table is already final.
+struct StatSrc {
+  const float* cpart;       // [gc][C][2] (sum y, sum y^2)
+  int gc;
+  const float* gamma; const float* beta;
+  float* bnf; float* var;   // published by CTA 0 of the consumer
+  float inv_m, eps;
+};
+struct BsumSrc {            // same for the BatchNorm-backward sums (sum dz, sum dz*xhat)
+  const float* cpart;       // [gc][C][2]
+  int gc;
+  float* bsum;              // [2][C], published by CTA 0 of the consumer
+};
+
 // Source of an activation tile: kind 0 = raw tensor, 1 = relu(bn(y)) with table bnf.
 struct ActSrc {
   const float* data;
   const float* bnf;   // [4][C]: mean, rstd, scale, beta
   int kind;
+  StatSrc st;
 };
 
 struct BnFinalize {         // what the last CTA of a producer kernel needs to finalise forward statistics
@@ -54,6 +70,7 @@ struct FwdArgs {
   ActSrc shortcut;          // kind 2 only: raw prev activation / relu(bn(y_down))
   float* out_write;         // kind 2 only: materialised block output [N, t_in, cin]
   int n, U, t_in, cin;
+  int nvb;                  // CTAs with work; the launch grid is nvb rounded up to whole clusters
   // main conv
   const float* w; float* y; float* fpart;
   int cout, stride, t_out, pad_left, KS;
@@ -74,6 +91,7 @@ struct HeadArgs {
   ActSrc shortcut;          // raw / relu(bn(y_down))
   float* out_write;         // [N, T', C]
   int n, t, c, classes;
+  int nvb;                  // CTAs with work (grid = nvb rounded up to whole clusters)
   const float* wfc;         // [C, classes]
   const float* onehot;      // may be null (no loss, no backward)
   const float* mask;        // injected dropout mask or null
@@ -101,10 +119,12 @@ struct DySrc {              // dy = scale * (dz - s1/M - xhat * s2/M), dz option
   const float* bsum;        // [2][C]
   int mask_relu;            // 1: dz *= (bn(y) > 0)   (down conv: its own ReLU is applied here)
   float inv_m;              // 1 / (N * T')
+  BsumSrc bs;               // where the sums come from when the producer kernel has just written them
 };
 
 struct BwdDataArgs {
   int n, U;
+  int nvb;                  // CTAs with work (grid = nvb rounded up to whole clusters)
   int w_smem;               // 1: filter bank(s) staged in shared memory by one TMA bulk copy
   // conv whose input gradient we compute
   DySrc dy; const float* w; int cin, cout, k, stride, t_in, t_out, pad_left, KS;

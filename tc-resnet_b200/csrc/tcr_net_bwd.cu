@@ -30,12 +30,13 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(
 // ------------------------------------------------------------------------------------------------
 template <int K, bool WSMEM>
 __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const int vb, const int nvb, unsigned char* smem_raw,
-                                                   MbarCtx& mb, const bool tree) {
+                                                   MbarCtx& mb) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
   const int S = a.stride;
   const int u0 = vb * a.U;
-  const int Ue = imin(a.U, a.n - u0);
+  const int Ue = imax(0, imin(a.U, a.n - u0));        // 0: a CTA that only pads the grid to whole clusters
+  (void)nvb;
   const int COS = chan_stride(a.cout);
   const int PLd = (K - 1) / S;
   const int PRd = imax(0, (a.t_in - 1 + a.pad_left) / S - (a.t_out - 1));
@@ -66,6 +67,10 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
   float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
   float* red = ws;                                                   // [4][nseg][cin]: aliases the filter bank / dy tiles,
                                                                      // which are dead once the transposed conv is done
+  float* stat = dxs + (size_t)a.KS * Rin_max * a.cin;                // BN-backward sums: [2][cout] + [2][coutd] while staging,
+  float* sb_main = stat;                                             // then this CTA's [4*cin] partial sums of the epilogue
+  float* sb_down = stat + 2 * a.cout;
+  float* stat_scratch = stat + imax(4 * a.cin, 2 * a.cout + 2 * a.coutd);   // [kThreads]
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), dys_off = (int)(dys - smem), dysd_off = (int)(dysd - smem);
 
   // ---- stage dy (BatchNorm backward applied on load) ----
@@ -77,12 +82,14 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
       st4(dys + ((size_t)(u * TPd + row) * COS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
     }
     pdl_wait();                     // the transposed filter bank (TMA above) was written at the start of the step
+    bsum_build(a.dy.bs, a.dy.bsum, a.cout, sb_main, stat_scratch, vb == 0);
+    if (a.has_down) bsum_build(a.dyd.bs, a.dyd.bsum, a.coutd, sb_down, stat_scratch, vb == 0);
     {
       const RowWalk w = row_walk(tid, kThreads, c4n);
       const int rows = Ue * a.t_out;
       const size_t grow = (size_t)u0 * a.t_out;
       if (w.row < rows) {
-        const Dy4 d = dy4_make(a.dy, a.cout, 4 * w.c4);
+        const Dy4 d = dy4_make(a.dy, a.cout, 4 * w.c4, sb_main);
         int u = w.row / a.t_out, t = w.row - u * a.t_out;
         for (int row = w.row; row < rows; row += w.rstep) {
           st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * w.c4), dy4_load(d, (grow + row) * a.cout + 4 * w.c4));
@@ -97,7 +104,7 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
       const int rows = Ue * a.t_out;
       const size_t grow = (size_t)u0 * a.t_out;
       if (w.row < rows) {
-        const Dy4 d = dy4_make(a.dyd, a.coutd, 4 * w.c4);
+        const Dy4 d = dy4_make(a.dyd, a.coutd, 4 * w.c4, sb_down);
         for (int row = w.row; row < rows; row += w.rstep)
           st4(dysd + ((size_t)row * COSD + 4 * w.c4), dy4_load(d, (grow + row) * a.coutd + 4 * w.c4));
       }
@@ -254,18 +261,10 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
     const int qd = i / a.cin, c = i - qd * a.cin;
     float s = 0.f;
     for (int sg = 0; sg < nseg; ++sg) s += red[((size_t)qd * nseg + sg) * a.cin + c];
-    if (qd < 2) a.bpartp[((size_t)vb * a.cin + c) * 2 + qd] = s;
-    else a.bpartpd[((size_t)vb * a.cin + c) * 2 + (qd - 2)] = s;
+    stat[(qd >> 1) * 2 * a.cin + c * 2 + (qd & 1)] = s;          // producer layer: [c*2+q], then its down conv: [c*2+q]
   }
-  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
-    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
-    bwdsum_combine_l1(a.finp, grp, nvb, a.finp.l2);
-    if (nq == 4) bwdsum_combine_l1(a.finpd, grp, nvb, a.finpd.l2);
-    if (tree_arrive_l2(a.counter, nvb)) {
-      bwdsum_combine_l2(a.finp, ngrp, a.finp.l2);
-      if (nq == 4) bwdsum_combine_l2(a.finpd, ngrp, a.finpd.l2);
-    }
-  }
+  const PubSeg segs[2] = {{stat, 2 * a.cin, a.bpartp}, {stat + 2 * a.cin, nq == 4 ? 2 * a.cin : 0, a.bpartpd}};
+  cluster_publish(segs, vb);
 }
 
 template <int K, bool WSMEM>
@@ -273,7 +272,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_data_kernel(BwdDataArgs a) 
   TCR_DYNAMIC_SMEM(smem_raw);
   MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
   pdl_trigger();
-  conv_bwd_data_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
+  conv_bwd_data_body<K, WSMEM>(a, blockIdx.x, a.nvb, smem_raw, mb);
 }
 
 // Transposed filter banks wT[k][co][ci] for the backward-data kernels (all conv layers, one launch).  `params`
@@ -310,6 +309,11 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
   const int NP = CI2 * (a.cot >> 2);
   float* xs = smem;                                            // [UB][TP][cin]
   float* dys = xs + (size_t)a.UB * TP * a.cin;                 // [UB * t_out][cot]
+  float* tblx = dys + (size_t)a.UB * a.t_out * a.cot;          // [4][cin] BN table of the input layer
+  float* sbw = tblx + 4 * a.cin;                               // [2][cout] BN-backward sums of this layer
+  float* wscr = sbw + 2 * a.cout;                              // [kDwThreads] scratch
+  if (a.x.kind == 1) bn_table_build(a.x.st, a.x.bnf, a.cin, tblx, wscr, false);
+  bsum_build(a.dy.bs, a.dy.bsum, a.cout, sbw, wscr, bx == 0 && by == 0);   // conv0: no backward-data kernel published its sums
   const int rg = tid / NP, pr = tid - rg * NP;
   const int ci2 = pr % CI2, co4 = pr / CI2;
   const bool worker = rg < a.RG;
@@ -330,7 +334,7 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
       const RowWalk w = row_walk(tid, (int)blockDim.x, c4n);
       const int rows = Ue * a.t_in;
       if (w.row < rows) {
-        const Act4 src = act4_make(a.x, a.cin, 4 * w.c4);
+        const Act4 src = act4_make(a.x, a.cin, 4 * w.c4, tblx);
         int u = w.row / a.t_in, t = w.row - u * a.t_in;
         for (int row = w.row; row < rows; row += w.rstep) {
           st4(xs + ((size_t)(u * TP + a.pad_left + t) * a.cin + 4 * w.c4),
@@ -344,7 +348,7 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
       const RowWalk w = row_walk(tid, (int)blockDim.x, d4n);
       const int rows = Ue * a.t_out;
       if (w.row < rows) {
-        const Dy4 d = dy4_make(a.dy, a.cout, cot0 + 4 * w.c4);
+        const Dy4 d = dy4_make(a.dy, a.cout, cot0 + 4 * w.c4, sbw);
         for (int row = w.row; row < rows; row += w.rstep)
           st4(dys + (size_t)row * a.cot + 4 * w.c4, dy4_load(d, ((size_t)ub0 * a.t_out + row) * a.cout + cot0 + 4 * w.c4));
       }
@@ -372,7 +376,7 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
     __syncthreads();
   }
   // ---- fixed-order reduction over the row groups of this CTA, then one partial per (row chunk, weight) ----
-  float* scratch = smem;                                       // [(RG-1)][NP][K][8], tiles are dead now
+  float* scratch = smem;                                       // [(RG-1)][NP][K][8], tiles and tables are dead now
   if (worker && rg > 0) {
     float* sc = scratch + ((size_t)(rg - 1) * NP + pr) * K * 8;
 #pragma unroll
@@ -403,7 +407,7 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
 // All layers' weight gradients in ONE launch: virtual CTA -> (layer, output-channel tile, row chunk) through a
 // static table, so ~600 CTAs of 256 threads keep every SM busy instead of ten serial 64-CTA launches.
 __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ layers, int nlayers, int n, const float* __restrict__ feat,
-                                                long long* tl, const int vb, unsigned char* smem_raw) {
+                                                long long* tl, const int vb, unsigned char* smem_raw, const BsumSrc& bs0) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   tl_stamp(tl, 4096 + vb, 0);
   int l = 0;
@@ -413,8 +417,8 @@ __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ laye
   const int ncot = L.cout / L.cot;
   BwdWeightArgs a;
   a.n = n;
-  a.x = ActSrc{L.x_data ? L.x_data : feat, L.x_bnf, L.x_kind};
-  a.dy = DySrc{L.dz, L.y, L.bnf, L.bsum, L.mask_relu, 1.0f / ((float)n * (float)L.t_out)};
+  a.x = ActSrc{L.x_data ? L.x_data : feat, L.x_bnf, L.x_kind, StatSrc{}};     // tables were published during the forward pass
+  a.dy = DySrc{L.dz, L.y, L.bnf, L.bsum, L.mask_relu, 1.0f / ((float)n * (float)L.t_out), l == 0 ? bs0 : BsumSrc{nullptr, 0, nullptr}};
   a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.stride = L.stride; a.t_in = L.t_in; a.t_out = L.t_out;
   a.pad_left = L.pad_left; a.cot = L.cot; a.RG = L.RG; a.R = L.R; a.UB = L.UB; a.dwpart = L.dwpart;
   const int bx = local % ncot, by = local / ncot;
@@ -426,10 +430,10 @@ __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ laye
   if (tl && threadIdx.x == 0) { tl[(size_t)(4096 + vb) * 8 + 3] = l; tl[(size_t)(4096 + vb) * 8 + 4] = (long long)by; }
 }
 __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
-                                                                const float* __restrict__ feat, long long* tl) {
+                                                                const float* __restrict__ feat, long long* tl, BsumSrc bs0) {
   TCR_DYNAMIC_SMEM(smem_raw);
   pdl_wait();
-  dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw);
+  dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw, bs0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,6 +452,7 @@ static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int K
   f += (w_smem ? (size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0) : 0);
   f = std::max(f, (size_t)4 * nseg * cv.cin);            // epilogue scratch aliases the filter bank + dy tiles
   f += 4 + (size_t)KS * U * cv.t_in * cv.cin;
+  f += std::max((size_t)4 * cv.cin, (size_t)2 * cv.cout + (dn ? (size_t)2 * dn->cout : 0)) + kThreads;   // BN-backward sums / partials
   return f * 4;
 }
 
@@ -486,7 +491,7 @@ static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_
 static size_t bwd_weight_smem(const ConvPlan& cv, int cot, int RG, int UB) {
   const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
   const int TP = cv.pad_left + cv.t_in + pad_right;
-  const size_t tiles = ((size_t)UB * TP * cv.cin + (size_t)UB * cv.t_out * cot) * 4;
+  const size_t tiles = ((size_t)UB * TP * cv.cin + (size_t)UB * cv.t_out * cot + 4 * cv.cin + 2 * cv.cout + kDwThreads) * 4;
   const size_t np = (size_t)(cv.cin / 2) * (cot / 4);
   const size_t scratch = (size_t)(RG - 1) * np * cv.k * 8 * 4;
   return std::max(tiles, scratch);
@@ -562,7 +567,7 @@ int build_dw_table(tcr_handle* h) {
 }
 
 template <int K, bool WSMEM>
-static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s) {
+static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s, int cluster) {
   auto kfn = conv_bwd_data_kernel<K, WSMEM>;
 #ifndef TCR_EMU
   static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
@@ -571,15 +576,18 @@ static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, s
     smem_limit = smem;
   }
 #endif
-  TCR_LAUNCH(name, kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  TCR_LAUNCH_CLUSTER(name, kfn, dim3(groups), dim3(kThreads), smem, s, cluster, a);
   return 0;
 }
 
 static DySrc make_dy(const ConvPlan& cv, const float* dz, int mask, int n) {
-  return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, 1.0f / ((float)n * (float)cv.t_out)};
+  return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, 1.0f / ((float)n * (float)cv.t_out),
+               BsumSrc{cv.b_gc ? cv.bpart : nullptr, cv.b_gc, cv.bsum}};
 }
 
-static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, int slot, cudaStream_t s) {
+// *gc_out: per-cluster records of BatchNorm-backward sums this launch leaves for the layer(s) below (0 when recording)
+static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, int slot, cudaStream_t s,
+                    int* gc_out) {
   int U, KS, wsm;
   pick_bwd_tile(cv, dn, n, &U, &KS, &wsm);
   a.n = n; a.U = U; a.w_smem = wsm;
@@ -589,16 +597,21 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.has_down = dn ? 1 : 0;
   a.wd = dn ? dn->wT : nullptr;
   a.coutd = dn ? dn->cout : 0;
-  a.counter = h->d_counters + (size_t)slot * h->counter_stride;
+  (void)slot;
   const int groups = (n + U - 1) / U;
+  a.nvb = groups;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
+  *gc_out = 0;
   if (h->rec) {
     rec_bwd(h, a, cv.k, wsm, groups, smem);
     return 0;
   }
+  const int CL = cluster_size(h);
+  const int grid = (groups + CL - 1) / CL * CL;
+  *gc_out = grid / CL;
   switch (cv.k) {
-    case 9: return wsm ? launch_bwd_data<9, true>(("dx:" + cv.name).c_str(), a, groups, smem, s)
-                       : launch_bwd_data<9, false>(("dx:" + cv.name).c_str(), a, groups, smem, s);
+    case 9: return wsm ? launch_bwd_data<9, true>(("dx:" + cv.name).c_str(), a, grid, smem, s, CL)
+                       : launch_bwd_data<9, false>(("dx:" + cv.name).c_str(), a, grid, smem, s, CL);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }
@@ -636,8 +649,10 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
       a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.bl2, ca.cout};
       a.finpd = a.finp;
-      int rc = bwd_data(h, cb, nullptr, a, params, n, slot++, s);
+      int gc = 0;
+      int rc = bwd_data(h, cb, nullptr, a, params, n, slot++, s, &gc);
       if (rc) return rc;
+      ca.b_gc = gc;
     }
     // (2) conv_a (+ down conv | identity): dx is the gradient at the block input
     {
@@ -667,8 +682,16 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
         a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.bl2, c0.cout};
         a.finpd = a.finp;
       }
-      int rc = bwd_data(h, ca, dn, a, params, n, slot++, s);
+      int gc = 0;
+      int rc = bwd_data(h, ca, dn, a, params, n, slot++, s, &gc);
       if (rc) return rc;
+      if (i > 0) {
+        BlockPlan& pb = h->blocks[i - 1];
+        h->convs[pb.b].b_gc = gc;
+        if (pb.down >= 0) h->convs[pb.down].b_gc = gc;
+      } else {
+        h->convs[0].b_gc = gc;
+      }
     }
   }
   // weight gradients: every layer's inputs are final now -> one grouped launch over all layers
@@ -683,7 +706,10 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       smem_limit = h->dw_smem;
     }
 #endif
-    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat, h->d_timeline);
+    // conv0's BatchNorm-backward sums have no backward-data consumer: its weight-gradient CTAs add the records themselves
+    const ConvPlan& c0 = h->convs[0];
+    const BsumSrc bs0{c0.b_gc ? c0.bpart : nullptr, c0.b_gc, c0.bsum};
+    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat, h->d_timeline, bs0);
   }
   return 0;
 }

@@ -21,12 +21,12 @@ constexpr int TM = 4;   // output rows per thread task
 // conv forward
 // ------------------------------------------------------------------------------------------------
 template <int K, bool WSMEM>
-__device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, const int nvb, unsigned char* smem_raw, MbarCtx& mb,
-                                              const bool tree) {
+__device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, const int nvb, unsigned char* smem_raw, MbarCtx& mb) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
   const int u0 = vb * a.U;
-  const int Ue = imin(a.U, a.n - u0);
+  const int Ue = imax(0, imin(a.U, a.n - u0));        // 0: a CTA that only pads the grid to whole clusters
+  (void)nvb;
   const int CS = chan_stride(a.cin);
   const int pad_right = imax((a.t_out - 1) * a.stride + K - a.pad_left - a.t_in, 0);
   const int TP = a.pad_left + a.t_in + pad_right;
@@ -40,8 +40,10 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
   float* xs = wsd + wdn;                              // [U][TP][CS]
   float* ys = xs + (size_t)a.U * TP * CS;             // [KS][Rmax][cout]
   float* ysd = ys + (size_t)a.KS * Rmax * a.cout;     // [Rmax][coutd]
-  float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);
-  float* smean = red + 2 * kThreads;
+  float* red = ysd + (a.wd ? (size_t)Rmax * a.coutd : 0);   // [2 * kThreads] scratch
+  float* tbl_in = red + 2 * kThreads;                 // [4][cin] BN table of the input layer
+  float* tbl_sh = tbl_in + 4 * a.cin;                 // [4][cin] BN table of the shortcut (down conv of the previous block)
+  float* spart = tbl_sh + 4 * a.cin;                  // [2*cout + 2*coutd] this CTA's (sum y, sum y^2)
   const int ws_off = (int)(ws - smem), wsd_off = (int)(wsd - smem), xs_off = (int)(xs - smem);
 
   tl_stamp(a.tl, vb, 0);
@@ -69,6 +71,9 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
     st4(xs + ((size_t)(u * TP + row) * CS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
   }
   pdl_wait();                       // everything above is independent of the producer kernel (filters: caller-owned params)
+  // BN tables of the layers this tile reads, summed from the producers' per-cluster records (tcr_bn.cuh)
+  if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
+  if (a.in_kind == 2 && a.shortcut.kind == 1) bn_table_build(a.shortcut.st, a.shortcut.bnf, a.cin, tbl_sh, red, vb == 0);
   {
     // c4 fixed per thread (per-channel constants in registers), rows advance incrementally: no div/mod per element
     const RowWalk w = row_walk(tid, kThreads, c4n);
@@ -77,8 +82,8 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
     if (w.row < rows) {
       int u = w.row / a.t_in, t = w.row - u * a.t_in;
       if (a.in_kind == 2) {
-        const Chan4 kb = chan4_load(a.in.bnf, a.cin, 4 * w.c4);
-        const Act4 sh = act4_make(a.shortcut, a.cin, 4 * w.c4);
+        const Chan4 kb = chan4_load_s(tbl_in, a.cin, 4 * w.c4);
+        const Act4 sh = act4_make(a.shortcut, a.cin, 4 * w.c4, tbl_sh);
         for (int row = w.row; row < rows; row += w.rstep) {
           const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
           const float4 v = relu4(add4(chan4_bn(kb, ld4(a.in.data + gofs)), act4_load(sh, gofs)));
@@ -88,7 +93,7 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
           while (t >= a.t_in) { t -= a.t_in; ++u; }
         }
       } else {
-        const Act4 src = act4_make(a.in, a.cin, 4 * w.c4);
+        const Act4 src = act4_make(a.in, a.cin, 4 * w.c4, tbl_in);
         for (int row = w.row; row < rows; row += w.rstep) {
           const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
           st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), act4_load(src, gofs));
@@ -199,18 +204,11 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
   if (!a.train) return;
   __syncthreads();
   tl_stamp(a.tl, vb, 4);
-  tile_stats(ys, R, a.cout, red, smean, a.fpart + (size_t)vb * a.cout * 2);
-  if (a.wd) tile_stats(ysd, R, a.coutd, red, smean, a.fpartd + (size_t)vb * a.coutd * 2);
+  tile_stats(ys, R, a.cout, red, nullptr, spart);
+  if (a.wd) tile_stats(ysd, R, a.coutd, red, nullptr, spart + 2 * a.cout);
   tl_stamp(a.tl, vb, 5);
-  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
-    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
-    bn_combine_l1(a.fin, grp, nvb, a.U, a.n, a.t_out, a.fin.l2);
-    if (a.wd) bn_combine_l1(a.find, grp, nvb, a.U, a.n, a.t_out, a.find.l2);
-    if (tree_arrive_l2(a.counter, nvb)) {
-      bn_combine_l2(a.fin, ngrp, a.fin.l2, a.eps, (double)a.n * a.t_out);
-      if (a.wd) bn_combine_l2(a.find, ngrp, a.find.l2, a.eps, (double)a.n * a.t_out);
-    }
-  }
+  const PubSeg segs[2] = {{spart, 2 * a.cout, a.fpart}, {spart + 2 * a.cout, a.wd ? 2 * a.coutd : 0, a.fpartd}};
+  cluster_publish(segs, vb);
   tl_stamp(a.tl, vb, 6);
 }
 
@@ -219,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_kernel(FwdArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   MbarCtx mb{reinterpret_cast<uint64_t*>(smem_raw), 0u, false};
   pdl_trigger();                    // grid <= resident CTA slots: the next kernel's CTAs may take slots as ours retire
-  conv_fwd_body<K, WSMEM>(a, blockIdx.x, gridDim.x, smem_raw, mb, true);
+  conv_fwd_body<K, WSMEM>(a, blockIdx.x, a.nvb, smem_raw, mb);
 }
 
 // Eval mode: BN tables from the moving statistics (bn_forward with is_training=False).
@@ -258,14 +256,15 @@ constexpr int kHeadThreads = 256;
 // logit, dl [U*NC] each | loss [U] (+pad) | red [4][SEG][C] (<= 4 * 256)
 __host__ __device__ inline size_t head_smem_floats(int T, int C, int NC) {
   return (size_t)8 * C + (size_t)C * NC + 4 + (size_t)3 * kHeadU * T * C + 4 + (size_t)3 * kHeadU * C + (size_t)2 * kHeadU * NC +
-         kHeadU + 8 + 4 * kHeadThreads;
+         kHeadU + 8 + 4 * kHeadThreads + 4 * C + 4;
 }
 
-__device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw, const bool tree) {
+__device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const int nvb, unsigned char* smem_raw) {
+  (void)nvb;
   float* smem = reinterpret_cast<float*>(smem_raw) + 4;          // first 16 bytes: the persistent kernel's mbarrier
   const int C = a.c, T = a.t, NC = a.classes, TC = T * C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int u0 = vb * kHeadU, nu = imin(kHeadU, a.n - u0), rows = nu * T;
+  const int u0 = vb * kHeadU, nu = imax(0, imin(kHeadU, a.n - u0)), rows = nu * T;   // nu == 0: cluster padding CTA
   float* tb = smem;
   float* td = tb + 4 * C;
   float* s_wfc = td + 4 * C;
@@ -278,15 +277,12 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
   float* s_logit = s_dnet + kHeadU * C;
   float* s_dl = s_logit + kHeadU * NC;
   float* s_loss = s_dl + kHeadU * NC;
-  float* red = s_loss + kHeadU;
+  float* red = s_loss + kHeadU;                           // [4 * kHeadThreads]: scratch, then the CTA's partial sums
   const bool sh_bn = a.shortcut.kind == 1;
   const size_t base = (size_t)u0 * TC;
 
-#pragma unroll 1
-  for (int i = tid; i < 4 * C; i += kHeadThreads) {
-    tb[i] = ldc1(a.in.bnf + i);
-    td[i] = sh_bn ? ldc1(a.shortcut.bnf + i) : 0.f;
-  }
+  bn_table_build(a.in.st, a.in.bnf, C, tb, red, vb == 0);
+  if (sh_bn) bn_table_build(a.shortcut.st, a.shortcut.bnf, C, td, red, vb == 0);
 #pragma unroll 1
   for (int i = tid; i < C * NC; i += kHeadThreads) s_wfc[i] = __ldg(a.wfc + i);
 #pragma unroll 2
@@ -367,15 +363,15 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
     if (lane == 0) s_loss[u] = loss_n;
   }
   __syncthreads();
-  if (tid == 0 && a.onehot) {
-    float s = 0.f;
-    for (int u = 0; u < nu; ++u) s += s_loss[u];
-    a.loss_part[vb] = s;
-  }
   if (!a.backward) {
-    if (a.onehot && tree && tree_arrive_l1(a.counter, vb, nvb)) {
-      scalar_combine_l1(a.loss_part, vb / kFanIn, nvb, a.loss_l2);
-      if (tree_arrive_l2(a.counter, nvb)) scalar_combine_l2(a.loss_l2, (nvb + kFanIn - 1) / kFanIn, a.loss_out);
+    if (a.onehot) {
+      if (tid == 0) {
+        float s = 0.f;
+        for (int u = 0; u < nu; ++u) s += s_loss[u];
+        red[0] = s;
+      }
+      const PubSeg segs[1] = {{red, 1, a.loss_part}};
+      cluster_publish(segs, vb);                          // one CE record per cluster; the loss kernel adds them
     }
     return;
   }
@@ -417,39 +413,35 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
     }
   }
   __syncthreads();
+  float* sp = red + 4 * SEG * C;                          // [4C + 1] this CTA's sums: conv_b (c*2+q), down (c*2+q), CE
 #pragma unroll 1
   for (int i = tid; i < 4 * C; i += kHeadThreads) {
     const int q = i / C, cc = i - q * C;
     float s = 0.f;
     for (int k = 0; k < SEG; ++k) s += red[(q * SEG + k) * C + cc];
-    if (q < 2) a.bpartb[((size_t)vb * C + cc) * 2 + q] = s;
-    else if (a.ydn) a.bpartd[((size_t)vb * C + cc) * 2 + (q - 2)] = s;
+    sp[(q >> 1) * 2 * C + cc * 2 + (q & 1)] = s;
+  }
+  if (tid == 0) {
+    float s = 0.f;
+    for (int u = 0; u < nu; ++u) s += s_loss[u];
+    sp[4 * C] = s;
   }
 #pragma unroll 1
   for (int i = tid; i < C * NC; i += kHeadThreads) {
     const int cc = i / NC, k = i - cc * NC;
     float s = 0.f;
     for (int u = 0; u < nu; ++u) s = fmaf(s_drop[u * C + cc], s_dl[u * NC + k], s);
-    a.dwfc_part[(size_t)vb * C * NC + i] = s;
+    if (nu > 0) a.dwfc_part[(size_t)vb * C * NC + i] = s;     // cluster-padding CTAs own no record
   }
-  if (tree && tree_arrive_l1(a.counter, vb, nvb)) {
-    const int grp = vb / kFanIn, ngrp = (nvb + kFanIn - 1) / kFanIn;
-    bwdsum_combine_l1(a.finb, grp, nvb, a.finb.l2);
-    if (a.ydn) bwdsum_combine_l1(a.find, grp, nvb, a.find.l2);
-    scalar_combine_l1(a.loss_part, grp, nvb, a.loss_l2);
-    if (tree_arrive_l2(a.counter, nvb)) {
-      bwdsum_combine_l2(a.finb, ngrp, a.finb.l2);
-      if (a.ydn) bwdsum_combine_l2(a.find, ngrp, a.find.l2);
-      scalar_combine_l2(a.loss_l2, ngrp, a.loss_out);
-    }
-  }
+  const PubSeg segs[3] = {{sp, 2 * C, a.bpartb}, {sp + 2 * C, a.ydn ? 2 * C : 0, a.bpartd}, {sp + 4 * C, 1, a.loss_part}};
+  cluster_publish(segs, vb);
 }
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   TCR_DYNAMIC_SMEM(smem_raw);
   pdl_trigger();
   pdl_wait();
-  head_body(a, blockIdx.x, gridDim.x, smem_raw, true);
+  head_body(a, blockIdx.x, a.nvb, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,7 +460,7 @@ static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int 
   const int pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
   const int TP = cv.pad_left + cv.t_in + pad_right;
   size_t f = (size_t)U * TP * CS + (size_t)KS * U * cv.t_out * cv.cout + (dn ? (size_t)U * cv.t_out * dn->cout : 0);
-  f += 2 * kThreads + std::max(cv.cout, dn ? dn->cout : 0);
+  f += 2 * kThreads + 8 * (size_t)cv.cin + 2 * (size_t)cv.cout + (dn ? 2 * (size_t)dn->cout : 0);   // scratch, 2 BN tables, partial sums
   f += 4 + (w_smem ? fwd_weight_floats(cv, dn) : 0);
   return f * 4;
 }
@@ -583,8 +575,27 @@ int net_alloc_workspace(tcr_handle* h) {
   return build_opt_segments(h);
 }
 
+// Thread-block cluster size of the conv / head launches: 8 CTAs add their BatchNorm partial sums through distributed shared
+// memory (tcr_bn.cuh).  TCR_CLUSTER=1 falls back to one record per CTA.
+int cluster_size(tcr_handle* h) {
+  if (h->cluster == 0) {
+    const char* e = getenv("TCR_CLUSTER");
+    int c = e ? atoi(e) : 8;
+    if (c != 1 && c != 2 && c != 4 && c != 8) c = 8;
+    h->cluster = c;
+  }
+  return h->rec ? 1 : h->cluster;
+}
+StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n) {
+  return StatSrc{cv.f_gc ? cv.fpart : nullptr, cv.f_gc, params + cv.gamma_off, params + cv.beta_off, cv.bnf, cv.var,
+                 1.0f / ((float)n * (float)cv.t_out), h->cfg.bn_epsilon};
+}
+static ActSrc act_of(const tcr_handle* h, const ConvPlan& cv, int kind, const float* params, int n) {
+  return ActSrc{cv.y, cv.bnf, kind, stat_src(h, cv, params, n)};
+}
+
 template <int K, bool WSMEM>
-static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s) {
+static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s, int cluster) {
   auto kfn = conv_fwd_kernel<K, WSMEM>;
 #ifndef TCR_EMU
   static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
@@ -593,7 +604,7 @@ static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_
     smem_limit = smem;
   }
 #endif
-  TCR_LAUNCH(name, kfn, dim3(groups), dim3(kThreads), smem, s, a);
+  TCR_LAUNCH_CLUSTER(name, kfn, dim3(groups), dim3(kThreads), smem, s, cluster, a);
   return 0;
 }
 
@@ -607,7 +618,7 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
   a.train = training ? 1 : 0;
   a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline + (h->rec ? 12 * 8192 : 0) : nullptr;
-  a.counter = h->d_counters + (size_t)counter_slot * h->counter_stride;
+  (void)counter_slot;
   a.eps = h->cfg.bn_epsilon;
   a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.fl2, cv.cout};
   a.find = a.fin;
@@ -616,16 +627,25 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
     a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->fl2, dn->cout};
   }
   const int groups = (n + U - 1) / U;
+  a.nvb = groups;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
+  cv.f_gc = 0;
+  if (dn) dn->f_gc = 0;
   if (h->rec) {
     rec_fwd(h, a, cv.k, wsm, groups, smem);
     return 0;
   }
+  const int CL = cluster_size(h);
+  const int grid = (groups + CL - 1) / CL * CL;
+  if (training) {                   // the consumers of this layer's statistics sum grid / CL records
+    cv.f_gc = grid / CL;
+    if (dn) dn->f_gc = grid / CL;
+  }
   switch (cv.k) {
-    case 3: return wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, groups, smem, s)
-                       : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
-    case 9: return wsm ? launch_conv_fwd<9, true>(("fwd:" + cv.name).c_str(), a, groups, smem, s)
-                       : launch_conv_fwd<9, false>(("fwd:" + cv.name).c_str(), a, groups, smem, s);
+    case 3: return wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
+                       : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
+    case 9: return wsm ? launch_conv_fwd<9, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
+                       : launch_conv_fwd<9, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
 }
@@ -652,11 +672,11 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
     FwdArgs a;
     memset(&a, 0, sizeof(a));
     a.in_kind = 0;
-    a.in = ActSrc{feat, nullptr, 0};
+    a.in = ActSrc{feat, nullptr, 0, StatSrc{}};
     int rc = conv_fwd(h, h->convs[0], nullptr, a, params, n, training, slot++, s);
     if (rc) return rc;
   }
-  ActSrc prev{h->convs[0].y, h->convs[0].bnf, 1};   // activation feeding the next block
+  ActSrc prev = act_of(h, h->convs[0], 1, params, n);   // activation feeding the next block
   for (size_t i = 0; i < h->blocks.size(); ++i) {
     BlockPlan& b = h->blocks[i];
     ConvPlan& ca = h->convs[b.a];
@@ -671,25 +691,25 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       // input = output of block i-1 = relu(bn(y_b) + shortcut); materialised here for the backward pass
       BlockPlan& pb = h->blocks[i - 1];
       a.in_kind = 2;
-      a.in = ActSrc{h->convs[pb.b].y, h->convs[pb.b].bnf, 0};
-      a.shortcut = pb.down >= 0 ? ActSrc{h->convs[pb.down].y, h->convs[pb.down].bnf, 1} : prev;
+      a.in = act_of(h, h->convs[pb.b], 0, params, n);
+      a.shortcut = pb.down >= 0 ? act_of(h, h->convs[pb.down], 1, params, n) : prev;
       a.out_write = pb.out;
     }
     int rc = conv_fwd(h, ca, dn, a, params, n, training, slot++, s);
     if (rc) return rc;
-    if (i > 0) prev = ActSrc{h->blocks[i - 1].out, nullptr, 0};   // materialised by the launch above
+    if (i > 0) prev = ActSrc{h->blocks[i - 1].out, nullptr, 0, StatSrc{}};   // materialised by the launch above
     FwdArgs a2;
     memset(&a2, 0, sizeof(a2));
     a2.in_kind = 1;
-    a2.in = ActSrc{ca.y, ca.bnf, 1};
+    a2.in = act_of(h, ca, 1, params, n);
     rc = conv_fwd(h, cb, nullptr, a2, params, n, training, slot++, s);
     if (rc) return rc;
     if (i + 1 == h->blocks.size()) {
       BlockPlan& lb = b;
       HeadArgs ha;
       memset(&ha, 0, sizeof(ha));
-      ha.in = ActSrc{cb.y, cb.bnf, 0};
-      ha.shortcut = dn ? ActSrc{dn->y, dn->bnf, 1} : prev;
+      ha.in = act_of(h, cb, 0, params, n);
+      ha.shortcut = dn ? act_of(h, *dn, 1, params, n) : prev;
       ha.out_write = lb.out;
       ha.n = n; ha.t = lb.t; ha.c = lb.c; ha.classes = h->cfg.num_classes;
       ha.wfc = params + h->fc_off;
@@ -706,12 +726,17 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.yb = cb.y; ha.bnfb = cb.bnf; ha.bpartb = cb.bpart;
       ha.ydn = dn ? dn->y : nullptr; ha.bnfd = dn ? dn->bnf : nullptr; ha.bpartd = dn ? dn->bpart : nullptr;
       ha.dwfc_part = h->d_dwfc_part;
-      ha.counter = h->d_counters + (size_t)(slot++) * h->counter_stride;
       ha.loss_l2 = h->d_loss_l2;
       ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.bl2, cb.cout};
       ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->bl2, dn->cout} : ha.finb;
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
+      ha.nvb = groups;
+      const int CL = cluster_size(h);
+      const int grid = (groups + CL - 1) / CL * CL;
+      h->loss_gc = h->rec ? groups : grid / CL;           // CE records the loss / update kernel adds
+      cb.b_gc = (backward && !h->rec) ? grid / CL : 0;
+      if (dn) dn->b_gc = cb.b_gc;
       const size_t smem = (head_smem_floats(lb.t, lb.c, ha.classes) + 8) * 4;
       if (smem > kSmemBudget || lb.c > kHeadThreads) { set_error("head tile does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
       if (h->rec) {
@@ -724,7 +749,7 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
           head_lim = smem;
         }
 #endif
-        TCR_LAUNCH("head", head_kernel, dim3(groups), dim3(kHeadThreads), smem, s, ha);
+        TCR_LAUNCH_CLUSTER("head", head_kernel, dim3(grid), dim3(kHeadThreads), smem, s, CL, ha);
       }
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next

@@ -80,7 +80,7 @@ struct UpdateArgs {
   float lr, momentum, weight_decay, one_minus_decay, grad_scale;
   const MovingSegment* msegs; int nmsegs; int n;
   const float* l2part; int l2blocks;
-  const float* ce_sum; float inv_n;
+  const float* ce_sum; int ce_count; float inv_n;      // cross-entropy records of the head launch
   float* losses;          // may be null
   float* grads_out;       // may be null: scaled gradient actually applied
   int apply;
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int i = 0; i < kOptThreads; ++i) tot += s_l2[i];
-      const float model = *a.ce_sum * a.inv_n;
+      double ce = 0.0;
+      for (int i = 0; i < a.ce_count; ++i) ce += (double)a.ce_sum[i];      // per-cluster records of the head launch, fixed order
+      const float model = (float)ce * a.inv_n;
       a.losses[1] = model;
       a.losses[0] = model + a.weight_decay * (float)(0.5 * tot);
     }
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
 
 // Loss scalars for a forward-only call: sum of w^2 over the decayed variables in one CTA.
 __global__ void __launch_bounds__(1024) loss_only_kernel(const OptSegment* __restrict__ segs, int nsegs, const float* __restrict__ params,
-                                                         float weight_decay, const float* ce_sum, float inv_n, float* losses) {
+                                                         float weight_decay, const float* ce_sum, int ce_count, float inv_n, float* losses) {
   pdl_wait();
   __shared__ float s_red[32];
   float w2 = 0.f;
@@ -150,7 +152,9 @@ __global__ void __launch_bounds__(1024) loss_only_kernel(const OptSegment* __res
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (unsigned i = 0; i < blockDim.x / 32; ++i) s += (double)s_red[i];
-    const float model = *ce_sum * inv_n;
+    double ce = 0.0;
+    for (int i = 0; i < ce_count; ++i) ce += (double)ce_sum[i];
+    const float model = (float)ce * inv_n;
     losses[1] = model;
     losses[0] = model + weight_decay * (float)(0.5 * s);
   }
@@ -208,7 +212,7 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   u.grad_scale = 1.0f / (float)h->world;
   u.msegs = h->d_msegs; u.nmsegs = h->n_msegs; u.n = a->n;
   u.l2part = h->d_l2part; u.l2blocks = blocks;
-  u.ce_sum = h->d_loss; u.inv_n = 1.0f / (float)a->n;
+  u.ce_sum = h->d_loss_part; u.ce_count = h->loss_gc; u.inv_n = 1.0f / (float)a->n;
   u.losses = a->losses; u.grads_out = a->grads; u.apply = a->apply_update ? 1 : 0;
   u.param_blocks = blocks;
   TCR_LAUNCH("update", update_kernel, dim3(blocks + h->n_msegs + 1), dim3(kOptThreads), 0, s, u);
@@ -216,8 +220,8 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
 }
 
 int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int n, float* losses, cudaStream_t s) {
-  TCR_LAUNCH("loss_only", loss_only_kernel, dim3(1), dim3(1024), 0, s, h->d_segs, h->n_segs, params, weight_decay, h->d_loss,
-             1.0f / (float)n, losses);
+  TCR_LAUNCH("loss_only", loss_only_kernel, dim3(1), dim3(1024), 0, s, h->d_segs, h->n_segs, params, weight_decay, h->d_loss_part,
+             h->loss_gc, 1.0f / (float)n, losses);
   return 0;
 }
 

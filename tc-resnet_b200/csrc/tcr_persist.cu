@@ -111,11 +111,11 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
         for (int vb = b; vb < p.nvb; vb += nb) {
           const FwdArgs& a = P.fwd[p.idx];
           if (p.k == 9) {
-            if (p.wsmem) conv_fwd_body<9, true>(a, vb, p.nvb, smem_raw, mb, false);
-            else conv_fwd_body<9, false>(a, vb, p.nvb, smem_raw, mb, false);
+            if (p.wsmem) conv_fwd_body<9, true>(a, vb, p.nvb, smem_raw, mb);
+            else conv_fwd_body<9, false>(a, vb, p.nvb, smem_raw, mb);
           } else {
-            if (p.wsmem) conv_fwd_body<3, true>(a, vb, p.nvb, smem_raw, mb, false);
-            else conv_fwd_body<3, false>(a, vb, p.nvb, smem_raw, mb, false);
+            if (p.wsmem) conv_fwd_body<3, true>(a, vb, p.nvb, smem_raw, mb);
+            else conv_fwd_body<3, false>(a, vb, p.nvb, smem_raw, mb);
           }
           __syncthreads();
         }
@@ -125,15 +125,15 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
         break;
       case PH_HEAD:
         for (int vb = b; vb < p.nvb; vb += nb) {
-          head_body(P.head, vb, p.nvb, smem_raw, false);
+          head_body(P.head, vb, p.nvb, smem_raw);
           __syncthreads();
         }
         break;
       case PH_BWD:
         for (int vb = b; vb < p.nvb; vb += nb) {
           const BwdDataArgs& a = P.bwd[p.idx];
-          if (p.wsmem) conv_bwd_data_body<9, true>(a, vb, p.nvb, smem_raw, mb, false);
-          else conv_bwd_data_body<9, false>(a, vb, p.nvb, smem_raw, mb, false);
+          if (p.wsmem) conv_bwd_data_body<9, true>(a, vb, p.nvb, smem_raw, mb);
+          else conv_bwd_data_body<9, false>(a, vb, p.nvb, smem_raw, mb);
           __syncthreads();
         }
         break;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 2) step_kernel(const __grid_constant
         break;
       case PH_DW:
         for (int vb = b; vb < p.nvb; vb += nb) {
-          dw_grouped_body(P.dw_layers, P.n_dw_layers, P.n, P.feat, nullptr, vb, smem_raw);
+          dw_grouped_body(P.dw_layers, P.n_dw_layers, P.n, P.feat, nullptr, vb, smem_raw, BsumSrc{nullptr, 0, nullptr});
           __syncthreads();
         }
         break;

@@ -27,6 +27,9 @@ struct ConvPlan {
   float* dwpart = nullptr;     // [R][k*cin*cout]
   float* wT = nullptr;         // [k][cout][cin] transposed filter bank (refreshed per backward pass)
   int dw_R = 1, dw_cot = 0, dw_RG = 1, dw_UB = 1;
+  // per call: how many per-cluster records the producer launch of this step left in fpart / bpart (0: the global table /
+  // sums are final: persistent kernel, evaluation tables)
+  int f_gc = 0, b_gc = 0;
   int64_t wnumel() const { return (int64_t)k * cin * cout; }
 };
 
@@ -70,6 +73,8 @@ struct tcr_handle {
   // data-parallel
   void* comm = nullptr; int rank = 0, world = 1;
   int last_n = 0;
+  int loss_gc = 0;            // cross-entropy records left by the head launch of this call
+  int cluster = 0;            // CTAs per thread-block cluster of the conv / head launches (env TCR_CLUSTER, default 8)
   void* hostfeed = nullptr;   // HostFeedState (tcr_api.cu): staging slots of tcr_train_step_host
   tcr::StepProgram* rec = nullptr;   // non-null while a training step is being recorded for the persistent kernel
   size_t rec_smem = 0; int persist = -1; int persist_grid = 0; unsigned* d_gridbar = nullptr;

@@ -35,6 +35,7 @@ std::vector<BlockState> g_blocks;
 ucontext_t g_sched;
 const std::function<void()>* g_body = nullptr;
 int g_cur = 0, g_total_alive = 0, g_grid_count = 0;
+unsigned g_cluster = 1;   // CTAs per cluster of the running launch (1: ordinary / cooperative launches)
 unsigned g_grid_gen = 0;
 unsigned long long g_progress = 0;
 
@@ -187,6 +188,31 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
         one[0] = uint3{bx, by, bz};
         run(grid, block, smem_bytes, body, one, 256 * 1024);
       }
+}
+
+unsigned cluster_rank() { return g_cluster > 1 ? (unsigned)me().block : 0u; }
+unsigned cluster_size() { return g_cluster; }
+void cluster_sync() {
+  if (g_cluster > 1) gridsync();   // a cluster launch keeps exactly one cluster alive per run
+  else syncthreads();
+}
+const void* dsmem(const void* local, unsigned rank) {
+  if (g_cluster <= 1) return local;
+  const unsigned char* mine = me().tc.smem;
+  const unsigned char* theirs = g_fibers[(size_t)rank * (g_state.bdim.x * g_state.bdim.y * g_state.bdim.z)].tc.smem;
+  return theirs + ((const unsigned char*)local - mine);
+}
+
+void launch_cluster(dim3 grid, dim3 block, size_t smem_bytes, unsigned cluster, const std::function<void()>& body) {
+  if (cluster <= 1) { launch(grid, block, smem_bytes, body); return; }
+  if (grid.x % cluster != 0 || grid.y != 1 || grid.z != 1) { fprintf(stderr, "emu: grid %u not a multiple of cluster %u\n", grid.x, cluster); abort(); }
+  std::vector<uint3> blocks(cluster);
+  g_cluster = cluster;
+  for (unsigned c0 = 0; c0 < grid.x; c0 += cluster) {
+    for (unsigned r = 0; r < cluster; ++r) blocks[r] = uint3{c0 + r, 0, 0};
+    run(grid, block, smem_bytes, body, blocks, 128 * 1024);
+  }
+  g_cluster = 1;
 }
 
 void launch_cooperative(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {

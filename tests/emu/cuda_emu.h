@@ -52,7 +52,12 @@ struct State {
 State& st();
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 void launch_cooperative(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);   // all blocks co-resident
+void launch_cluster(dim3 grid, dim3 block, size_t smem_bytes, unsigned cluster, const std::function<void()>& body);   // one cluster at a time
 void gridsync();
+unsigned cluster_rank();
+unsigned cluster_size();
+void cluster_sync();                                  // barrier over the CTAs of the running cluster
+const void* dsmem(const void* local, unsigned rank);  // same offset in the shared memory of CTA `rank`
 void syncthreads();
 void syncwarp();
 uint64_t warp_exchange(uint64_t v, int src_lane);   // every lane posts v, returns lane src_lane's value
@@ -164,5 +169,7 @@ namespace tcr { void pdl_chain_reset(); }
 #define TCR_LAUNCH(name, kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define TCR_DYNAMIC_SMEM(name) unsigned char* name = emu::st().cur->smem
+#define TCR_LAUNCH_CLUSTER(name, kernel, grid, block, smem, stream, cluster, ...) \
+  emu::launch_cluster((grid), (block), (smem), (cluster), [&]() { kernel(__VA_ARGS__); })
 #define TCR_LAUNCH_COOP(name, kernel, grid, block, smem, stream, arg) \
   emu::launch_cooperative((grid), (block), (smem), [&]() { kernel(arg); })
