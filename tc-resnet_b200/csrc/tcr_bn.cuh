@@ -155,8 +155,11 @@ __device__ __forceinline__ void cluster_publish(const PubSeg (&seg)[NSEG], int v
       if (k == j && c >= seg[j].n) { c -= seg[j].n; k = j + 1; }
     const float* sp = seg[k].sp + c;
     float s = 0.f;
-#pragma unroll 4
-    for (int q = 0; q < CL; ++q) s += ld_dsmem(sp, (unsigned)q);
+    if (CL == 8) {
+      s = sum_dsmem8(sp);
+    } else {
+      for (int q = 0; q < CL; ++q) s += ld_dsmem(sp, (unsigned)q);
+    }
     seg[k].g[(size_t)cid * seg[k].n + c] = s;
   }
   cluster_sync_all();               // nobody exits (and releases its shared memory) while a peer may still read it
@@ -178,7 +181,7 @@ __device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, doubl
 // Sum `gc` records of `cols` floats each: thread i < cols * nch takes column i % cols and records i / cols, + nch, ...
 // (loads batched 8 deep); the nch chunk sums land in scratch[chunk * cols + col].  Needs cols <= blockDim.x.
 constexpr int kFanIn = 16;         // sizing unit of the legacy per-layer scratch records (workspace layout only)
-constexpr int kRecB = 8;
+constexpr int kRecB = 16;
 __device__ __forceinline__ int records_sum(const float* part, int gc, int cols, float* scratch) {
   const int nch = imax(1, (int)blockDim.x / cols);
   const int i = threadIdx.x;

@@ -96,11 +96,35 @@ __device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) {
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
   return v;
 }
+// the same offset in all 8 CTAs of a cluster, summed in rank order: one asm block so the 8 loads are in flight together
+__device__ __forceinline__ float sum_dsmem8(const float* local) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  float v0, v1, v2, v3, v4, v5, v6, v7;
+  asm volatile(
+      "{\n\t.reg .u32 a0, a1, a2, a3, a4, a5, a6, a7;\n\t"
+      "mapa.shared::cluster.u32 a0, %8, 0;\n\tmapa.shared::cluster.u32 a1, %8, 1;\n\t"
+      "mapa.shared::cluster.u32 a2, %8, 2;\n\tmapa.shared::cluster.u32 a3, %8, 3;\n\t"
+      "mapa.shared::cluster.u32 a4, %8, 4;\n\tmapa.shared::cluster.u32 a5, %8, 5;\n\t"
+      "mapa.shared::cluster.u32 a6, %8, 6;\n\tmapa.shared::cluster.u32 a7, %8, 7;\n\t"
+      "ld.shared::cluster.f32 %0, [a0];\n\tld.shared::cluster.f32 %1, [a1];\n\t"
+      "ld.shared::cluster.f32 %2, [a2];\n\tld.shared::cluster.f32 %3, [a3];\n\t"
+      "ld.shared::cluster.f32 %4, [a4];\n\tld.shared::cluster.f32 %5, [a5];\n\t"
+      "ld.shared::cluster.f32 %6, [a6];\n\tld.shared::cluster.f32 %7, [a7];\n\t}"
+      : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3), "=f"(v4), "=f"(v5), "=f"(v6), "=f"(v7)
+      : "r"(la)
+      : "memory");
+  return ((((((v0 + v1) + v2) + v3) + v4) + v5) + v6) + v7;
+}
 #else
 __device__ __forceinline__ unsigned cluster_ctarank() { return emu::cluster_rank(); }
 __device__ __forceinline__ unsigned cluster_nctarank() { return emu::cluster_size(); }
 __device__ __forceinline__ void cluster_sync_all() { emu::cluster_sync(); }
 __device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) { return *reinterpret_cast<const float*>(emu::dsmem(local, rank)); }
+__device__ __forceinline__ float sum_dsmem8(const float* local) {
+  float s = 0.f;
+  for (unsigned q = 0; q < 8; ++q) s += ld_dsmem(local, q);
+  return s;
+}
 #endif
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
