@@ -146,13 +146,27 @@ static int build_frontend_tables(tcr_handle* h) {
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < F; ++k)
       dct[(size_t)m * F + k] = (float)(2.0 * cos(M_PI * k * (2.0 * m + 1.0) / (2.0 * M)) / sqrt(2.0 * M));
-  TCR_TRY(dev_upload(h, &h->d_window, win));
-  TCR_TRY(dev_upload(h, &h->d_tw, tw));
-  TCR_TRY(dev_upload(h, &h->d_tw2, tw2));
+  // constant block of the front-end kernel (tcr_mfcc.h): tw | tw2 | mel weights | window, sections padded to 16 bytes
+  {
+    std::vector<float> blk;
+    auto pad4 = [&]() { while (blk.size() % 4) blk.push_back(0.f); };
+    for (auto& v : tw) { blk.push_back(v.x); blk.push_back(v.y); }
+    pad4();
+    h->c_tw2 = (int)blk.size();
+    for (auto& v : tw2) { blk.push_back(v.x); blk.push_back(v.y); }
+    pad4();
+    h->c_melw = (int)blk.size();
+    blk.insert(blk.end(), wts.begin(), wts.end());
+    pad4();
+    h->c_win = (int)blk.size();
+    blk.insert(blk.end(), win.begin(), win.end());
+    pad4();
+    h->c_total = (int)blk.size();
+    TCR_TRY(dev_upload(h, &h->d_fe_consts, blk));
+  }
   TCR_TRY(dev_upload(h, &h->d_mel_start, start));
   TCR_TRY(dev_upload(h, &h->d_mel_len, len));
   TCR_TRY(dev_upload(h, &h->d_mel_off, off));
-  TCR_TRY(dev_upload(h, &h->d_mel_w, wts));
   TCR_TRY(dev_upload(h, &h->d_dct, dct));
   return TCR_OK;
 }
@@ -171,13 +185,11 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.fpb = h->fpb;
   a.magnitude = h->cfg.feature_kind == TCR_FEATURE_LOG_MEL;
   a.use_dct = h->cfg.feature_kind == TCR_FEATURE_MFCC;
-  a.window_tab = h->d_window;
-  a.tw = h->d_tw;
-  a.tw2 = h->d_tw2;
+  a.consts = h->d_fe_consts;
+  a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_total = h->c_total;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;
-  a.mel_w = h->d_mel_w;
   a.dct = h->d_dct;
   return a;
 }

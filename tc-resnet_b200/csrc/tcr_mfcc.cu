@@ -169,11 +169,16 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* s_wav = smem + 16;
   const int span_max = (a.fpb - 1) * a.stride + a.window;
-  float2* s_tw = reinterpret_cast<float2*>(s_wav + (size_t)span_max * 4);
+  // constant block (one TMA bulk copy): FFT twiddles | real-FFT twiddles | packed mel weights | window
+  float* s_const = reinterpret_cast<float*>(s_wav + (size_t)span_max * 4);
+  const float2* s_tw = reinterpret_cast<const float2*>(s_const);
+  const float2* s_tw2 = reinterpret_cast<const float2*>(s_const + a.c_tw2);
+  const float* s_melw = s_const + a.c_melw;
+  const float2* s_win = reinterpret_cast<const float2*>(s_const + a.c_win);
   const int z_elems = NF2 + (NF2 >> 4);
   const int pw_elems = ((NF2 + 1 + 3) / 4) * 4;
   const int per_warp_floats = 2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3);
-  float* s_warp = reinterpret_cast<float*>(s_tw + NF2) + (size_t)warp * per_warp_floats;
+  float* s_warp = s_const + a.c_total + (size_t)warp * per_warp_floats;
   float2* z = reinterpret_cast<float2*>(s_warp);
   float* pw = s_warp + 2 * z_elems;
   float* lm = pw + pw_elems;
@@ -183,17 +188,17 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)span * SB);
+    mbar_expect_tx(bar, (uint32_t)span * SB + (uint32_t)a.c_total * 4u);
     tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB,
                 (uint32_t)span * SB, bar);
+    tma_load_1d(s_const, a.consts, (uint32_t)a.c_total * 4u, bar);
   }
-  for (int i = threadIdx.x; i < NF2; i += blockDim.x) s_tw[i] = __ldg(&a.tw[i]);   // overlaps the bulk copy
   mbar_wait(bar, 0);
   __syncthreads();
 
   const int half_w = a.window >> 1;
   for (int f = warp; f < nf; f += nwarps) {
-    fft_warp<NF2, PCM>(s_wav + (size_t)f * a.stride * SB, reinterpret_cast<const float2*>(a.window_tab), half_w, z, s_tw, lane);
+    fft_warp<NF2, PCM>(s_wav + (size_t)f * a.stride * SB, s_win, half_w, z, s_tw, lane);
     // real-FFT post-processing, bins k and NF2-k from the same pair (Z[k], Z[NF2-k]):
     //   E = (Z[k] + conj Z[NF2-k]) / 2, O = (Z[k] - conj Z[NF2-k]) / 2, T = e^{-2 pi i k / fft} O
     //   X[k] = E - i T,  X[NF2-k] = conj(E) - i conj(T) ... written out below in components
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
       const float2 zr = z[zi((NF2 - k) & (NF2 - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
       const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y + zr.y));
-      const float2 t = cmul(__ldg(&a.tw2[k]), o);
+      const float2 t = cmul(s_tw2[k], o);
       const float ar = e.x + t.y, ai = e.y - t.x;          // X[k]
       const float br = e.x - t.y, bi = e.y + t.x;          // X[NF2-k] (imaginary part negated: only |.|^2 is used)
       const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
@@ -219,9 +224,16 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
         const int m = h ? a.mel_bins - 1 - i : i;
         if (h && m == i) break;
         const int start = __ldg(&a.mel_start[m]), len = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
-        float acc = 0.f;
-        for (int q = 0; q < len; ++q) acc = fmaf(pw[start + q], __ldg(&a.mel_w[off + q]), acc);
-        lm[m] = logf(acc + 1e-6f);
+        const float* pp = pw + start;
+        const float* ww = s_melw + off;
+        float a0 = 0.f, a1 = 0.f;                         // two chains: the band loop is latency-, not throughput-bound
+        int q = 0;
+        for (; q + 1 < len; q += 2) {
+          a0 = fmaf(pp[q], ww[q], a0);
+          a1 = fmaf(pp[q + 1], ww[q + 1], a1);
+        }
+        if (q < len) a0 = fmaf(pp[q], ww[q], a0);
+        lm[m] = logf((a0 + a1) + 1e-6f);
       }
     }
     __syncwarp();
@@ -234,10 +246,21 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       const int nj = (a.features + 7) >> 3;
-#pragma unroll 2
-      for (int m = q; m < a.mel_bins; m += 4) {
-        const float v = lm[m];
+      // DCT-II rows are mirror images: D[M-1-m][c] = (-1)^c D[m][c], and c = g + 8 j has the parity of g, so a lane folds
+      // the two halves of the log-mel vector first and walks only M/2 rows (odd M: the middle row is added unfolded).
+      const int M = a.mel_bins, half = M >> 1;
+      const float sgn = (g & 1) ? -1.f : 1.f;
+#pragma unroll 4
+      for (int m = q; m < half; m += 4) {
+        const float v = fmaf(sgn, lm[M - 1 - m], lm[m]);
         const float* row = a.dct + m * a.features + g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nj && g + 8 * j < a.features) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
+      }
+      if ((M & 1) && q == 0) {
+        const float v = lm[half];
+        const float* row = a.dct + half * a.features + g;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < nj && g + 8 * j < a.features) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
@@ -262,7 +285,7 @@ size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps) {
   const int z_elems = nf2 + (nf2 >> 4);
   const int pw_elems = ((nf2 + 1 + 3) / 4) * 4;
   const size_t per_warp = (size_t)(2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3)) * 4;
-  return 16 + (size_t)span_max * 4 + (size_t)nf2 * 8 + per_warp * warps;
+  return 16 + (size_t)span_max * 4 + (size_t)a.c_total * 4 + per_warp * warps;
 }
 
 int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {

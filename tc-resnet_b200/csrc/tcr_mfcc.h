@@ -12,13 +12,13 @@ struct MfccArgs {
   int fpb;                  // frames per CTA (== warps per CTA)
   int magnitude;            // 0: power spectrogram (MFCC path), 1: magnitude (log-mel path)
   int use_dct;              // 1: MFCC, 0: log-mel output
-  const float* window_tab;  // [window] periodic Hann
-  const float2* tw;         // [fft/2]   exp(-2 pi i n / (fft/2))
-  const float2* tw2;        // [fft/2+1] exp(-2 pi i k / fft)
+  // constant block, staged in shared memory by one TMA bulk copy (offsets in floats, each section 16-byte aligned):
+  //   [0, 2*fft/2)  tw  exp(-2 pi i n / (fft/2)) | c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_melw: packed mel weights |
+  //   c_win: periodic Hann window [window]
+  const float* consts; int c_tw2, c_melw, c_win, c_total;
   const int* mel_start;     // [mel_bins] first FFT bin with non-zero weight
   const int* mel_len;       // [mel_bins]
   const int* mel_off;       // [mel_bins] offset into mel_w
-  const float* mel_w;       // packed non-zero weights
   const float* dct;         // [mel_bins, features]
 };
 

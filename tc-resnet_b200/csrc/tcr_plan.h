@@ -54,9 +54,9 @@ struct tcr_handle {
   int g_max = 0;                 // max CTA groups of any producer kernel (partials are sized for it)
   int head_groups_max = 0;
   // front-end tables
-  float* d_window = nullptr; float2* d_tw = nullptr; float2* d_tw2 = nullptr;
+  float* d_fe_consts = nullptr; int c_tw2 = 0, c_melw = 0, c_win = 0, c_total = 0;   // front-end constant block (tcr_mfcc.h)
   int* d_mel_start = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr;
-  float* d_mel_w = nullptr; float* d_dct = nullptr;
+  float* d_dct = nullptr;
   // workspace
   float* d_feat = nullptr;
   float* d_logits = nullptr; float* d_probs = nullptr;
