@@ -103,7 +103,7 @@ __device__ __forceinline__ float2 frame_sample(const void* x, const float2* __re
   } else {
     xs = ld2(reinterpret_cast<const float*>(x) + 2 * n);
   }
-  const float2 ws = __ldg(wtab + n);
+  const float2 ws = wtab[n];                          // window table: shared memory (constant block)
   return make_float2(xs.x * ws.x, xs.y * ws.y);
 }
 template <int R, int MAXQ, bool PCM>
