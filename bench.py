@@ -356,10 +356,14 @@ def run_ours(a):
             assert len(seen) == esteps, (len(seen), esteps)
             return n * world * esteps / float(el.item()), seen[-1]
 
-        e2e_value, last = e2e_run(h_wavs)
+        def median3(host_bufs):                         # PCIe / host interference on a shared box: median of 3 runs of esteps
+            runs = sorted((e2e_run(host_bufs) for _ in range(3)), key=lambda r: r[0])
+            return runs[1]
+
+        e2e_value, last = median3(h_wavs)
         # the same clips as the wav files store them (int16 PCM); decode_wav's 1/32768 scaling runs on the device
         h_pcm = [(w.clamp(-1, 1) * 32767.0).round().to(torch.int16).cpu().pin_memory() for w in wavs[:min(rot, 4)]]
-        pcm_value, _ = e2e_run(h_pcm)
+        pcm_value, _ = median3(h_pcm)
         h2d = int(h_wavs[0].numel() * 4 + h_hots[0].numel() * 4)
         # serial H2D bandwidth of the same buffers, for context
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,7 +373,7 @@ def run_ours(a):
         c1.record()
         torch.cuda.synchronize()
         out["e2e"] = {"value": e2e_value, "unit": "utterances/sec",
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "steps": esteps,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "steps": esteps, "runs": "median of 3 runs of `steps` steps",
                       "h2d_GBps_measured": 10 * h_wavs[0].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9,
                       "last_total_loss": last[1] if last else None,
                       "pcm16": {"value": pcm_value, "unit": "utterances/sec", "h2d_bytes_per_step": int(h_pcm[0].numel() * 2 + h_hots[0].numel() * 4),

@@ -62,3 +62,28 @@ for lag in (0, 1, 2):
     feed_loop(f32, lag, tag="f32  ")
 for lag in (0, 1, 2):
     feed_loop(pcm, lag, tag="pcm16")
+
+# pure host cost of one submit: the pipeline is empty, so nothing blocks on the GPU
+feed = HostFeed(eng, lag=2)
+costs = []
+for rep in range(30):
+    feed.flush(); torch.cuda.synchronize()
+    a = time.perf_counter()
+    feed.submit(pcm[0], hot[0], params, slots, moving, 0.1, 0.9, 1e-3, dropout_seed=rep)
+    b = time.perf_counter()
+    feed.submit(pcm[1], hot[1], params, slots, moving, 0.1, 0.9, 1e-3, dropout_seed=rep)
+    c = time.perf_counter()
+    costs.append((b - a, c - b))
+feed.flush()
+costs.sort()
+print(f"non-blocking submit (host only): first median {1e3*sorted(x[0] for x in costs)[15]:.3f} ms, second median {1e3*sorted(x[1] for x in costs)[15]:.3f} ms")
+t = []
+for rep in range(30):
+    torch.cuda.synchronize()
+    a = time.perf_counter()
+    eng.train_step(d_w[0], d_h[0], params, slots, moving, 0.1, 0.9, 1e-3, dropout_seed=rep, losses=losses)
+    t.append(time.perf_counter() - a)
+t.sort()
+print(f"non-blocking device train_step (host only): median {1e3*t[15]:.3f} ms  min {1e3*t[0]:.3f}")
+import os
+print("cpus", os.cpu_count(), "loadavg", os.getloadavg())
