@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "utterances/sec (fwd+bwd+update) TCResNet8-1.0"
+METRIC = "utterances/sec (fwd+bwd+update) TCResNet8-1.0"     # BASELINE.json's metric; other models are named in config.workload
 SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -263,7 +263,8 @@ def run_ours(a):
     final_loss = float(losses[0].item())
     value = n * world * a.steps / (ms * 1e-3)
 
-    out = {"metric": METRIC, "value": value, "unit": "utterances/sec", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    metric = METRIC if (a.model == "TCResNet8" and a.width == 1.0) else f"utterances/sec (fwd+bwd+update) {a.model}-{a.width}"
+    out = {"metric": metric, "value": value, "unit": "utterances/sec", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "ours",
            "config": {"workload": workload_name(a), "global_batch": n * world, "parallelism": f"dp{world}",
