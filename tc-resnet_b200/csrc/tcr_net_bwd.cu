@@ -456,16 +456,19 @@ static size_t bwd_data_smem(const ConvPlan& cv, const ConvPlan* dn, int U, int K
   return f * 4;
 }
 
+double tile_cost(int n, int U, int occ, bool wsm);     // tcr_net_fwd.cu
+
 static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
   const size_t wbytes = ((size_t)cv.wnumel() + (dn ? (size_t)dn->wnumel() : 0)) * 4;
-  int U = std::max(1, (n + 295) / 296);
-  U = std::min(U, 16);
   const int S = cv.stride, NT0 = (cv.k + S - 1) / S;
-  for (;; --U) {
-    for (int pass = 0; pass < 3; ++pass) {
-      const bool wsm = pass < 2;
-      const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
-      if (wsm && wbytes + 16 * 1024 > budget) continue;
+  double best = 1e30;
+  *U_out = 1; *KS_out = 1; *wsm_out = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const bool wsm = pass < 2;
+    const int occ = pass == 0 ? 2 : 1;
+    const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+    if (wsm && wbytes + 16 * 1024 > budget) continue;
+    for (int U = std::min(16, std::max(1, (n + 148 * occ - 1) / (148 * occ))); U >= 1; --U) {
       int best_ks = 0;
       double best_cost = 1e30;
       for (int KS = 1; KS <= NT0; ++KS) {
@@ -479,12 +482,11 @@ static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_
           best_ks = KS;
         }
       }
-      if (best_ks) {
-        *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0;
-        return;
-      }
+      if (!best_ks) continue;
+      const double c = tile_cost(n, U, occ, wsm);
+      if (c < best - 1e-9) { best = c; *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0; }
+      break;
     }
-    if (U == 1) { *U_out = 1; *KS_out = 1; *wsm_out = 0; return; }
   }
 }
 
@@ -504,7 +506,11 @@ void plan_bwd_weight(tcr_handle* h) {
   // Measured (tools/timeline.py): tiny output-channel tiles re-stage the same x tile many times and need a huge cross-group
   // reduction; long chunks of K=1 layers run for 150 us on a handful of CTAs.  So: the LARGEST tile that fits 256 threads, at
   // most 4 row groups, and chunks bounded both in MACs and in utterances so that no CTA runs much longer than the others.
-  const double target_macs = 0.5e6;
+  double target_macs = 2e6;          // swept on B200 (tools/sweep_dw.sh): 0.5e6/8 -> 64 us, 2e6/16 -> 58 us and 4x fewer partials to sum
+  int upc_cap = 16, r_cap = 128;
+  if (const char* e = getenv("TCR_DW_MACS")) target_macs = atof(e);        // tuning knobs (tools/sweep_dw.sh)
+  if (const char* e = getenv("TCR_DW_UPC")) upc_cap = atoi(e);
+  if (const char* e = getenv("TCR_DW_RCAP")) r_cap = atoi(e);
   for (auto& cv : h->convs) {
     int cot = 4;
     for (int c = 4; c <= cv.cout; c += 4)
@@ -512,9 +518,9 @@ void plan_bwd_weight(tcr_handle* h) {
     const int np = (cv.cin / 2) * (cot / 4);
     int RG = std::max(1, std::min(4, kDwThreads / np));
     const double macs_per_utt = (double)cv.t_out * cv.k * cv.cin * cot;
-    int upc = std::max(1, std::min(8, (int)(target_macs / macs_per_utt)));     // utterances per chunk
+    int upc = std::max(1, std::min(upc_cap, (int)(target_macs / macs_per_utt)));     // utterances per chunk
     int R = std::max(1, (h->cfg.max_batch + upc - 1) / upc);
-    R = std::min(R, 128);
+    R = std::min(R, r_cap);
     int UB = 8;
     while (UB > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudgetW) --UB;
     while (RG > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudget) --RG;

@@ -469,16 +469,27 @@ static size_t fwd_smem_bytes(const ConvPlan& cv, const ConvPlan* dn, int U, int 
 // Goals: >= 2 resident CTAs per SM when the batch allows (latency hiding), all 148 SMs busy, balanced thread tasks.
 static constexpr size_t kSmemMax = 200 * 1024;      // opt-in limit we are willing to use for one CTA
 
+// Candidate tilings are compared by a small cost model: waves x (U x (co-residency slowdown) + fixed part), where a wave is one
+// round of CTAs over the 148 SMs at the residency the shared-memory footprint allows.  (Measured on TCResNet14-1.5, N=1024: a tile
+// that fits only one CTA per SM must cover the batch in ONE wave of <= 148 CTAs; two waves of 128 cost 2x the fixed part.)
+static constexpr int kSMs = 148;
+double tile_cost(int n, int U, int occ, bool wsm) {
+  const int groups = (n + U - 1) / U;
+  const int waves = (groups + kSMs * occ - 1) / (kSMs * occ);
+  return waves * (U * (occ == 2 ? 1.7 : 1.0) * (wsm ? 1.0 : 2.5) + 1.5);
+}
+
 static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
   const size_t wbytes = fwd_weight_floats(cv, dn) * 4;
-  int U = std::max(1, (n + 295) / 296);             // two CTAs per SM worth of groups
-  U = std::min(U, 16);
-  for (;; --U) {
-    for (int pass = 0; pass < 3; ++pass) {
-      // pass 0: weights in smem, two CTAs per SM; pass 1: weights in smem, one CTA per SM; pass 2: weights via L1/L2
-      const bool wsm = pass < 2;
-      const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
-      if (wsm && wbytes + 16 * 1024 > budget) continue;
+  double best = 1e30;
+  *U_out = 1; *KS_out = 1; *wsm_out = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    // pass 0: weights in smem, two CTAs per SM; pass 1: weights in smem, one CTA per SM; pass 2: weights via L1/L2
+    const bool wsm = pass < 2;
+    const int occ = pass == 0 ? 2 : 1;
+    const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+    if (wsm && wbytes + 16 * 1024 > budget) continue;
+    for (int U = std::min(16, std::max(1, (n + kSMs * occ - 1) / (kSMs * occ))); U >= 1; --U) {
       int best_ks = 0;
       double best_cost = 1e30;
       for (int KS = 1; KS <= cv.k; ++KS) {
@@ -491,12 +502,11 @@ static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_
           best_ks = KS;
         }
       }
-      if (best_ks) {
-        *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0;
-        return;
-      }
+      if (!best_ks) continue;
+      const double c = tile_cost(n, U, occ, wsm);
+      if (c < best - 1e-9) { best = c; *U_out = U; *KS_out = best_ks; *wsm_out = wsm ? 1 : 0; }
+      break;                        // the largest U that fits is the candidate of this pass
     }
-    if (U == 1) { *U_out = 1; *KS_out = 1; *wsm_out = 0; return; }
   }
 }
 
