@@ -463,10 +463,10 @@ static void pick_bwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_
   const int S = cv.stride, NT0 = (cv.k + S - 1) / S;
   double best = 1e30;
   *U_out = 1; *KS_out = 1; *wsm_out = 0;
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int pass = 0; pass < 4; ++pass) {
     const bool wsm = pass < 2;
-    const int occ = pass == 0 ? 2 : 1;
-    const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+    const int occ = (pass & 1) ? 1 : 2;
+    const size_t budget = occ == 2 ? kSmemBudget : kSmemMax;
     if (wsm && wbytes + 16 * 1024 > budget) continue;
     for (int U = std::min(16, std::max(1, (n + 148 * occ - 1) / (148 * occ))); U >= 1; --U) {
       int best_ks = 0;

@@ -476,18 +476,20 @@ static constexpr int kSMs = 148;
 double tile_cost(int n, int U, int occ, bool wsm) {
   const int groups = (n + U - 1) / U;
   const int waves = (groups + kSMs * occ - 1) / (kSMs * occ);
-  return waves * (U * (occ == 2 ? 1.7 : 1.0) * (wsm ? 1.0 : 2.5) + 1.5);
+  // unit = FMA time of one utterance at one CTA per SM; the per-wave fixed part (launch, filter TMA, staging latency, statistics,
+  // cluster publish) measured at ~4 such units
+  return waves * (U * (occ == 2 ? 1.7 : 1.0) * (wsm ? 1.0 : 2.5) + 4.0);
 }
 
 static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
   const size_t wbytes = fwd_weight_floats(cv, dn) * 4;
   double best = 1e30;
   *U_out = 1; *KS_out = 1; *wsm_out = 0;
-  for (int pass = 0; pass < 3; ++pass) {
-    // pass 0: weights in smem, two CTAs per SM; pass 1: weights in smem, one CTA per SM; pass 2: weights via L1/L2
+  for (int pass = 0; pass < 4; ++pass) {
+    // passes 0/1: filter bank in shared memory, two / one CTA per SM; passes 2/3: filters through L1/L2 (bank too large)
     const bool wsm = pass < 2;
-    const int occ = pass == 0 ? 2 : 1;
-    const size_t budget = pass == 0 ? kSmemBudget : kSmemMax;
+    const int occ = (pass & 1) ? 1 : 2;
+    const size_t budget = occ == 2 ? kSmemBudget : kSmemMax;
     if (wsm && wbytes + 16 * 1024 > budget) continue;
     for (int U = std::min(16, std::max(1, (n + kSMs * occ - 1) / (kSMs * occ))); U >= 1; --U) {
       int best_ks = 0;
