@@ -146,22 +146,22 @@ static int build_frontend_tables(tcr_handle* h) {
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < F; ++k)
       dct[(size_t)m * F + k] = (float)(2.0 * cos(M_PI * k * (2.0 * m + 1.0) / (2.0 * M)) / sqrt(2.0 * M));
-  // constant block of the front-end kernel (tcr_mfcc.h): tw | tw2 | mel weights | window, sections padded to 16 bytes
+  // constant block of the front-end kernel (tcr_mfcc.h): tw | mel weights | tw2 | window, sections padded to 16 bytes
   {
     std::vector<float> blk;
     auto pad4 = [&]() { while (blk.size() % 4) blk.push_back(0.f); };
     for (auto& v : tw) { blk.push_back(v.x); blk.push_back(v.y); }
     pad4();
-    h->c_tw2 = (int)blk.size();
-    for (auto& v : tw2) { blk.push_back(v.x); blk.push_back(v.y); }
-    pad4();
     h->c_melw = (int)blk.size();
     blk.insert(blk.end(), wts.begin(), wts.end());
+    pad4();
+    h->c_smem = (int)blk.size();                   // everything above is staged in shared memory
+    h->c_tw2 = (int)blk.size();
+    for (auto& v : tw2) { blk.push_back(v.x); blk.push_back(v.y); }
     pad4();
     h->c_win = (int)blk.size();
     blk.insert(blk.end(), win.begin(), win.end());
     pad4();
-    h->c_total = (int)blk.size();
     TCR_TRY(dev_upload(h, &h->d_fe_consts, blk));
   }
   TCR_TRY(dev_upload(h, &h->d_mel_start, start));
@@ -186,7 +186,7 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.magnitude = h->cfg.feature_kind == TCR_FEATURE_LOG_MEL;
   a.use_dct = h->cfg.feature_kind == TCR_FEATURE_MFCC;
   a.consts = h->d_fe_consts;
-  a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_total = h->c_total;
+  a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_smem = h->c_smem;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;

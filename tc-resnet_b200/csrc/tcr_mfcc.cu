@@ -103,7 +103,7 @@ __device__ __forceinline__ float2 frame_sample(const void* x, const float2* __re
   } else {
     xs = ld2(reinterpret_cast<const float*>(x) + 2 * n);
   }
-  const float2 ws = wtab[n];                          // window table: shared memory (constant block)
+  const float2 ws = __ldg(wtab + n);
   return make_float2(xs.x * ws.x, xs.y * ws.y);
 }
 template <int R, int MAXQ, bool PCM>
@@ -155,8 +155,11 @@ __device__ __forceinline__ void fft_warp(const void* x, const float2* __restrict
 //   wav   : span floats             (TMA destination, 16-byte aligned)
 //   tw    : NF2 float2              FFT twiddles exp(-2 pi i n / NF2)
 //   per warp: z   (NF2 + NF2/16) float2, pw (NF2 + 1 [+pad]) floats, lm (mel_bins) floats
+// ALIAS (fft <= 1024): the power spectrum overwrites the FFT buffer (the bins are staged in registers first), which brings
+// the CTA to ~50 KB of shared memory and four CTAs (28 warps) per SM instead of three.
 template <int NF2, bool PCM>
-__global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
+__global__ void __launch_bounds__(224, (NF2 <= 512) ? 4 : 2) mfcc_kernel(MfccArgs a) {
+  constexpr bool ALIAS = NF2 <= 512;
   TCR_DYNAMIC_SMEM(smem);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -169,51 +172,80 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* s_wav = smem + 16;
   const int span_max = (a.fpb - 1) * a.stride + a.window;
-  // constant block (one TMA bulk copy): FFT twiddles | real-FFT twiddles | packed mel weights | window
+  // constant block: FFT twiddles | packed mel weights staged in shared memory by one TMA bulk copy; real-FFT twiddles and the
+  // window (touched once per frame) stay in global memory / L1
   float* s_const = reinterpret_cast<float*>(s_wav + (size_t)span_max * 4);
   const float2* s_tw = reinterpret_cast<const float2*>(s_const);
-  const float2* s_tw2 = reinterpret_cast<const float2*>(s_const + a.c_tw2);
   const float* s_melw = s_const + a.c_melw;
-  const float2* s_win = reinterpret_cast<const float2*>(s_const + a.c_win);
+  const float2* g_tw2 = reinterpret_cast<const float2*>(a.consts + a.c_tw2);
+  const float2* g_win = reinterpret_cast<const float2*>(a.consts + a.c_win);
   const int z_elems = NF2 + (NF2 >> 4);
-  const int pw_elems = ((NF2 + 1 + 3) / 4) * 4;
+  const int pw_elems = ALIAS ? 0 : ((NF2 + 1 + 3) / 4) * 4;
   const int per_warp_floats = 2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3);
-  float* s_warp = s_const + a.c_total + (size_t)warp * per_warp_floats;
+  float* s_warp = s_const + a.c_smem + (size_t)warp * per_warp_floats;
   float2* z = reinterpret_cast<float2*>(s_warp);
-  float* pw = s_warp + 2 * z_elems;
-  float* lm = pw + pw_elems;
+  float* pw = ALIAS ? s_warp : s_warp + 2 * z_elems;
+  float* lm = s_warp + 2 * z_elems + pw_elems;
 
   const int span = (nf - 1) * a.stride + a.window;   // samples actually needed (span * SB is a multiple of 16)
   if (threadIdx.x == 0) mbar_init(bar, 1);
   pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)span * SB + (uint32_t)a.c_total * 4u);
+    mbar_expect_tx(bar, (uint32_t)span * SB + (uint32_t)a.c_smem * 4u);
     tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB,
                 (uint32_t)span * SB, bar);
-    tma_load_1d(s_const, a.consts, (uint32_t)a.c_total * 4u, bar);
+    tma_load_1d(s_const, a.consts, (uint32_t)a.c_smem * 4u, bar);
   }
   mbar_wait(bar, 0);
   __syncthreads();
 
   const int half_w = a.window >> 1;
   for (int f = warp; f < nf; f += nwarps) {
-    fft_warp<NF2, PCM>(s_wav + (size_t)f * a.stride * SB, s_win, half_w, z, s_tw, lane);
+    fft_warp<NF2, PCM>(s_wav + (size_t)f * a.stride * SB, g_win, half_w, z, s_tw, lane);
     // real-FFT post-processing, bins k and NF2-k from the same pair (Z[k], Z[NF2-k]):
     //   E = (Z[k] + conj Z[NF2-k]) / 2, O = (Z[k] - conj Z[NF2-k]) / 2, T = e^{-2 pi i k / fft} O
     //   X[k] = E - i T,  X[NF2-k] = conj(E) - i conj(T) ... written out below in components
+    constexpr int NIT = NF2 / 64 + 1;                       // k = lane + 32 it <= NF2 / 2
+    if (ALIAS) {
+      float2 zk[NIT], zr[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int k = lane + 32 * it;
+        if (k <= NF2 / 2) {
+          zk[it] = z[zi(k)];
+          zr[it] = z[zi((NF2 - k) & (NF2 - 1))];
+        }
+      }
+      __syncwarp();                                         // every bin is in registers: the buffer may be overwritten
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int k = lane + 32 * it;
+        if (k <= NF2 / 2) {
+          const float2 e = make_float2(0.5f * (zk[it].x + zr[it].x), 0.5f * (zk[it].y - zr[it].y));
+          const float2 o = make_float2(0.5f * (zk[it].x - zr[it].x), 0.5f * (zk[it].y + zr[it].y));
+          const float2 t = cmul(__ldg(&g_tw2[k]), o);
+          const float ar = e.x + t.y, ai = e.y - t.x;
+          const float br = e.x - t.y, bi = e.y + t.x;
+          const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+          pw[k] = a.magnitude ? sqrtf(pa) : pa;
+          pw[NF2 - k] = a.magnitude ? sqrtf(pb) : pb;
+        }
+      }
+    } else {
 #pragma unroll 1
-    for (int k = lane; k <= NF2 / 2; k += 32) {
-      const float2 zk = z[zi(k)];
-      const float2 zr = z[zi((NF2 - k) & (NF2 - 1))];
-      const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
-      const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y + zr.y));
-      const float2 t = cmul(s_tw2[k], o);
-      const float ar = e.x + t.y, ai = e.y - t.x;          // X[k]
-      const float br = e.x - t.y, bi = e.y + t.x;          // X[NF2-k] (imaginary part negated: only |.|^2 is used)
-      const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
-      pw[k] = a.magnitude ? sqrtf(pa) : pa;
-      pw[NF2 - k] = a.magnitude ? sqrtf(pb) : pb;
+      for (int k = lane; k <= NF2 / 2; k += 32) {
+        const float2 zk = z[zi(k)];
+        const float2 zr = z[zi((NF2 - k) & (NF2 - 1))];
+        const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
+        const float2 o = make_float2(0.5f * (zk.x - zr.x), 0.5f * (zk.y + zr.y));
+        const float2 t = cmul(__ldg(&g_tw2[k]), o);
+        const float ar = e.x + t.y, ai = e.y - t.x;          // X[k]
+        const float br = e.x - t.y, bi = e.y + t.x;          // X[NF2-k] (imaginary part negated: only |.|^2 is used)
+        const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+        pw[k] = a.magnitude ? sqrtf(pa) : pa;
+        pw[NF2 - k] = a.magnitude ? sqrtf(pb) : pb;
+      }
     }
     __syncwarp();
     // banded mel + log; a lane takes bins i and mel_bins-1-i so short and long bands pair up
@@ -283,9 +315,9 @@ __global__ void __launch_bounds__(256, 3) mfcc_kernel(MfccArgs a) {
 size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps) {
   const int span_max = (a.fpb - 1) * a.stride + a.window;
   const int z_elems = nf2 + (nf2 >> 4);
-  const int pw_elems = ((nf2 + 1 + 3) / 4) * 4;
+  const int pw_elems = nf2 <= 512 ? 0 : ((nf2 + 1 + 3) / 4) * 4;      // fft <= 1024: the power spectrum aliases the FFT buffer
   const size_t per_warp = (size_t)(2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3)) * 4;
-  return 16 + (size_t)span_max * 4 + (size_t)a.c_total * 4 + per_warp * warps;
+  return 16 + (size_t)span_max * 4 + (size_t)a.c_smem * 4 + per_warp * warps;
 }
 
 int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {

@@ -12,10 +12,10 @@ struct MfccArgs {
   int fpb;                  // frames per CTA (== warps per CTA)
   int magnitude;            // 0: power spectrogram (MFCC path), 1: magnitude (log-mel path)
   int use_dct;              // 1: MFCC, 0: log-mel output
-  // constant block, staged in shared memory by one TMA bulk copy (offsets in floats, each section 16-byte aligned):
-  //   [0, 2*fft/2)  tw  exp(-2 pi i n / (fft/2)) | c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_melw: packed mel weights |
-  //   c_win: periodic Hann window [window]
-  const float* consts; int c_tw2, c_melw, c_win, c_total;
+  // constant block (offsets in floats, each section 16-byte aligned); the first c_smem floats are staged in shared memory by
+  // one TMA bulk copy:  [0, 2*fft/2) tw exp(-2 pi i n / (fft/2)) | c_melw: packed mel weights | (c_smem) |
+  //   c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_win: periodic Hann window [window]
+  const float* consts; int c_tw2, c_melw, c_win, c_smem;
   const int* mel_start;     // [mel_bins] first FFT bin with non-zero weight
   const int* mel_len;       // [mel_bins]
   const int* mel_off;       // [mel_bins] offset into mel_w

@@ -71,6 +71,7 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
     st4(xs + ((size_t)(u * TP + row) * CS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
   }
   pdl_wait();                       // everything above is independent of the producer kernel (filters: caller-owned params)
+  tl_stamp(a.tl, vb, 7);
   // BN tables of the layers this tile reads, summed from the producers' per-cluster records (tcr_bn.cuh)
   if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
   if (a.in_kind == 2 && a.shortcut.kind == 1) bn_table_build(a.shortcut.st, a.shortcut.bnf, a.cin, tbl_sh, red, vb == 0);
@@ -630,6 +631,7 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
   a.train = training ? 1 : 0;
   a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline + (h->rec ? 12 * 8192 : 0) : nullptr;
+  if (h->d_timeline && !h->rec && cv.name == "block1/conv1_1") a.tl = h->d_timeline + 2048 * 8;   // its producer, rows 2048..
   (void)counter_slot;
   a.eps = h->cfg.bn_epsilon;
   a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.fl2, cv.cout};

@@ -54,7 +54,7 @@ struct tcr_handle {
   int g_max = 0;                 // max CTA groups of any producer kernel (partials are sized for it)
   int head_groups_max = 0;
   // front-end tables
-  float* d_fe_consts = nullptr; int c_tw2 = 0, c_melw = 0, c_win = 0, c_total = 0;   // front-end constant block (tcr_mfcc.h)
+  float* d_fe_consts = nullptr; int c_tw2 = 0, c_melw = 0, c_win = 0, c_smem = 0;   // front-end constant block (tcr_mfcc.h)
   int* d_mel_start = nullptr; int* d_mel_len = nullptr; int* d_mel_off = nullptr;
   float* d_dct = nullptr;
   // workspace
