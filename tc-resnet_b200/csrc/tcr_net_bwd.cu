@@ -503,28 +503,44 @@ static size_t bwd_weight_smem(const ConvPlan& cv, int cot, int RG, int UB) {
 // the tile that keeps most threads busy, chunks of roughly equal work (~0.7 M MAC) so all layers together give a
 // few waves of CTAs.
 void plan_bwd_weight(tcr_handle* h) {
-  // Measured (tools/timeline.py): tiny output-channel tiles re-stage the same x tile many times and need a huge cross-group
-  // reduction; long chunks of K=1 layers run for 150 us on a handful of CTAs.  So: the LARGEST tile that fits 256 threads, at
-  // most 4 row groups, and chunks bounded both in MACs and in utterances so that no CTA runs much longer than the others.
-  double target_macs = 2e6;          // swept on B200 (tools/sweep_dw.sh): 0.5e6/8 -> 64 us, 2e6/16 -> 58 us and 4x fewer partials to sum
-  int upc_cap = 16, r_cap = 128;
-  if (const char* e = getenv("TCR_DW_MACS")) target_macs = atof(e);        // tuning knobs (tools/sweep_dw.sh)
-  if (const char* e = getenv("TCR_DW_UPC")) upc_cap = atoi(e);
-  if (const char* e = getenv("TCR_DW_RCAP")) r_cap = atoi(e);
+  // Per layer: the LARGEST output-channel tile that fits 256 threads (tiny tiles re-stage the same x tile many times) and at
+  // most 4 row groups.  Row chunks: ONE wave of CTAs (148 SMs x 2) with equal predicted duration.  tools/timeline.py on
+  // TCResNet8 (N=512) gives the time of a CTA as ~ utterances x (0.9 + MACs per utterance and tile / 70e3) in us: the K=1
+  // shortcut convs are staging-bound, the others FMA-bound at ~40 % of peak.  With chunks of equal MACs the launch took 51 us
+  // (long conv0 chunks, late second wave); balanced it is bounded by sum(tau_l x tiles_l) x N / 296.
+  struct L { ConvPlan* cv; int cot, ncot; double tau; };
+  std::vector<L> ls;
   for (auto& cv : h->convs) {
     int cot = 4;
     for (int c = 4; c <= cv.cout; c += 4)
       if (cv.cout % c == 0 && (cv.cin / 2) * (c / 4) <= kDwThreads) cot = c;
-    const int np = (cv.cin / 2) * (cot / 4);
+    const double macs = (double)cv.t_out * cv.k * cv.cin * cot;
+    ls.push_back(L{&cv, cot, cv.cout / cot, 0.9 + macs / 70e3});
+  }
+  const int n = h->cfg.max_batch;
+  int slots = 2 * 148, upc_cap = 64;
+  if (const char* e = getenv("TCR_DW_SLOTS")) slots = atoi(e);              // tuning knobs (tools/sweep_dw.sh)
+  if (const char* e = getenv("TCR_DW_UPC")) upc_cap = atoi(e);
+  auto ctas_at = [&](double D) {
+    long c = 0;
+    for (auto& l : ls) {
+      const int upc = std::max(1, std::min(upc_cap, (int)(D / l.tau)));
+      c += (long)l.ncot * ((n + upc - 1) / upc);
+    }
+    return c;
+  };
+  double D = 1.0;
+  while (ctas_at(D) > slots && D < 1e5) D *= 1.05;
+  for (auto& l : ls) {
+    ConvPlan& cv = *l.cv;
+    const int np = (cv.cin / 2) * (l.cot / 4);
     int RG = std::max(1, std::min(4, kDwThreads / np));
-    const double macs_per_utt = (double)cv.t_out * cv.k * cv.cin * cot;
-    int upc = std::max(1, std::min(upc_cap, (int)(target_macs / macs_per_utt)));     // utterances per chunk
-    int R = std::max(1, (h->cfg.max_batch + upc - 1) / upc);
-    R = std::min(R, r_cap);
+    const int upc = std::max(1, std::min(upc_cap, (int)(D / l.tau)));     // utterances per chunk
+    const int R = std::max(1, (n + upc - 1) / upc);
     int UB = 8;
-    while (UB > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudgetW) --UB;
-    while (RG > 1 && bwd_weight_smem(cv, cot, RG, UB) > kSmemBudget) --RG;
-    cv.dw_cot = cot;
+    while (UB > 1 && bwd_weight_smem(cv, l.cot, RG, UB) > kSmemBudgetW) --UB;
+    while (RG > 1 && bwd_weight_smem(cv, l.cot, RG, UB) > kSmemBudget) --RG;
+    cv.dw_cot = l.cot;
     cv.dw_RG = RG;
     cv.dw_R = R;
     cv.dw_UB = UB;
