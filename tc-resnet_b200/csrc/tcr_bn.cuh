@@ -180,7 +180,6 @@ __device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, doubl
 
 // Sum `gc` records of `cols` floats each: thread i < cols * nch takes column i % cols and records i / cols, + nch, ...
 // (loads batched 8 deep); the nch chunk sums land in scratch[chunk * cols + col].  Needs cols <= blockDim.x.
-constexpr int kFanIn = 16;         // sizing unit of the legacy per-layer scratch records (workspace layout only)
 constexpr int kRecB = 16;
 __device__ __forceinline__ int records_sum(const float* part, int gc, int cols, float* scratch) {
   const int nch = imax(1, (int)blockDim.x / cols);

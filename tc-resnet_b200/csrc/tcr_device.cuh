@@ -41,6 +41,21 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 }  // namespace tcr
+// Opt a kernel in to `smem` bytes of dynamic shared memory; the attribute is per device, so is the cache (one per call site).
+struct SmemOptIn {
+  size_t limit[32];
+  SmemOptIn() { for (auto& l : limit) l = 32 * 1024; }   // static smem counts against the 48 KB default
+  template <typename K>
+  cudaError_t ensure(K kernel, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& lim = limit[dev & 31];
+    if (smem <= lim) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) lim = smem;
+    return e;
+  }
+};
 // cluster launch: CTAs of a cluster share partial BatchNorm sums through distributed shared memory
 #define TCR_LAUNCH_CLUSTER(name, kernel, grid, block, smem, stream, cluster, ...)                                   \
   do {                                                                                                              \

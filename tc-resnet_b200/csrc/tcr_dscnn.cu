@@ -361,8 +361,8 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
       const size_t smem = (size_t)(((hp * wp + 3) & ~3) + L.kh * L.kw * L.cout + 2 * L.cout) * 4;
       auto kfn = dscnn_conv_kernel;
 #ifndef TCR_EMU
-      static size_t lim = 32 * 1024;
-      if (smem > lim) { if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA; lim = smem; }
+      static SmemOptIn optin;
+      if (optin.ensure(kfn, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
       TCR_LAUNCH("dscnn_conv", kfn, dim3(n), dim3(256), smem, s, L, params, in, out, eps);
     } else {
@@ -377,8 +377,8 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
       if (smem > 200 * 1024) { set_error("DS-CNN layer does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
       auto kfn = dscnn_dsblock_kernel;
 #ifndef TCR_EMU
-      static size_t lim = 32 * 1024;
-      if (smem > lim) { if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA; lim = smem; }
+      static SmemOptIn optin;
+      if (optin.ensure(kfn, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
       TCR_LAUNCH("dscnn_dsblock", kfn, dim3((L.hout + RH - 1) / RH, n), dim3(256), smem, s, L, RH, params, in, out, eps);
     }

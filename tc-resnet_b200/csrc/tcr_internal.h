@@ -45,20 +45,20 @@ struct ActSrc {
   StatSrc st;
 };
 
-struct BnFinalize {         // what the last CTA of a producer kernel needs to finalise forward statistics
+// What the finalize PHASES of the opt-in persistent kernel (tcr_persist.cu) need: there the records are per CTA and a
+// phase behind a grid barrier sums them (the default multi-kernel path sums per-cluster records in the consumer, tcr_bn.cuh).
+struct BnFinalize {
   const float* gamma;       // params + gamma_off
   const float* beta;
-  const float* fpart;       // [G][C][2] (mean, M2)
+  const float* fpart;       // [G][C][2] (sum y, sum y^2)
   float* bnf;               // [4][C]
   float* var;               // [C] biased batch variance (moving-average update reads it)
-  float* l2;                // [ceil(G/16)][C][3] level-2 records of the finalize tree
   int c;
 };
 
-struct BwdSumFinalize {     // last CTA: sum partial (sum dz, sum dz*xhat) over groups
+struct BwdSumFinalize {     // sum of (sum dz, sum dz*xhat) records
   const float* bpart;       // [G][C][2]
   float* bsum;              // [2][C]
-  float* l2;                // [ceil(G/16)][C][2] level-2 records of the finalize tree
   int c;
 };
 
@@ -80,7 +80,6 @@ struct FwdArgs {
   const float* wd; float* yd; float* fpartd; int coutd;
   // training statistics
   int train;
-  unsigned* counter;
   BnFinalize fin, find;
   float eps;
 };
@@ -97,7 +96,7 @@ struct HeadArgs {
   const float* mask;        // injected dropout mask or null
   uint64_t seed; float keep; int use_dropout; float label_smoothing;
   float* logits; float* probs;   // may be null
-  float* loss_part;         // [Gh] per-CTA sum of per-utterance CE
+  float* loss_part;         // [clusters] sum of per-utterance CE per cluster record
   int backward;             // 1: also produce gblk, BN-backward partial sums and fc dW partials
   float inv_n;              // 1 / n (mean over the local batch)
   float* gout;              // gblk_last [N, T', C]
@@ -105,10 +104,8 @@ struct HeadArgs {
   const float* yb; const float* bnfb; float* bpartb;
   const float* ydn; const float* bnfd; float* bpartd;   // null when the last block has no down conv
   float* dwfc_part;         // [Gh][C*classes]
-  unsigned* counter;
   BwdSumFinalize finb, find;
-  float* loss_out;          // [1] sum over utterances of CE (finalised by the last CTA)
-  float* loss_l2;           // [ceil(Gh/16)] level-2 loss sums
+  float* loss_out;          // [1] sum over utterances of CE (persistent kernel's finalize phase)
 };
 
 // ---------------- backward-data kernel ----------------
@@ -138,7 +135,6 @@ struct BwdDataArgs {
   const float* out_prev;                                        // kind 2
   const float* ypd; const float* bnfpd; float* bpartpd;         // kind 2: down conv of prev block (may be null)
   float* gprev;             // [N, t_in, cin]
-  unsigned* counter;
   BwdSumFinalize finp, finpd;
 };
 

@@ -327,16 +327,12 @@ int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
   dim3 block(32 * warps, 1, 1);
   const size_t smem = mfcc_smem_bytes(a, nf2, warps);
 #ifndef TCR_EMU
-#define TCR_MFCC_CASE(NF2)                                                                                   \
-  case NF2: {                                                                                                \
-    auto k = a.pcm16 ? mfcc_kernel<NF2, true> : mfcc_kernel<NF2, false>;                                     \
-    static size_t smem_limit[2] = {32 * 1024, 32 * 1024};                                                    \
-    size_t& lim = smem_limit[a.pcm16 ? 1 : 0];                                                               \
-    if (smem > lim) {                                                                                 \
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-      lim = smem;                                                                                            \
-    }                                                                                                        \
-    TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);                                                             \
+#define TCR_MFCC_CASE(NF2)                                                         \
+  case NF2: {                                                                      \
+    auto k = a.pcm16 ? mfcc_kernel<NF2, true> : mfcc_kernel<NF2, false>;           \
+    static SmemOptIn optin[2];                                                     \
+    if (optin[a.pcm16 ? 1 : 0].ensure(k, smem) != cudaSuccess) return 1;           \
+    TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);                           \
   } break;
 #else
 #define TCR_MFCC_CASE(NF2)                         \

@@ -592,11 +592,8 @@ template <int K, bool WSMEM>
 static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, size_t smem, cudaStream_t s, int cluster) {
   auto kfn = conv_bwd_data_kernel<K, WSMEM>;
 #ifndef TCR_EMU
-  static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
-  if (smem > smem_limit) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
-    smem_limit = smem;
-  }
+  static SmemOptIn optin;           // one per template instantiation
+  if (optin.ensure(kfn, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
   TCR_LAUNCH_CLUSTER(name, kfn, dim3(groups), dim3(kThreads), smem, s, cluster, a);
   return 0;
@@ -608,8 +605,7 @@ static DySrc make_dy(const ConvPlan& cv, const float* dz, int mask, int n) {
 }
 
 // *gc_out: per-cluster records of BatchNorm-backward sums this launch leaves for the layer(s) below (0 when recording)
-static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, int slot, cudaStream_t s,
-                    int* gc_out) {
+static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, const float* params, int n, cudaStream_t s, int* gc_out) {
   int U, KS, wsm;
   pick_bwd_tile(cv, dn, n, &U, &KS, &wsm);
   a.n = n; a.U = U; a.w_smem = wsm;
@@ -619,7 +615,6 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.has_down = dn ? 1 : 0;
   a.wd = dn ? dn->wT : nullptr;
   a.coutd = dn ? dn->cout : 0;
-  (void)slot;
   const int groups = (n + U - 1) / U;
   a.nvb = groups;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
@@ -656,7 +651,6 @@ int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s) {
 }
 
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s) {
-  int slot = 32;
   for (int i = (int)h->blocks.size() - 1; i >= 0; --i) {
     BlockPlan& b = h->blocks[i];
     ConvPlan& ca = h->convs[b.a];
@@ -669,10 +663,10 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       a.dy = make_dy(cb, b.gblk, 0, n);
       a.epi_kind = 1;
       a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
-      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.bl2, ca.cout};
+      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.cout};
       a.finpd = a.finp;
       int gc = 0;
-      int rc = bwd_data(h, cb, nullptr, a, params, n, slot++, s, &gc);
+      int rc = bwd_data(h, cb, nullptr, a, params, n, s, &gc);
       if (rc) return rc;
       ca.b_gc = gc;
     }
@@ -689,23 +683,23 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
         a.epi_kind = 2;
         a.out_prev = pb.out;
         a.yp = pcb.y; a.bnfp = pcb.bnf; a.bpartp = pcb.bpart;
-        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.bl2, pcb.cout};
+        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.cout};
         a.finpd = a.finp;
         if (pb.down >= 0) {
           ConvPlan& pd = h->convs[pb.down];
           a.ypd = pd.y; a.bnfpd = pd.bnf; a.bpartpd = pd.bpart;
-          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.bl2, pd.cout};
+          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.cout};
         }
         a.gprev = pb.gblk;
       } else {
         ConvPlan& c0 = h->convs[0];
         a.epi_kind = 1;
         a.yp = c0.y; a.bnfp = c0.bnf; a.bpartp = c0.bpart; a.gprev = c0.g;
-        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.bl2, c0.cout};
+        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.cout};
         a.finpd = a.finp;
       }
       int gc = 0;
-      int rc = bwd_data(h, ca, dn, a, params, n, slot++, s, &gc);
+      int rc = bwd_data(h, ca, dn, a, params, n, s, &gc);
       if (rc) return rc;
       if (i > 0) {
         BlockPlan& pb = h->blocks[i - 1];
@@ -722,11 +716,8 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
   } else {
     auto kfn = dw_grouped_kernel;
 #ifndef TCR_EMU
-    static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default
-    if (h->dw_smem > smem_limit) {
-      if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dw_smem) != cudaSuccess) return TCR_ERR_CUDA;
-      smem_limit = h->dw_smem;
-    }
+    static SmemOptIn optin;
+    if (optin.ensure(kfn, h->dw_smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
     // conv0's BatchNorm-backward sums have no backward-data consumer: its weight-gradient CTAs add the records themselves
     const ConvPlan& c0 = h->convs[0];

@@ -553,8 +553,6 @@ int net_alloc_workspace(tcr_handle* h) {
     WS(ws_alloc(h, &cv.fpart, (size_t)h->g_max * cv.cout * 2));
     WS(ws_alloc(h, &cv.bpart, (size_t)std::max(h->g_max, h->head_groups_max) * cv.cout * 2));
     WS(ws_alloc(h, &cv.bsum, 2 * (size_t)cv.cout));
-    WS(ws_alloc(h, &cv.fl2, (size_t)(h->g_max / kFanIn + 1) * cv.cout * 3));
-    WS(ws_alloc(h, &cv.bl2, (size_t)(h->g_max / kFanIn + 1) * cv.cout * 2));
     WS(ws_alloc(h, &cv.dwpart, (size_t)cv.dw_R * cv.wnumel()));
     WS(ws_alloc(h, &cv.wT, (size_t)cv.wnumel()));
   }
@@ -572,10 +570,6 @@ int net_alloc_workspace(tcr_handle* h) {
   WS(ws_alloc(h, &h->d_dwfc_part, (size_t)h->head_groups_max * h->c_last * h->cfg.num_classes));
   WS(ws_alloc(h, &h->d_grads, (size_t)h->n_train));
   WS(ws_alloc(h, &h->d_l2part, 4096));
-  h->counter_stride = 2 + h->g_max / kFanIn;
-  WS(ws_alloc(h, &h->d_counters, (size_t)64 * h->counter_stride));
-  if (cudaMemset(h->d_counters, 0, (size_t)64 * h->counter_stride * sizeof(unsigned)) != cudaSuccess) return TCR_ERR_CUDA;
-  WS(ws_alloc(h, &h->d_loss_l2, (size_t)h->head_groups_max / kFanIn + 2));
   WS(ws_alloc(h, &h->d_hyper, 1));
   WS(ws_alloc(h, &h->d_gridbar, 4));
   if (getenv("TCR_DEBUG_TIMELINE")) {
@@ -611,18 +605,15 @@ template <int K, bool WSMEM>
 static int launch_conv_fwd(const char* name, const FwdArgs& a, int groups, size_t smem, cudaStream_t s, int cluster) {
   auto kfn = conv_fwd_kernel<K, WSMEM>;
 #ifndef TCR_EMU
-  static size_t smem_limit = 32 * 1024;   // static smem (finalize scratch) counts against the 48 KB default   // per template instantiation
-  if (smem > smem_limit) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
-    smem_limit = smem;
-  }
+  static SmemOptIn optin;           // one per template instantiation
+  if (optin.ensure(kfn, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
   TCR_LAUNCH_CLUSTER(name, kfn, dim3(groups), dim3(kThreads), smem, s, cluster, a);
   return 0;
 }
 
 static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const float* params, int n, bool training,
-                    int counter_slot, cudaStream_t s) {
+                    cudaStream_t s) {
   int U, KS, wsm;
   pick_fwd_tile(cv, dn, n, &U, &KS, &wsm);
   a.n = n; a.U = U; a.t_in = cv.t_in; a.cin = cv.cin; a.w_smem = wsm;
@@ -632,13 +623,12 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.train = training ? 1 : 0;
   a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline + (h->rec ? 12 * 8192 : 0) : nullptr;
   if (h->d_timeline && !h->rec && cv.name == "block1/conv1_1") a.tl = h->d_timeline + 2048 * 8;   // its producer, rows 2048..
-  (void)counter_slot;
   a.eps = h->cfg.bn_epsilon;
-  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.fl2, cv.cout};
+  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.cout};
   a.find = a.fin;
   if (dn) {
     a.wd = params + dn->w_off; a.yd = dn->y; a.fpartd = dn->fpart; a.coutd = dn->cout;
-    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->fl2, dn->cout};
+    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->cout};
   }
   const int groups = (n + U - 1) / U;
   a.nvb = groups;
@@ -680,14 +670,13 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
     }
     TCR_LAUNCH("bn_table_eval", bn_table_eval_kernel, dim3(e.nlayers), dim3(128), 0, s, e);
   }
-  int slot = 0;
   // conv0 on raw features
   {
     FwdArgs a;
     memset(&a, 0, sizeof(a));
     a.in_kind = 0;
     a.in = ActSrc{feat, nullptr, 0, StatSrc{}};
-    int rc = conv_fwd(h, h->convs[0], nullptr, a, params, n, training, slot++, s);
+    int rc = conv_fwd(h, h->convs[0], nullptr, a, params, n, training, s);
     if (rc) return rc;
   }
   ActSrc prev = act_of(h, h->convs[0], 1, params, n);   // activation feeding the next block
@@ -709,14 +698,14 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       a.shortcut = pb.down >= 0 ? act_of(h, h->convs[pb.down], 1, params, n) : prev;
       a.out_write = pb.out;
     }
-    int rc = conv_fwd(h, ca, dn, a, params, n, training, slot++, s);
+    int rc = conv_fwd(h, ca, dn, a, params, n, training, s);
     if (rc) return rc;
     if (i > 0) prev = ActSrc{h->blocks[i - 1].out, nullptr, 0, StatSrc{}};   // materialised by the launch above
     FwdArgs a2;
     memset(&a2, 0, sizeof(a2));
     a2.in_kind = 1;
     a2.in = act_of(h, ca, 1, params, n);
-    rc = conv_fwd(h, cb, nullptr, a2, params, n, training, slot++, s);
+    rc = conv_fwd(h, cb, nullptr, a2, params, n, training, s);
     if (rc) return rc;
     if (i + 1 == h->blocks.size()) {
       BlockPlan& lb = b;
@@ -740,9 +729,8 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.yb = cb.y; ha.bnfb = cb.bnf; ha.bpartb = cb.bpart;
       ha.ydn = dn ? dn->y : nullptr; ha.bnfd = dn ? dn->bnf : nullptr; ha.bpartd = dn ? dn->bpart : nullptr;
       ha.dwfc_part = h->d_dwfc_part;
-      ha.loss_l2 = h->d_loss_l2;
-      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.bl2, cb.cout};
-      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->bl2, dn->cout} : ha.finb;
+      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.cout};
+      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->cout} : ha.finb;
       ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       ha.nvb = groups;
@@ -756,12 +744,9 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       if (h->rec) {
         rec_head(h, ha, groups, smem);
       } else {
-        static size_t head_lim = 32 * 1024;
 #ifndef TCR_EMU
-        if (smem > head_lim) {
-          if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TCR_ERR_CUDA;
-          head_lim = smem;
-        }
+        static SmemOptIn optin;
+        if (optin.ensure(head_kernel, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
         TCR_LAUNCH_CLUSTER("head", head_kernel, dim3(grid), dim3(kHeadThreads), smem, s, CL, ha);
       }

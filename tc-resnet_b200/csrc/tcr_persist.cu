@@ -269,17 +269,16 @@ int rec_launch(tcr_handle* h, cudaStream_t s) {
   auto kfn = step_kernel;
   int grid = 3;     // emulator: a few co-resident CTAs are enough to exercise every path
 #ifndef TCR_EMU
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > h->persist_smem) {     // per handle (hence per device): the occupancy query below depends on it
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { rec_abort(h); return TCR_ERR_CUDA; }
-    smem_set = smem;
+    h->persist_smem = smem;
     h->persist_grid = 0;
   }
   if (!h->persist_grid) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, smem_set) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, h->persist_smem) != cudaSuccess || per_sm < 1) {
       rec_abort(h);
       set_error("persistent step kernel does not fit on an SM");
       return TCR_ERR_CUDA;

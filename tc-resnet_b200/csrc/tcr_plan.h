@@ -19,11 +19,9 @@ struct ConvPlan {
   float* g = nullptr;          // [N, t_out, cout] dL/dz (conv_a / conv0 own one; conv_b and down alias gblk)
   float* bnf = nullptr;        // [4][cout]
   float* var = nullptr;        // [cout]
-  float* fpart = nullptr;      // [G][cout][2]
-  float* bpart = nullptr;      // [G][cout][2]
+  float* fpart = nullptr;      // [records][cout][2] (sum y, sum y^2) per cluster (per CTA in the persistent kernel)
+  float* bpart = nullptr;      // [records][cout][2] (sum dz, sum dz*xhat)
   float* bsum = nullptr;       // [2][cout]
-  float* fl2 = nullptr;        // level-2 records of the forward-statistics tree
-  float* bl2 = nullptr;        // level-2 records of the backward-sum tree
   float* dwpart = nullptr;     // [R][k*cin*cout]
   float* wT = nullptr;         // [k][cout][cin] transposed filter bank (refreshed per backward pass)
   int dw_R = 1, dw_cot = 0, dw_RG = 1, dw_UB = 1;
@@ -63,7 +61,6 @@ struct tcr_handle {
   float* d_loss_part = nullptr; float* d_loss = nullptr; float* d_dwfc_part = nullptr;
   float* d_grads = nullptr;
   float* d_l2part = nullptr;
-  unsigned* d_counters = nullptr; int counter_stride = 0; float* d_loss_l2 = nullptr;
   tcr::Hyper* d_hyper = nullptr; tcr::Hyper* h_hyper = nullptr;
   tcr::OptSegment* d_segs = nullptr; int n_segs = 0;
   tcr::MovingSegment* d_msegs = nullptr; int n_msegs = 0;
@@ -74,6 +71,7 @@ struct tcr_handle {
   void* comm = nullptr; int rank = 0, world = 1;
   int last_n = 0;
   int loss_gc = 0;            // cross-entropy records left by the head launch of this call
+  size_t persist_smem = 0;    // dynamic shared memory the persistent kernel is opted in to on this handle's device
   int cluster = 0;            // CTAs per thread-block cluster of the conv / head launches (env TCR_CLUSTER, default 8)
   void* hostfeed = nullptr;   // HostFeedState (tcr_api.cu): staging slots of tcr_train_step_host
   tcr::StepProgram* rec = nullptr;   // non-null while a training step is being recorded for the persistent kernel
