@@ -64,7 +64,11 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
   }
   float* dys = wsd + wdn;                                            // [U][TPd][COS]
   float* dysd = dys + (size_t)a.U * TPd * COS;                       // [U][t_out][COSD]
-  float* dxs = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);   // [KS][Rin_max][cin]
+  // dx planes start past BOTH the staged tiles and the epilogue scratch `red` (which aliases the filter bank / dy tiles from
+  // `ws` on): with the filters read through L1/L2 and a small tile, `red` is the larger of the two.
+  float* tiles_end = dysd + (a.has_down ? (size_t)a.U * a.t_out * COSD : 0);
+  const int red_floats = 4 * imax(1, kThreads / (a.cin >> 2)) * a.cin;
+  float* dxs = ws + imax((int)(tiles_end - ws), red_floats);         // [KS][Rin_max][cin]
   float* red = ws;                                                   // [4][nseg][cin]: aliases the filter bank / dy tiles,
                                                                      // which are dead once the transposed conv is done
   float* stat = dxs + (size_t)a.KS * Rin_max * a.cin;                // BN-backward sums: [2][cout] + [2][coutd] while staging,

@@ -477,9 +477,11 @@ static constexpr int kSMs = 148;
 double tile_cost(int n, int U, int occ, bool wsm) {
   const int groups = (n + U - 1) / U;
   const int waves = (groups + kSMs * occ - 1) / (kSMs * occ);
-  // unit = FMA time of one utterance at one CTA per SM; the per-wave fixed part (launch, filter TMA, staging latency, statistics,
-  // cluster publish) measured at ~4 such units
-  return waves * (U * (occ == 2 ? 1.7 : 1.0) * (wsm ? 1.0 : 2.5) + 4.0);
+  // unit = FMA time of one utterance on an otherwise idle SM.  Measured on TCResNet14-1.5 (profiles/r01_v11_*): a lone 8-warp CTA
+  // per SM cannot hide its latencies (76-89 us at 152 CTAs vs 47-54 us at 256 CTAs, two per SM), and reading the filter bank
+  // through L1/L2 costs about the same as staging it in shared memory (48 us), so residency decides, not the filter path.
+  // The per-wave fixed part (launch, filter TMA, staging latency, statistics, cluster publish) is ~4 such units.
+  return waves * (U * (occ == 2 ? 1.7 : 1.8) * (wsm ? 1.0 : 1.1) + 4.0);
 }
 
 static void pick_fwd_tile(const ConvPlan& cv, const ConvPlan* dn, int n, int* U_out, int* KS_out, int* wsm_out) {
