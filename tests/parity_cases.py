@@ -95,11 +95,11 @@ def run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=4, ke
             report[f"slots{step}"] = rel_err(ts["slots"], O.flatten_vars(spec, sl1, np.float64))
             report[f"moving{step}"] = rel_err(ts["moving"], O.flatten_moving(spec, mv1, np.float64))
             floor = 0.0
-            if check_f32_floor and step == 0:
+            if check_f32_floor:                      # every step: the fp32 NumPy oracle's own distance to fp64 on this input
                 p32, mv32, sl32 = (O.cast_vars(d, np.float32) for d in (p, mv, sl))
                 _, _, _, r32 = O.train_step(spec, p32, mv32, sl32, feat.astype(np.float32), onehot, lr, mom, wd, keep, mask, ls)
                 floor = 4 * rel_err(O.flatten_vars(spec, r32["grads"], np.float64), O.flatten_vars(spec, ref["grads"], np.float64))
-                report["grads_f32_oracle_floor"] = floor / 4
+                report[f"grads_f32_oracle_floor{step}"] = floor / 4
             assert report[f"train_logits{step}"] <= TOL_LOGITS, report
             assert report[f"grads{step}"] <= max(TOL_STATE, floor), report
             assert report[f"params{step}"] <= max(TOL_STATE, floor), report
