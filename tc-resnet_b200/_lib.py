@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtcr_b200.so")
 
 TCR_MODEL_TCRESNET8 = 8
 TCR_MODEL_TCRESNET14 = 14
+ABI_VERSION = 2          # TCR_ABI_VERSION of include/tcr_b200.h this binding was written against
 TCR_INPUT_WAV_F32, TCR_INPUT_FEATURES, TCR_INPUT_WAV_PCM16 = 0, 1, 2
 TCR_FEATURE_MFCC = 0
 TCR_FEATURE_LOG_MEL = 1
@@ -117,8 +118,8 @@ def load(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, name)      # AttributeError if the export is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.tcr_abi_version() != 2:
-        raise TcrError(f"ABI version mismatch: library {lib.tcr_abi_version()}, binding 2")
+    if lib.tcr_abi_version() != ABI_VERSION:
+        raise TcrError(f"ABI version mismatch: library {lib.tcr_abi_version()}, binding {ABI_VERSION}")
     return lib
 
 

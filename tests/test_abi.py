@@ -28,6 +28,15 @@ def test_header_and_binding_agree(lib):
         assert hasattr(lib, name), f"libtcr_b200.so does not export {name}"
 
 
+def test_abi_version_is_consistent_everywhere(lib):
+    """Header, binding, library and the driver's build() check must agree (a mismatch fails the round's build gate)."""
+    header = open(os.path.join(ROOT, "include", "tcr_b200.h")).read()
+    declared = int(re.search(r"#define TCR_ABI_VERSION (\d+)", header).group(1))
+    assert declared == L.ABI_VERSION == lib.tcr_abi_version()
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert "_lib.ABI_VERSION" in entry
+
+
 def test_every_entry_point_cites_the_reference():
     header = open(os.path.join(ROOT, "include", "tcr_b200.h")).read()
     for needle in ("datasets/preprocessors.py", "audio_nets/tc_resnet.py", "factory/audio_nets.py",
