@@ -193,7 +193,7 @@ def run_reference(a):
            "config": {"workload": workload_name(a), "global_batch": a.batch * a.gpus, "sample_batch": batch},
            "cpu_baseline": {"value": value, "unit": "utterances/sec", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "utterances/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,7 +415,7 @@ def run_ours(a):
             except Exception as e:  # the oracle port must never take the bench line down
                 out["cpu_baseline"] = {"value": None, "unit": "utterances/sec", "cores": os.cpu_count(), "kind": "port",
                                        "sample": f"failed: {e}"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -445,16 +445,33 @@ def run_dscnn(a):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = n * a.steps / (ms * 1e-3)
-    print(json.dumps({"metric": "utterances/sec (forward) DS-CNN-S", "value": value, "unit": "utterances/sec", "n_gpus": 1,
+    emit({"metric": "utterances/sec (forward) DS-CNN-S", "value": value, "unit": "utterances/sec", "n_gpus": 1,
                       "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
                       "config": {"workload": f"DS-CNN-S forward (inference), MFCC 49x40 features resident in HBM, batch {n}",
                                  "forward_flops_per_utt": net.forward_flops},
-                      "fp32_tflops": value * net.forward_flops / 1e12}), flush=True)
+                      "fp32_tflops": value * net.forward_flops / 1e12})
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL's version banner, torch
+    warnings) was rerouted to stderr by main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    global _JSON_FD
     a = parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)                # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                       # ... and send fd 1 (C libraries included) to stderr for the rest of the run
     if a.workload == "dscnn":
         return run_dscnn(a)
     if a.impl == "reference":
