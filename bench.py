@@ -44,8 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
-    ap.add_argument("--workload", default="train", choices=["train", "dscnn"],
-                    help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point)")
+    ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer"],
+                    help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point); "
+                         "infer: evaluation-mode forward from wav (config 1 with --batch 1: latency)")
     return ap.parse_args()
 
 
@@ -420,6 +421,43 @@ def run_ours(a):
         torch.distributed.destroy_process_group()
 
 
+def run_infer(a):
+    """Config 1: evaluation-mode forward (moving-statistics BN, no dropout) from wav; with --batch 1 this is the latency case.
+    Device-timed per call (CUDA events), and synchronously from the host (call -> logits on the host)."""
+    import torch
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.engine import Engine
+    dev = torch.device("cuda", 0)
+    n = a.batch
+    eng = Engine(model=a.model, width_multiplier=a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms, max_batch=n)
+    params, _, moving = eng.new_variables(seed=0)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    wavs = [torch.rand(n, 16000, device=dev, generator=gen) * 2 - 1 for _ in range(a.rotate)]
+    for i in range(max(a.warmup, 3)):
+        eng.forward(wavs[i % a.rotate], params, moving)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        eng.forward(wavs[i % a.rotate], params, moving)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    h_wav = wavs[0].cpu().pin_memory()
+    d_wav = torch.empty_like(wavs[0])
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        d_wav.copy_(h_wav, non_blocking=True)
+        logits = eng.forward(d_wav, params, moving)["logits"].cpu()          # synchronises: the caller holds the prediction
+    host_ms = (time.perf_counter() - t0) / a.steps * 1e3
+    emit({"metric": f"utterances/sec (evaluation forward from wav) {a.model}-{a.width:g}", "value": n / (ms * 1e-3), "unit": "utterances/sec",
+          "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+          "config": {"workload": f"{a.model}-{a.width:g} evaluation forward (MFCC + network, moving-statistics BN), batch {n}"},
+          "latency_ms_device": ms, "latency_ms_host_roundtrip": host_ms, "gpu_launches": eng.launch_count(),
+          "argmax_first": int(logits[0].argmax())})
+
+
 def run_dscnn(a):
     """Config 5: DS-CNN-S forward, MFCC 49x40 features resident in HBM, batch 512, one B200 (2-D-conv comparison point)."""
     import torch
@@ -474,6 +512,8 @@ def main():
     os.dup2(2, 1)                       # ... and send fd 1 (C libraries included) to stderr for the rest of the run
     if a.workload == "dscnn":
         return run_dscnn(a)
+    if a.workload == "infer":
+        return run_infer(a)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -101,9 +101,7 @@ __device__ __forceinline__ Dy4 dy4_make(const DySrc& d, int C, int c, const floa
   r.s2m = make_float4(s2.x * im, s2.y * im, s2.z * im, s2.w * im);
   return r;
 }
-__device__ __forceinline__ float4 dy4_load(const Dy4& d, size_t ofs) {
-  float4 dz = ld4(d.dz + ofs);
-  const float4 y = ld4(d.y + ofs);
+__device__ __forceinline__ float4 dy4_apply(const Dy4& d, float4 dz, const float4 y) {
   if (d.mask) {
     const float4 z = chan4_bn(d.k, y);
     if (z.x <= 0.f) dz.x = 0.f;
@@ -118,6 +116,7 @@ __device__ __forceinline__ float4 dy4_load(const Dy4& d, size_t ofs) {
   r.w = d.k.scale.w * (dz.w - d.s1m.w - (y.w - d.k.mean.w) * d.k.rstd.w * d.s2m.w);
   return r;
 }
+__device__ __forceinline__ float4 dy4_load(const Dy4& d, size_t ofs) { return dy4_apply(d, ld4(d.dz + ofs), ld4(d.y + ofs)); }
 
 // 2-D walk of a [rows][c4n] float4 grid by the CTA: c4 fixed per thread, rows advance by rstep.
 // Threads beyond rstep * c4n idle (row = huge).

@@ -86,31 +86,47 @@ __device__ __forceinline__ void conv_bwd_data_body(const BwdDataArgs& a, const i
       st4(dys + ((size_t)(u * TPd + row) * COS + 4 * c4), make_float4(0.f, 0.f, 0.f, 0.f));
     }
     pdl_wait();                     // the transposed filter bank (TMA above) was written at the start of the step
+    // raw (dz, y) rows are requested BEFORE the BatchNorm-backward sums are built: the two global round trips overlap
+    constexpr int PF = 4;
+    const RowWalk w = row_walk(tid, kThreads, c4n);
+    const int rows = Ue * a.t_out;
+    const size_t grow = (size_t)u0 * a.t_out;
+    float4 pdz[PF], py[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int row = w.row + i * w.rstep;
+      pdz[i] = py[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows) {
+        const size_t gofs = (grow + row) * a.cout + 4 * w.c4;
+        pdz[i] = ld4(a.dy.dz + gofs);
+        py[i] = ld4(a.dy.y + gofs);
+      }
+    }
     bsum_build(a.dy.bs, a.dy.bsum, a.cout, sb_main, stat_scratch, vb == 0);
     if (a.has_down) bsum_build(a.dyd.bs, a.dyd.bsum, a.coutd, sb_down, stat_scratch, vb == 0);
-    {
-      const RowWalk w = row_walk(tid, kThreads, c4n);
-      const int rows = Ue * a.t_out;
-      const size_t grow = (size_t)u0 * a.t_out;
-      if (w.row < rows) {
-        const Dy4 d = dy4_make(a.dy, a.cout, 4 * w.c4, sb_main);
-        int u = w.row / a.t_out, t = w.row - u * a.t_out;
-        for (int row = w.row; row < rows; row += w.rstep) {
-          st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * w.c4), dy4_load(d, (grow + row) * a.cout + 4 * w.c4));
-          t += w.rstep;
-          while (t >= a.t_out) { t -= a.t_out; ++u; }
-        }
+    if (w.row < rows) {
+      const Dy4 d = dy4_make(a.dy, a.cout, 4 * w.c4, sb_main);
+      int u = w.row / a.t_out, t = w.row - u * a.t_out;
+      auto place = [&](float4 dz, float4 y) {
+        st4(dys + ((size_t)(u * TPd + PLd + t) * COS + 4 * w.c4), dy4_apply(d, dz, y));
+        t += w.rstep;
+        while (t >= a.t_out) { t -= a.t_out; ++u; }
+      };
+#pragma unroll
+      for (int i = 0; i < PF; ++i)
+        if (w.row + i * w.rstep < rows) place(pdz[i], py[i]);
+      for (int row = w.row + PF * w.rstep; row < rows; row += w.rstep) {
+        const size_t gofs = (grow + row) * a.cout + 4 * w.c4;
+        place(ld4(a.dy.dz + gofs), ld4(a.dy.y + gofs));
       }
     }
     if (a.has_down) {
       const int d4n = a.coutd >> 2;
-      const RowWalk w = row_walk(tid, kThreads, d4n);
-      const int rows = Ue * a.t_out;
-      const size_t grow = (size_t)u0 * a.t_out;
-      if (w.row < rows) {
-        const Dy4 d = dy4_make(a.dyd, a.coutd, 4 * w.c4, sb_down);
-        for (int row = w.row; row < rows; row += w.rstep)
-          st4(dysd + ((size_t)row * COSD + 4 * w.c4), dy4_load(d, (grow + row) * a.coutd + 4 * w.c4));
+      const RowWalk wd = row_walk(tid, kThreads, d4n);
+      if (wd.row < rows) {
+        const Dy4 d = dy4_make(a.dyd, a.coutd, 4 * wd.c4, sb_down);
+        for (int row = wd.row; row < rows; row += wd.rstep)
+          st4(dysd + ((size_t)row * COSD + 4 * wd.c4), dy4_load(d, (grow + row) * a.coutd + 4 * wd.c4));
       }
     }
   }

@@ -72,35 +72,56 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
   }
   pdl_wait();                       // everything above is independent of the producer kernel (filters: caller-owned params)
   tl_stamp(a.tl, vb, 7);
-  // BN tables of the layers this tile reads, summed from the producers' per-cluster records (tcr_bn.cuh)
-  if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
-  if (a.in_kind == 2 && a.shortcut.kind == 1) bn_table_build(a.shortcut.st, a.shortcut.bnf, a.cin, tbl_sh, red, vb == 0);
   {
-    // c4 fixed per thread (per-channel constants in registers), rows advance incrementally: no div/mod per element
+    // c4 fixed per thread (per-channel constants in registers), rows advance incrementally: no div/mod per element.
+    // The raw rows are requested BEFORE the BN tables are built, so the two global round trips (records, tile) overlap.
     const RowWalk w = row_walk(tid, kThreads, c4n);
     const int rows = Ue * a.t_in;
     const size_t grow = (size_t)u0 * a.t_in;
+    constexpr int PF = 4;             // rows per thread kept in flight (a thread owns at most ~4 rows at the tile sizes in use)
+    const bool res = a.in_kind == 2;
+    float4 pin[PF], psh[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int row = w.row + i * w.rstep;
+      pin[i] = psh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows) {
+        const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
+        pin[i] = ld4(a.in.data + gofs);
+        if (res) psh[i] = ld4(a.shortcut.data + gofs);
+      }
+    }
+    // BN tables of the layers this tile reads, summed from the producers' per-cluster records (tcr_bn.cuh)
+    if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
+    if (res && a.shortcut.kind == 1) bn_table_build(a.shortcut.st, a.shortcut.bnf, a.cin, tbl_sh, red, vb == 0);
     if (w.row < rows) {
       int u = w.row / a.t_in, t = w.row - u * a.t_in;
-      if (a.in_kind == 2) {
-        const Chan4 kb = chan4_load_s(tbl_in, a.cin, 4 * w.c4);
-        const Act4 sh = act4_make(a.shortcut, a.cin, 4 * w.c4, tbl_sh);
-        for (int row = w.row; row < rows; row += w.rstep) {
-          const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
-          const float4 v = relu4(add4(chan4_bn(kb, ld4(a.in.data + gofs)), act4_load(sh, gofs)));
-          if (a.out_write) st4(a.out_write + gofs, v);
-          st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), v);
-          t += w.rstep;
-          while (t >= a.t_in) { t -= a.t_in; ++u; }
+      Chan4 kin, ksh;
+      kin.mean = kin.rstd = kin.scale = kin.beta = ksh.mean = ksh.rstd = ksh.scale = ksh.beta = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.in_kind != 0) kin = chan4_load_s(tbl_in, a.cin, 4 * w.c4);
+      const bool sh_bn = res && a.shortcut.kind == 1;
+      if (sh_bn) ksh = chan4_load_s(tbl_sh, a.cin, 4 * w.c4);
+      auto place = [&](int row, float4 vin, float4 vsh) {
+        float4 v = vin;
+        if (a.in_kind == 1) {
+          v = relu4(chan4_bn(kin, vin));
+        } else if (res) {
+          if (sh_bn) vsh = relu4(chan4_bn(ksh, vsh));
+          v = relu4(add4(chan4_bn(kin, vin), vsh));
+          if (a.out_write) st4(a.out_write + (grow + row) * a.cin + 4 * w.c4, v);
         }
-      } else {
-        const Act4 src = act4_make(a.in, a.cin, 4 * w.c4, tbl_in);
-        for (int row = w.row; row < rows; row += w.rstep) {
-          const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
-          st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), act4_load(src, gofs));
-          t += w.rstep;
-          while (t >= a.t_in) { t -= a.t_in; ++u; }
-        }
+        st4(xs + ((size_t)(u * TP + a.pad_left + t) * CS + 4 * w.c4), v);
+        t += w.rstep;
+        while (t >= a.t_in) { t -= a.t_in; ++u; }
+      };
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int row = w.row + i * w.rstep;
+        if (row < rows) place(row, pin[i], psh[i]);
+      }
+      for (int row = w.row + PF * w.rstep; row < rows; row += w.rstep) {
+        const size_t gofs = (grow + row) * a.cin + 4 * w.c4;
+        place(row, ld4(a.in.data + gofs), res ? ld4(a.shortcut.data + gofs) : make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }
