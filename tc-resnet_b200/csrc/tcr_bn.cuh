@@ -179,7 +179,7 @@ __device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, doubl
 
 // Sum `gc` records of `cols` floats each: thread i < cols * nch takes column i % cols and records i / cols, + nch, ...
 // (loads batched 8 deep); the nch chunk sums land in scratch[chunk * cols + col].  Needs cols <= blockDim.x.
-constexpr int kRecB = 16;
+constexpr int kRecB = 32;          // records in flight per thread: one batch covers 32 records x column chunks
 __device__ __forceinline__ int records_sum(const float* part, int gc, int cols, float* scratch) {
   const int nch = imax(1, (int)blockDim.x / cols);
   const int i = threadIdx.x;
@@ -216,6 +216,62 @@ __device__ __forceinline__ void bn_table_build(const StatSrc& st, const float* b
     for (int ch = 0; ch < nch; ++ch) {
       s1 += (double)scratch[ch * 2 * C + 2 * c];
       s2 += (double)scratch[ch * 2 * C + 2 * c + 1];
+    }
+    const double mean = s1 * (double)st.inv_m;
+    double var = s2 * (double)st.inv_m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)st.eps);
+    const float g = st.gamma[c], b = st.beta[c];
+    const float fm = (float)mean, fr = (float)rstd, fs = (float)((double)g * rstd);
+    tbl[c] = fm; tbl[C + c] = fr; tbl[2 * C + c] = fs; tbl[3 * C + c] = b;
+    if (publish) {
+      st.bnf[c] = fm; st.bnf[C + c] = fr; st.bnf[2 * C + c] = fs; st.bnf[3 * C + c] = b;
+      st.var[c] = (float)var;
+    }
+  }
+  __syncthreads();
+}
+
+// Two tables of the same width (a block's conv_b and its shortcut conv) in ONE pass: the record loads of both layers are in
+// flight together and the two barriers are shared.  Falls back to two passes when 4C columns exceed the block.
+__device__ __forceinline__ void bn_table_build2(const StatSrc& sa, const float* bnf_a, float* tbl_a, const StatSrc& sb, const float* bnf_b,
+                                                float* tbl_b, int C, float* scratch, bool publish) {
+  const int cols = 4 * C;
+  if (!sa.cpart || !sb.cpart || cols > (int)blockDim.x) {
+    bn_table_build(sa, bnf_a, C, tbl_a, scratch, publish);
+    bn_table_build(sb, bnf_b, C, tbl_b, scratch, publish);
+    return;
+  }
+  const int nch = (int)blockDim.x / cols;
+  const int i = threadIdx.x;
+  if (i < cols * nch) {
+    const int col = i % cols, ch = i / cols;
+    const bool second = col >= 2 * C;
+    const float* part = second ? sb.cpart : sa.cpart;
+    const int gc = second ? sb.gc : sa.gc, cc = second ? col - 2 * C : col;
+    float s = 0.f;
+    for (int g0 = ch; g0 < gc; g0 += nch * kRecB) {
+      float v[kRecB];
+#pragma unroll
+      for (int j = 0; j < kRecB; ++j) {
+        const int g = g0 + j * nch;
+        v[j] = g < gc ? __ldcg(part + (size_t)g * 2 * C + cc) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kRecB; ++j) s += v[j];
+    }
+    scratch[ch * cols + col] = s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    const bool second = j >= C;
+    const int c = second ? j - C : j;
+    const StatSrc& st = second ? sb : sa;
+    float* tbl = second ? tbl_b : tbl_a;
+    double s1 = 0.0, s2 = 0.0;
+    for (int ch = 0; ch < nch; ++ch) {
+      s1 += (double)scratch[ch * cols + (second ? 2 * C : 0) + 2 * c];
+      s2 += (double)scratch[ch * cols + (second ? 2 * C : 0) + 2 * c + 1];
     }
     const double mean = s1 * (double)st.inv_m;
     double var = s2 * (double)st.inv_m - mean * mean;

@@ -92,8 +92,8 @@ __device__ __forceinline__ void conv_fwd_body(const FwdArgs& a, const int vb, co
       }
     }
     // BN tables of the layers this tile reads, summed from the producers' per-cluster records (tcr_bn.cuh)
-    if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
-    if (res && a.shortcut.kind == 1) bn_table_build(a.shortcut.st, a.shortcut.bnf, a.cin, tbl_sh, red, vb == 0);
+    if (res && a.shortcut.kind == 1) bn_table_build2(a.in.st, a.in.bnf, tbl_in, a.shortcut.st, a.shortcut.bnf, tbl_sh, a.cin, red, vb == 0);
+    else if (a.in_kind != 0) bn_table_build(a.in.st, a.in.bnf, a.cin, tbl_in, red, vb == 0);
     if (w.row < rows) {
       int u = w.row / a.t_in, t = w.row - u * a.t_in;
       Chan4 kin, ksh;
@@ -303,12 +303,26 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, const int vb, const
   const bool sh_bn = a.shortcut.kind == 1;
   const size_t base = (size_t)u0 * TC;
 
-  bn_table_build(a.in.st, a.in.bnf, C, tb, red, vb == 0);
-  if (sh_bn) bn_table_build(a.shortcut.st, a.shortcut.bnf, C, td, red, vb == 0);
+  // the CTA's utterances are one contiguous span; its first rows are requested before the tables are summed
+  constexpr int PF = 2;
+  float4 pyb[PF], psh[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const int e = 4 * (tid + i * kHeadThreads);
+    pyb[i] = psh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < nu * TC) { pyb[i] = ld4(a.in.data + base + e); psh[i] = ld4(a.shortcut.data + base + e); }
+  }
+  if (sh_bn) bn_table_build2(a.in.st, a.in.bnf, tb, a.shortcut.st, a.shortcut.bnf, td, C, red, vb == 0);
+  else bn_table_build(a.in.st, a.in.bnf, C, tb, red, vb == 0);
 #pragma unroll 1
   for (int i = tid; i < C * NC; i += kHeadThreads) s_wfc[i] = __ldg(a.wfc + i);
-#pragma unroll 2
-  for (int e = 4 * tid; e < nu * TC; e += 4 * kHeadThreads) {     // the CTA's utterances are one contiguous span
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const int e = 4 * (tid + i * kHeadThreads);
+    if (e < nu * TC) { st4(syb + e, pyb[i]); st4(ssh + e, psh[i]); }
+  }
+#pragma unroll 1
+  for (int e = 4 * (tid + PF * kHeadThreads); e < nu * TC; e += 4 * kHeadThreads) {
     st4(syb + e, ld4(a.in.data + base + e));
     st4(ssh + e, ld4(a.shortcut.data + base + e));
   }
