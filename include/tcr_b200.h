@@ -189,6 +189,13 @@ int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr, int64_t* 
  * (128 bytes, ncclUniqueId) is created on rank 0 and distributed by the host (torch.distributed). */
 int tcr_comm_unique_id(void* id128);
 int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int32_t world_size);
+/* Peer-memory gradient exchange over NVLink / NVSwitch (optional, same node, world_size <= 8): every rank exports two CUDA IPC
+ * handles (128 bytes: its double-buffered flat gradient and its arrival flags), the host gathers all ranks' handles (rank-major,
+ * world_size x 128 bytes) and every rank attaches them.  From then on the update kernel of tcr_train_step announces its gradient
+ * in every peer's flag array, waits for all ranks' flags and sums the ranks' gradients itself (fixed rank order: replicas stay
+ * bit-identical) — compute and collective in ONE kernel, no ncclAllReduce launch in the step. */
+int tcr_comm_p2p_export(tcr_handle* h, void* handles128);
+int tcr_comm_p2p_attach(tcr_handle* h, const void* all_handles, int32_t rank, int32_t world_size);
 int tcr_comm_destroy(tcr_handle* h);
 
 /* Measured fp32 FMA peak of the device the handle lives on (TFLOP/s), used as the compute-roofline

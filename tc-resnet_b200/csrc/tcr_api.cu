@@ -621,7 +621,7 @@ extern "C" int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr
   };
   if (s == "timeline" && h->d_timeline) return ret((float*)h->d_timeline, 2 * 16 * 8192);   // int64 viewed as float pairs
   if (s == "features") return ret(h->d_feat, n * h->frames * h->features);
-  if (s == "grads") return ret(h->d_grads, h->n_train);
+  if (s == "grads") return ret(h->p2p.attached && h->world > 1 ? h->p2p.grads + (size_t)(h->p2p.step & 1u) * h->n_train : h->d_grads, h->n_train);
   if (s == "logits") return ret(h->d_logits, n * h->cfg.num_classes);
   if (s == "probs") return ret(h->d_probs, n * h->cfg.num_classes);
   const size_t colon = s.find(':');
@@ -654,6 +654,16 @@ extern "C" int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int
   if (!h || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(TCR_ERR_INVALID, "bad comm arguments");
   int rc = comm_init(h, id128, rank, world_size);
   return rc ? fail(rc, "ncclCommInitRank failed: %s", comm_error()) : TCR_OK;
+}
+extern "C" int tcr_comm_p2p_export(tcr_handle* h, void* handles128) {
+  if (!h || !handles128) return fail(TCR_ERR_INVALID, "NULL argument");
+  int rc = comm_p2p_export(h, handles128);
+  return rc ? fail(rc, "peer-memory export failed: %s", comm_error()) : TCR_OK;
+}
+extern "C" int tcr_comm_p2p_attach(tcr_handle* h, const void* all_handles, int32_t rank, int32_t world_size) {
+  if (!h || !all_handles || world_size < 1 || rank < 0 || rank >= world_size) return fail(TCR_ERR_INVALID, "bad comm arguments");
+  int rc = comm_p2p_attach(h, all_handles, rank, world_size);
+  return rc ? fail(rc, "peer-memory attach failed: %s", comm_error()) : TCR_OK;
 }
 extern "C" int tcr_comm_destroy(tcr_handle* h) {
   if (!h) return TCR_OK;

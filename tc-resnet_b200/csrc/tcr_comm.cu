@@ -21,6 +21,9 @@ int comm_unique_id(void*) { snprintf(g_comm_err, sizeof(g_comm_err), "no NCCL in
 int comm_init(tcr_handle*, const void*, int, int) { return comm_unique_id(nullptr); }
 void comm_destroy(tcr_handle*) {}
 int comm_allreduce_sum(tcr_handle*, float*, int64_t, cudaStream_t) { return TCR_ERR_COMM; }
+int comm_p2p_export(tcr_handle*, void*) { return comm_unique_id(nullptr); }
+int comm_p2p_attach(tcr_handle*, const void*, int, int) { return comm_unique_id(nullptr); }
+void comm_p2p_destroy(tcr_handle*) {}
 #else
 
 typedef struct ncclComm* ncclComm_t;
@@ -89,11 +92,67 @@ int comm_init(tcr_handle* h, const void* id128, int rank, int world) {
   return 0;
 }
 
+void comm_p2p_destroy(tcr_handle* h);
 void comm_destroy(tcr_handle* h) {
+  comm_p2p_destroy(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
   h->comm = nullptr;
   h->world = 1;
   h->rank = 0;
+}
+
+// ---- peer-memory exchange: every rank maps every other rank's gradient buffer and flag array through CUDA IPC ----
+// handles: [0, 64) cudaIpcMemHandle_t of `grads`, [64, 128) of `flags`.
+static int cuda_fail(const char* what, cudaError_t e) {
+  snprintf(g_comm_err, sizeof(g_comm_err), "%s: %s", what, cudaGetErrorString(e));
+  return TCR_ERR_COMM;
+}
+int comm_p2p_export(tcr_handle* h, void* handles128) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  auto& p = h->p2p;
+  cudaError_t e;
+  if (!p.grads) {
+    if ((e = cudaMalloc((void**)&p.grads, (size_t)2 * h->n_train * sizeof(float))) != cudaSuccess) return cuda_fail("cudaMalloc(p2p grads)", e);
+    if ((e = cudaMalloc((void**)&p.flags, 64 * sizeof(unsigned))) != cudaSuccess) return cuda_fail("cudaMalloc(p2p flags)", e);
+    cudaMemset(p.grads, 0, (size_t)2 * h->n_train * sizeof(float));
+    cudaMemset(p.flags, 0, 64 * sizeof(unsigned));
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t hg, hf;
+  if ((e = cudaIpcGetMemHandle(&hg, p.grads)) != cudaSuccess) return cuda_fail("cudaIpcGetMemHandle", e);
+  if ((e = cudaIpcGetMemHandle(&hf, p.flags)) != cudaSuccess) return cuda_fail("cudaIpcGetMemHandle", e);
+  memcpy(handles128, &hg, 64);
+  memcpy((char*)handles128 + 64, &hf, 64);
+  return 0;
+}
+int comm_p2p_attach(tcr_handle* h, const void* all_handles, int rank, int world) {
+  auto& p = h->p2p;
+  if (!p.grads || world < 1 || world > 8) { snprintf(g_comm_err, sizeof(g_comm_err), "p2p: export first, world <= 8"); return TCR_ERR_COMM; }
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { p.peer_grads[r] = p.grads; p.peer_flags[r] = p.flags; continue; }
+    cudaIpcMemHandle_t hg, hf;
+    memcpy(&hg, (const char*)all_handles + (size_t)r * 128, 64);
+    memcpy(&hf, (const char*)all_handles + (size_t)r * 128 + 64, 64);
+    cudaError_t e;
+    if ((e = cudaIpcOpenMemHandle((void**)&p.peer_grads[r], hg, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return cuda_fail("cudaIpcOpenMemHandle(grads)", e);
+    if ((e = cudaIpcOpenMemHandle((void**)&p.peer_flags[r], hf, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return cuda_fail("cudaIpcOpenMemHandle(flags)", e);
+  }
+  h->rank = rank;
+  h->world = world;
+  p.attached = 1;
+  p.step = 0;
+  return 0;
+}
+void comm_p2p_destroy(tcr_handle* h) {
+  auto& p = h->p2p;
+  for (int r = 0; r < 8; ++r) {
+    if (p.peer_grads[r] && p.peer_grads[r] != p.grads) cudaIpcCloseMemHandle(p.peer_grads[r]);
+    if (p.peer_flags[r] && p.peer_flags[r] != p.flags) cudaIpcCloseMemHandle(p.peer_flags[r]);
+    p.peer_grads[r] = nullptr; p.peer_flags[r] = nullptr;
+  }
+  if (p.grads) cudaFree(p.grads);
+  if (p.flags) cudaFree(p.flags);
+  p.grads = nullptr; p.flags = nullptr; p.attached = 0;
 }
 
 int comm_allreduce_sum(tcr_handle* h, float* buf, int64_t count, cudaStream_t s) {

@@ -46,6 +46,9 @@ int comm_unique_id(void* id128);
 int comm_init(tcr_handle* h, const void* id128, int rank, int world);
 void comm_destroy(tcr_handle* h);
 int comm_allreduce_sum(tcr_handle* h, float* buf, int64_t count, cudaStream_t s);
+int comm_p2p_export(tcr_handle* h, void* handles128);
+int comm_p2p_attach(tcr_handle* h, const void* all_handles, int rank, int world);
+void comm_p2p_destroy(tcr_handle* h);
 const char* comm_error();
 
 }  // namespace tcr

@@ -85,13 +85,59 @@ struct UpdateArgs {
   float* grads_out;       // may be null: scaled gradient actually applied
   int apply;
   int param_blocks;
+  // peer-memory exchange (world > 1 with tcr_comm_p2p_attach): every rank's gradient buffer and flag array as mapped here
+  int p2p_world, p2p_rank;
+  unsigned p2p_step;
+  const float* peer_grads[8];
+  unsigned* peer_flags[8];
 };
+
+// System-scope flag accesses for the cross-GPU arrival barrier.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+#ifndef TCR_EMU
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+#ifndef TCR_EMU
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *p;
+#endif
+}
 
 __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
   pdl_wait();
+  if (a.p2p_world > 1) {
+    // Cross-GPU arrival barrier in peer memory.  The gradient of this rank is complete (previous kernel); block 0 announces it
+    // in every rank's flag array, every CTA waits until all ranks have announced this step.  A rank cannot be more than one
+    // step ahead of the slowest one, and the gradient buffers alternate with the step parity, so nobody overwrites what a
+    // peer is still reading.
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) {
+        __threadfence_system();
+        for (int r = 0; r < a.p2p_world; ++r) st_release_sys(a.peer_flags[r] + a.p2p_rank, a.p2p_step);
+      }
+      const unsigned* mine = a.peer_flags[a.p2p_rank];
+      for (int r = 0; r < a.p2p_world; ++r)
+        while ((int)(ld_acquire_sys(mine + r) - a.p2p_step) < 0) __nanosleep(100);
+    }
+    __syncthreads();
+  }
   const int64_t p = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
   if (p < a.total) {
-    const float g = a.grads[p] * a.grad_scale;
+    float gsum;
+    if (a.p2p_world > 1) {
+      gsum = 0.f;
+      for (int r = 0; r < a.p2p_world; ++r) gsum += __ldcv(a.peer_grads[r] + p);     // fixed rank order: replicas stay identical
+    } else {
+      gsum = a.grads[p];
+    }
+    const float g = gsum * a.grad_scale;
     if (a.grads_out) a.grads_out[p] = g;
     if (a.apply) {
       const float m = fmaf(a.slots[p], a.momentum, g);     // accum = accum * momentum + grad
@@ -191,8 +237,11 @@ static int fc_segment(const tcr_handle* h) { return (int)h->convs.size() * 3; }
 int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   const int blocks = (int)((h->n_train + kOptThreads - 1) / kOptThreads);
   if (blocks > 4096) { set_error("parameter count too large for the l2 partial buffer"); return TCR_ERR_UNSUPPORTED; }
+  const bool p2p = h->p2p.attached && h->world > 1;
+  if (p2p) ++h->p2p.step;
+  float* grads = p2p ? h->p2p.grads + (size_t)(h->p2p.step & 1u) * h->n_train : h->d_grads;
   GradArgs ga{h->d_segs, h->n_segs, h->n_train, fc_segment(h), h->d_dwfc_part, head_groups(a->n), a->params, a->weight_decay,
-              h->d_grads, h->d_l2part};
+              grads, h->d_l2part};
   if (h->rec) {
     rec_grad(h, ga, blocks);
     int rc0 = rec_launch(h, s);
@@ -200,13 +249,18 @@ int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s) {
   } else {
     TCR_LAUNCH("grad_finalize", grad_finalize_kernel, dim3(blocks), dim3(kOptThreads), 0, s, ga);
   }
-  if (h->comm && h->world > 1) {
+  if (!p2p && h->comm && h->world > 1) {
     int rc = comm_allreduce_sum(h, h->d_grads, h->n_train, s);
     if (rc) return rc;
   }
   UpdateArgs u;
   u.total = h->n_train;
-  u.params = a->params; u.slots = a->slots; u.grads = h->d_grads; u.moving = a->moving;
+  u.params = a->params; u.slots = a->slots; u.grads = grads; u.moving = a->moving;
+  u.p2p_world = p2p ? h->world : 1; u.p2p_rank = h->rank; u.p2p_step = h->p2p.step;
+  for (int r = 0; r < 8; ++r) {
+    u.peer_grads[r] = p2p && r < h->world ? h->p2p.peer_grads[r] + (size_t)(h->p2p.step & 1u) * h->n_train : nullptr;
+    u.peer_flags[r] = p2p && r < h->world ? h->p2p.peer_flags[r] : nullptr;
+  }
   u.lr = a->learning_rate; u.momentum = a->momentum; u.weight_decay = a->weight_decay;
   u.one_minus_decay = (float)(1.0 - (double)h->cfg.bn_decay);
   u.grad_scale = 1.0f / (float)h->world;

@@ -69,6 +69,16 @@ struct tcr_handle {
   int64_t workspace_bytes = 0;
   // data-parallel
   void* comm = nullptr; int rank = 0, world = 1;
+  // peer-memory gradient exchange (csrc/tcr_comm.cu): own double-buffered flat gradient + arrival flags, and every rank's
+  // mappings of them (CUDA IPC).  When attached, the update kernel sums the ranks' gradients itself and NCCL is not used.
+  struct P2P {
+    int attached = 0;
+    float* grads = nullptr;          // [2][n_train] this rank's flat gradient, buffer = step parity
+    unsigned* flags = nullptr;       // [kMaxPeers] flags[r] = last step whose gradient rank r has finished
+    float* peer_grads[8] = {};       // every rank's `grads` as mapped here (own entry = own pointer)
+    unsigned* peer_flags[8] = {};
+    unsigned step = 0;
+  } p2p;
   int last_n = 0;
   int loss_gc = 0;            // cross-entropy records left by the head launch of this call
   size_t persist_smem = 0;    // dynamic shared memory the persistent kernel is opted in to on this handle's device

@@ -213,6 +213,28 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(self.lib, self.lib.tcr_comm_init(self._h, idbuf, rank, world), "tcr_comm_init")
         self.world_size = world
+        self.exchange = "nccl"
+        # Peer-memory exchange (same node, <= 8 ranks): the update kernel sums the ranks' gradients itself over NVLink
+        # (include/tcr_b200.h, tcr_comm_p2p_*).  Every rank must take the same branch, hence the all_gather of the outcome.
+        import os
+        if world <= 8 and os.environ.get("TCR_P2P", "1") != "0":
+            mine = (C.c_char * 128)()
+            with torch.cuda.device(self.device):
+                ok = self.lib.tcr_comm_p2p_export(self._h, mine) == 0
+            gathered = [None] * world
+            dist.all_gather_object(gathered, bytes(mine) if ok else None)
+            if all(g is not None for g in gathered):
+                table = (C.c_char * (128 * world)).from_buffer_copy(b"".join(gathered))
+                with torch.cuda.device(self.device):
+                    ok = self.lib.tcr_comm_p2p_attach(self._h, table, rank, world) == 0
+            else:
+                ok = False
+            outcome = [None] * world
+            dist.all_gather_object(outcome, bool(ok))
+            if all(outcome):
+                self.exchange = "peer-memory"
+            elif ok:                                  # someone failed to map a peer: everybody stays on NCCL
+                raise L.TcrError("peer-memory attach succeeded on some ranks only; set TCR_P2P=0")
 
     # ------------------------------------------------------------------ accounting
     def launch_count(self) -> int:

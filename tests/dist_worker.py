@@ -79,11 +79,17 @@ def main():
         expect = O.flatten_vars(spec, params, np.float64) - lr * ref
         perr = np.abs(p.cpu().numpy() - expect).max() / np.abs(expect).max()
         assert perr < 1e-4, perr
+        for step in range(1, 4):                      # more steps: the peer-memory exchange alternates two gradient buffers
+            eng.train_step(torch.from_numpy(wav[lo:hi]).to(dev), torch.from_numpy(onehot[lo:hi]).to(dev), p, sl, mv, lr, mom, wd,
+                           dropout_seed=step)
+        torch.cuda.synchronize()
         gathered = [torch.zeros_like(p) for _ in range(world)]
         dist.all_gather(gathered, p)
         assert all(torch.equal(x, gathered[0]) for x in gathered), "replicas diverged"
+        assert torch.isfinite(p).all()
         if rank == 0:
-            print(f"nccl world={world}: grad rel err {err:.2e}, params rel err {perr:.2e}, replicas bit-identical")
+            print(f"exchange={eng.exchange} world={world}: grad rel err {err:.2e}, params rel err {perr:.2e}, replicas bit-identical "
+                  f"after 4 steps")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -74,6 +74,7 @@ int lane_id();
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::syncwarp(); }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 static inline void __nanosleep(unsigned) {}
 static inline void __threadfence_block() {}
 
@@ -109,6 +110,7 @@ static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned old = *p;
 template <class T> static inline T atomicExch(T* p, T v) { T old = *p; *p = v; return old; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline T __ldcv(const T* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }

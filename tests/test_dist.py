@@ -8,10 +8,10 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _torchrun(mode, nproc, port):
+def _torchrun(mode, nproc, port, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "dist_worker.py"), mode]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
 
 
 def test_data_parallel_identity_gloo_world2():
@@ -20,10 +20,13 @@ def test_data_parallel_identity_gloo_world2():
 
 
 @pytest.mark.gpu
-def test_nccl_gradient_allreduce_matches_oracle():
+@pytest.mark.parametrize("exchange,env", [("peer-memory", {}), ("nccl", {"TCR_P2P": "0"})])
+def test_gradient_exchange_matches_oracle(exchange, env):
+    """Both exchanges of the data-parallel step: the update kernel summing the ranks' gradients from peer memory (default on
+    one node) and the ncclAllReduce fallback; 4 steps, averaged gradient vs the oracle's shard-wise mean, identical replicas."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    r = _torchrun("nccl", min(torch.cuda.device_count(), 8), 29612)
+    r = _torchrun("nccl", min(torch.cuda.device_count(), 8), 29612 if exchange == "nccl" else 29613, env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "replicas bit-identical" in r.stdout
+    assert "replicas bit-identical" in r.stdout and f"exchange={exchange}" in r.stdout, r.stdout[-500:]
