@@ -6,7 +6,7 @@
 //   out_i     [N, T'_i, C_i]  per block       relu(bn(y_b) + shortcut), materialised by its first consumer
 //   g_L       [N, T'_L, C_L]                  dLoss/d(BN output) after the ReLU mask (backward)
 //   bnf_L     [4][C_L]                        finalised BN table: mean, rstd, scale=gamma*rstd, beta
-//   fpart/bpart [G][C][2]                     per-CTA partial statistics (deterministic two-level reduce)
+//   fpart/bpart [records][C][2]               partial BatchNorm sums, one record per 8-CTA cluster (tcr_bn.cuh)
 //   dwpart_L  [R][k*C_in*C_out]               per-row-chunk partial weight gradients
 // Activations are never stored post-BN/ReLU: consumers re-apply the per-channel table on load.
 #pragma once

@@ -2,11 +2,13 @@
 //
 // Replaces the gradient graph slim.learning.create_train_op builds (helper/trainer.py:199-211):
 // Conv2DBackpropInput / Conv2DBackpropFilter / FusedBatchNormGrad / ReluGrad per layer.
-//   conv_bwd_data_kernel<K>   : dy = FusedBatchNormGrad(dz) is formed while staging the tile (two per-channel
-//                               sums s1 = sum dz, s2 = sum dz*xhat come finalised from the producer kernel);
+//   conv_bwd_data_kernel<K>   : dy = FusedBatchNormGrad(dz) is formed while staging the tile (the two per-channel
+//                               sums s1 = sum dz, s2 = sum dz*xhat are added up from the producer kernel's per-cluster
+//                               records in the prologue, tcr_bn.cuh);
 //                               dx = conv^T(dy, W) [+ the block's 1x1 shortcut conv^T] [+ identity gradient];
 //                               epilogue applies the consumer-side ReLU mask, writes the next dz and emits the
-//                               per-CTA partial (s1, s2) of the layer(s) below; the last CTA finalises them.
+//                               partial (s1, s2) of the layer(s) below, reduced over the 8 CTAs of a thread-block cluster
+//                               through distributed shared memory into one record per cluster.
 //                               Stride-2 transposed convs are split by output-row parity so no FMA is spent on
 //                               the zeros of a dilated gradient.
 //   conv_bwd_weight_kernel<K> : dW[k,ci,co] = sum_rows x[row+k, ci] * dy[row, co]; each thread owns 2 ci x 4 co

@@ -4,7 +4,8 @@
 // Replaces tc_resnet() (audio_nets/tc_resnet.py:6-54) under TCResNet_arg_scope (:102-123):
 //   conv_fwd_kernel<K>  : [k,1] temporal conv (+ the block's 1x1/stride-2 shortcut conv from the same staged
 //                         input tile), BN+ReLU(+residual) of the PRODUCER applied while staging the tile,
-//                         per-CTA BatchNorm partial statistics in the epilogue, last CTA finalises the table.
+//                         BatchNorm partial sums in the epilogue, reduced over the 8 CTAs of a thread-block cluster through
+//                         distributed shared memory; the CONSUMER kernel turns the records into the table (tcr_bn.cuh).
 //   head_kernel         : residual + ReLU + global average pool + dropout + fc + softmax + cross-entropy and,
 //                         for training, dlogits -> gradient of the last block + fc weight-gradient partials.
 // A CTA owns U whole utterances, so SAME padding is a few zero rows of the shared-memory tile.

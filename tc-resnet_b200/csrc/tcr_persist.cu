@@ -1,10 +1,10 @@
 // tcr_persist.cu — the whole training step (all layers forward, head, backward-data chain, weight gradients,
 // gradient finalisation) as ONE persistent cooperative kernel.
 //
-// Why: with ~10 us of real work per layer, kernel boundaries dominated (measured with tools/timeline.py: ~5 us launch gap
-// + ~11 us serial "last CTA finalises" tail per layer).  Here the existing kernel bodies run as PHASES over virtual CTAs;
-// a grid barrier replaces the kernel boundary and the BatchNorm statistics / BN-backward sums are finalised by a
-// distributed phase (one warp per channel, lanes stride the per-CTA partials, fp64 Chan combination, fixed order).
+// OPT-IN (TCR_PERSISTENT=1) and currently slower than the default multi-kernel path: kept as the
+// starting point for a cooperative + cluster launch.  The kernel bodies of the multi-kernel path run as PHASES over virtual
+// CTAs; a grid barrier replaces the kernel boundary and the BatchNorm statistics / BN-backward sums are finalised by a
+// distributed phase (one warp per channel, lanes stride the per-CTA records, plain sums in a fixed order).
 // The host records the phases with the same code that would launch the kernels one by one (h->rec != nullptr).
 // Launched cooperatively (all CTAs co-resident: 2 per SM) so the spin barrier cannot deadlock.
 #include <stdlib.h>
@@ -21,7 +21,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // Distributed finalize: one warp per channel; lanes stride the per-CTA partials in batches of kFinB independent loads
-// (the unbatched version was a 7 us latency chain per phase), fp64 Chan combination, fixed order -> deterministic.
+// (the unbatched version was a 7 us latency chain per phase), fixed order -> deterministic.
 constexpr int kFinB = 8;
 __device__ __forceinline__ void fin_fwd_phase(const FinFwd& F, int b, int nb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
