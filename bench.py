@@ -44,9 +44,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
-    ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer"],
+    ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer", "augment"],
                     help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point); "
-                         "infer: evaluation-mode forward from wav (config 1 with --batch 1: latency)")
+                         "infer: evaluation-mode forward from wav (config 1 with --batch 1: latency); "
+                         "augment: the device input stage (SURVEY.md 8f row 1), an HBM-bound elementwise pass")
     return ap.parse_args()
 
 
@@ -458,6 +459,51 @@ def run_infer(a):
           "argmax_first": int(logits[0].argmax())})
 
 
+def run_augment(a):
+    """Device input stage (tcr_augment_pcm16): int16 clips -> decoded, shifted, background-mixed, clipped fp32 wav."""
+    import numpy as np
+    import torch
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.engine import Engine
+    from tcresnet_b200.datasets import device_input_stage as D
+    dev = torch.device("cuda", 0)
+    n, clip = a.batch, 16000
+    eng = Engine(max_batch=n)
+    rng = np.random.RandomState(0)
+    bg_lengths = [960000] * 6                          # six one-minute background recordings, as in the dataset
+    background = (torch.rand(sum(bg_lengths), device=dev) * 2 - 1) * 0.5
+    rot = max(a.rotate, 4)
+    pcm = [torch.randint(-32768, 32768, (n, clip), dtype=torch.int16, device=dev) for _ in range(rot)]
+    clips = [D.pack(D.draw_clips(rng, [clip] * n, rng.uniform(size=n) < 0.1, clip, bg_lengths), dev) for _ in range(rot)]
+    outs = [torch.empty(n, clip, device=dev) for _ in range(rot)]
+    for i in range(max(a.warmup, 3)):
+        eng.augment(pcm[i % rot], clips[i % rot], background, out=outs[i % rot])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        eng.augment(pcm[i % rot], clips[i % rot], background, out=outs[i % rot])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = n * clip * (2 + 4 + 4)                       # int16 read + background read + fp32 write per sample
+    gbs = alg / (ms * 1e-3) / 1e9
+    emit({"metric": "utterances/sec (device input stage: decode + shift + background mix + clip)", "value": n / (ms * 1e-3),
+          "unit": "utterances/sec", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+          "config": {"workload": f"tcr_augment_pcm16, batch {n} clips of 16000 samples, 6 background recordings of 60 s",
+                     "l2": f"inputs/outputs rotate over {rot} buffers ({rot * alg / 1e6:.0f} MB > 126 MB L2)"},
+          "roofline": {"bound": "hbm", "kernel": "augment", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                       "traffic": None, "algorithmic_bytes_per_launch": alg},
+          "gpu_launches": eng.launch_count()})
+
+
 def run_dscnn(a):
     """Config 5: DS-CNN-S forward, MFCC 49x40 features resident in HBM, batch 512, one B200 (2-D-conv comparison point)."""
     import torch
@@ -514,6 +560,8 @@ def main():
         return run_dscnn(a)
     if a.workload == "infer":
         return run_infer(a)
+    if a.workload == "augment":
+        return run_augment(a)
     if a.impl == "reference":
         run_reference(a)
     else:

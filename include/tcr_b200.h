@@ -154,6 +154,24 @@ int tcr_mfcc_forward(tcr_handle* h, const float* wav, float* features, int32_t n
 /* Same front-end on int16 PCM samples [n, clip_samples] (decode_wav's 1/32768 scaling fused into the framing). */
 int tcr_mfcc_forward_pcm16(tcr_handle* h, const int16_t* pcm, float* features, int32_t n, tcr_stream stream);
 
+/* The per-clip input stage in front of the front-end, on the device (SURVEY.md 8f "next" row 1): decode_wav scaling, crop /
+ * zero-pad to clip_samples, silent clips, time shift with zero fill, background mix and clip to [-1,1]
+ * (datasets/augmentation_factory.py:30-211 as called from datasets/audio_data_wrapper.py:37-58).  The host makes the random
+ * draws and passes them per clip, so the output is bit-identical to the host stage for the same draws.
+ *   pcm        device int16 [n, pcm_stride]: the wav files' samples (row i holds clips[i].length valid samples)
+ *   clips      device [n] tcr_augment_clip
+ *   background device float: the background recordings concatenated (NULL: no mixing); bg_offset indexes into it
+ *   wav_out    device float [n, clip_samples], what tcr_mfcc_forward / tcr_train_step take as TCR_INPUT_WAV_F32 */
+typedef struct tcr_augment_clip {
+  int32_t length;      /* valid int16 samples of the clip's row (longer clips are cropped, shorter zero-padded) */
+  int32_t shift;       /* _shift_audio: out[i] = in[i - shift], zero outside; 0 for anchored_slice_or_pad */
+  int32_t silent;      /* 1: the "" filename of a synthesised silent sample: zeros before the background mix */
+  float   bg_volume;   /* 0 when the background is not mixed in (probability 1 - background_frequency, or evaluation) */
+  int64_t bg_offset;   /* start of the random crop inside `background` (recording start + crop offset); < 0: none */
+} tcr_augment_clip;
+int tcr_augment_pcm16(tcr_handle* h, const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips,
+                      const float* background, float* wav_out, int32_t n, tcr_stream stream);
+
 /* Forward pass.  is_training == 0: evaluate_audio.py path (BN moving statistics, dropout identity;
  * helper/base.py:52-125).  is_training == 1: the training graph's forward (batch statistics, dropout)
  * as run by the trainer's in-loop evaluation (helper/trainer.py:436-460); `moving` is not updated.

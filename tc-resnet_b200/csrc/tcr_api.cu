@@ -452,6 +452,18 @@ extern "C" int tcr_mfcc_forward_pcm16(tcr_handle* h, const int16_t* pcm, float* 
   return mfcc_run(h, pcm, 1, features, n, stream);
 }
 
+extern "C" int tcr_augment_pcm16(tcr_handle* h, const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips,
+                                 const float* background, float* wav_out, int32_t n, tcr_stream stream) {
+  pdl_chain_reset();
+  if (!h || !pcm || !clips || !wav_out) return fail(TCR_ERR_INVALID, "NULL argument");
+  TCR_TRY(check_n(h, n));
+  if (pcm_stride < 1) return fail(TCR_ERR_INVALID, "pcm_stride must be positive");
+  if (((uintptr_t)wav_out & 15) != 0) return fail(TCR_ERR_INVALID, "wav_out must be 16-byte aligned");
+  augment_launch(pcm, pcm_stride, clips, background, wav_out, h->cfg.clip_samples, n, (cudaStream_t)stream);
+  TCR_CUDA(cudaGetLastError());
+  return TCR_OK;
+}
+
 extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, const float* params,
                            const float* moving, int32_t n, int32_t is_training, uint64_t dropout_seed,
                            const float* dropout_mask, const float* onehot, float weight_decay, float* logits,

@@ -18,6 +18,8 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
 // Backward-data chain + all weight-gradient kernels; leaves per-layer partial sums in the workspace.
 int cluster_size(tcr_handle* h);
 StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n);
+int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, float* out, int clip,
+                   int n, cudaStream_t s);
 int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s);
 

@@ -159,6 +159,19 @@ class Engine:
                     "tcr_mfcc_forward")
         return out
 
+    def augment(self, pcm: torch.Tensor, clips: torch.Tensor, background: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device input stage (datasets/augmentation_factory.py): int16 clips [n, stride] + per-clip draws -> fp32 wav
+        [n, clip_samples].  `clips`: uint8 CUDA tensor holding n packed tcr_augment_clip records (24 bytes each, see
+        include/tcr_b200.h); `background`: the background recordings concatenated (fp32) or None."""
+        n = pcm.shape[0]
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+        assert clips.is_cuda and clips.dtype == torch.uint8 and clips.numel() == 24 * n
+        out = out if out is not None else self._f32(n, self.cfg.clip_samples)
+        L.check(self.lib, self.lib.tcr_augment_pcm16(self._h, pcm.data_ptr(), pcm.shape[1], clips.data_ptr(), self._ptr(background),
+                                                     self._ptr(out), n, self._stream), "tcr_augment_pcm16")
+        return out
+
     def forward(self, inputs: torch.Tensor, params: torch.Tensor, moving: Optional[torch.Tensor] = None,
                 is_training: bool = False, onehot: Optional[torch.Tensor] = None, weight_decay: float = 0.0,
                 dropout_seed: int = 0, dropout_mask: Optional[torch.Tensor] = None, input_is_features: bool = False):

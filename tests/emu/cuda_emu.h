@@ -114,6 +114,8 @@ template <class T> static inline T __ldcv(const T* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }   // no contraction into an fma
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline unsigned __float_as_uint(float f) { return emu_unbits<unsigned>(emu_bits(f)); }
 static inline float __uint_as_float(unsigned u) { return emu_unbits<float>(u); }
 static inline float __int_as_float(int u) { return emu_unbits<float>((unsigned)u); }

@@ -37,6 +37,9 @@ class NumpyBackend:
         a = np.asarray(a)
         return np.ascontiguousarray(a, dtype=np.int16 if a.dtype == np.int16 else np.float32).copy()
 
+    def upload_bytes(self, a):
+        return np.ascontiguousarray(a, np.uint8).copy()
+
     def download(self, a):
         return np.array(a, copy=True)
 
@@ -69,6 +72,9 @@ class TorchBackend:
     def upload(self, a):
         a = np.asarray(a)
         return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.int16 if a.dtype == np.int16 else np.float32)).to(self.dev)
+
+    def upload_bytes(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, np.uint8).copy()).to(self.dev)
 
     def download(self, a):
         return a.detach().cpu().numpy()
@@ -133,6 +139,19 @@ class Engine:
         L.check(self.lib, fn(self.h, b.ptr(wav), b.ptr(feat), n, b.stream), "tcr_mfcc_forward")
         b.sync()
         return b.download(feat)
+
+    def augment(self, pcm_np, clips_np, background_np):
+        """tcr_augment_pcm16 through the C ABI: int16 clips + packed tcr_augment_clip records (+ background) -> fp32 wav."""
+        b = self.b
+        n = pcm_np.shape[0]
+        pcm = b.upload(np.ascontiguousarray(pcm_np, np.int16))
+        clips = b.upload_bytes(np.frombuffer(np.ascontiguousarray(clips_np).tobytes(), np.uint8))
+        bg = b.upload(background_np) if background_np is not None else None
+        out = b.empty(n, self.cfg.clip_samples)
+        L.check(self.lib, self.lib.tcr_augment_pcm16(self.h, b.ptr(pcm), pcm_np.shape[1], b.ptr(clips), b.ptr(bg), b.ptr(out), n, b.stream),
+                "tcr_augment_pcm16")
+        b.sync()
+        return b.download(out)
 
     def forward(self, inp_np, params_np, moving_np=None, is_features=False, is_training=False, seed=0, mask_np=None,
                 onehot_np=None, weight_decay=0.0):

@@ -1,0 +1,88 @@
+"""Device input stage (tcr_augment_pcm16) vs the NumPy restatement of datasets/augmentation_factory.py: bit-exact for the same
+random draws.  Kernel logic on the CPU emulator here, the sm_100a build under -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import augment_oracle as A
+from oracle import tcr_oracle as O
+from tcr_harness import Engine, NumpyBackend
+
+L = 16000
+
+
+def _case(seed, n, stride, with_bg=True):
+    rng = np.random.RandomState(seed)
+    pcm = rng.randint(-32768, 32768, size=(n, stride)).astype(np.int16)
+    bg_lengths = [L, 23000, 61234] if with_bg else []
+    background = (rng.uniform(-1, 1, size=int(sum(bg_lengths))).astype(np.float32)) if with_bg else None
+    clips = A.random_clips(rng, n, L, stride, bg_lengths)
+    return pcm, clips, background
+
+
+def _edge_clips(clips):
+    clips = clips.copy()
+    clips[0]["shift"], clips[0]["silent"], clips[0]["length"] = 1599, 0, 16000       # largest forward shift
+    clips[1]["shift"], clips[1]["silent"] = -1600, 0                                  # largest backward shift
+    clips[2]["silent"] = 1                                                            # synthesised silence (+ background)
+    clips[3]["length"], clips[3]["shift"], clips[3]["silent"] = 9000, 0, 0            # short recording: zero-padded
+    clips[4]["bg_volume"] = np.float32(1.0)                                           # forces the clip to [-1, 1] to act
+    return clips
+
+
+def _check(backend, seed, n, stride, with_bg=True):
+    eng = Engine(backend, max_batch=n)
+    pcm, clips, background = _case(seed, n, stride, with_bg)
+    if n >= 5:
+        clips = _edge_clips(clips)
+    got = eng.augment(pcm, clips, background)
+    ref = A.augment(pcm, clips, background, L)
+    assert got.dtype == np.float32 and got.shape == (n, L)
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+    assert got.min() >= -1.0 and got.max() <= 1.0
+    eng.close()
+    return got
+
+
+def test_emulated_input_stage_is_bit_exact():
+    b = NumpyBackend()
+    _check(b, 1, 6, 16000)
+    _check(b, 2, 5, 20000)                     # recordings longer than the clip are cropped
+    _check(b, 3, 2, 16000, with_bg=False)      # evaluation split: no background bank
+
+
+def test_oracle_matches_the_host_restatement_of_the_input_pipeline():
+    """The oracle and the host-side module that mirrors the reference's API agree sample for sample."""
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.datasets import augmentation_factory as H
+    rng = np.random.RandomState(5)
+    x = rng.uniform(-1, 1, L).astype(np.float32)
+    pcm = np.round(x * 32767).astype(np.int16)[None]
+    shifted = H.shift_audio(pcm[0].astype(np.float32) / np.float32(32768.0), np.random.RandomState(11))
+    amount = int(np.random.RandomState(11).randint(-1600, 1600))
+    clips = np.zeros(1, A.CLIP_DTYPE)
+    clips[0]["length"], clips[0]["shift"], clips[0]["bg_offset"] = L, amount, -1
+    assert np.array_equal(A.augment(pcm, clips, None, L)[0], shifted)
+
+
+def test_host_side_draws_use_the_abi_record_layout():
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.datasets import device_input_stage as D
+    assert D.CLIP_DTYPE == A.CLIP_DTYPE and D.CLIP_DTYPE.itemsize == 24
+    clips = D.draw_clips(np.random.RandomState(3), [16000, 12000, 20000], [False, True, False], L, [L, 40000])
+    assert (np.abs(clips["shift"]) <= 1600).all() and (clips["bg_offset"] >= 0).all() and (clips["bg_volume"] <= 0.1).all()
+    assert ((clips["bg_offset"] < L + 40000 - L + 1)).all()
+    ev = D.draw_clips(np.random.RandomState(3), [16000], [False], L, [], shift=False, is_training=False)
+    assert ev[0]["shift"] == 0 and ev[0]["bg_offset"] == -1
+
+
+@pytest.mark.gpu
+def test_cuda_input_stage_is_bit_exact_and_feeds_the_front_end():
+    from tcr_harness import TorchBackend
+    b = TorchBackend()
+    wav = _check(b, 7, 64, 16000)
+    _check(b, 8, 33, 17000)
+    _check(b, 9, 3, 16000, with_bg=False)
+    eng = Engine(b, max_batch=64)
+    feat = eng.mfcc(wav)
+    assert np.abs(feat - O.mfcc(wav.astype(np.float64), 640, 320)).max() / np.abs(feat).max() < 2e-5
+    eng.close()
