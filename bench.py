@@ -136,7 +136,7 @@ def calibrate_cpu_threads(a):
         step()
         t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
         best = min(best, (dt, t))
-        if dt > 4 * best[0]:                  # far past the optimum: more threads only get slower
+        if dt > 1.3 * best[0]:                # past the optimum: more threads only get slower (and the probes much longer)
             break
     _CPU_THREADS = best[1]
     return _CPU_THREADS
