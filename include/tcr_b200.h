@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCR_ABI_VERSION 2
+#define TCR_ABI_VERSION 3
 
 enum {
   TCR_OK = 0,
@@ -107,6 +107,7 @@ typedef struct tcr_param_desc {
   int64_t numel;
 } tcr_param_desc;
 
+struct tcr_augment_clip;
 /* Arguments of one training step == one `session.run(train_op)` of helper/trainer.py:312-321. */
 typedef struct tcr_step_args {
   const float* input;        /* wav [n, clip_samples] in [-1,1], features [n,T,F], or (cast) int16 PCM: see TCR_INPUT_* */
@@ -126,6 +127,12 @@ typedef struct tcr_step_args {
   float*       probs;        /* optional device [n, num_classes] softmax (output/softmax) */
   float*       grads;        /* optional device [num_trainable]: gradient of total_loss actually applied */
   int32_t      apply_update; /* 1: momentum update + BN moving update; 0: gradients only */
+  /* Optional device input stage in front of the front-end (TCR_INPUT_WAV_PCM16 only, see tcr_augment_pcm16): when `clips` is not
+   * NULL, `input` holds the wav files' int16 samples [n, pcm_stride] and the step first decodes / shifts / mixes / clips them
+   * into an internal fp32 buffer.  Zero-initialise these fields when the stage is not used. */
+  const struct tcr_augment_clip* clips;   /* [n]: device memory (tcr_train_step) / pinned host memory (tcr_train_step_host) */
+  const float* background;   /* device: concatenated background recordings, may be NULL */
+  int64_t      pcm_stride;   /* int16 samples per row of `input`; 0 = clip_samples; at most 2 * clip_samples */
 } tcr_step_args;
 
 int         tcr_abi_version(void);

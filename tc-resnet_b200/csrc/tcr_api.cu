@@ -496,7 +496,20 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
   const float* feat = a->input;
   if (a->input_is_features != TCR_INPUT_FEATURES) {
     if (a->input_is_features != TCR_INPUT_WAV_F32 && a->input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "unknown input kind %d", a->input_is_features);
-    TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, a->n, stream));
+    if (a->clips) {                  // device input stage first: int16 clips + per-clip draws -> fp32 wav (tcr_augment.cu)
+      if (a->input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "clips need TCR_INPUT_WAV_PCM16 input");
+      const int64_t stride = a->pcm_stride > 0 ? a->pcm_stride : h->cfg.clip_samples;
+      if (!h->d_aug) {
+        void* p = nullptr;
+        TCR_CUDA(cudaMalloc(&p, (size_t)h->cfg.max_batch * h->cfg.clip_samples * sizeof(float)));
+        h->allocs.push_back(p);
+        h->d_aug = (float*)p;
+      }
+      augment_launch((const int16_t*)a->input, stride, a->clips, a->background, h->d_aug, h->cfg.clip_samples, a->n, s);
+      TCR_TRY(mfcc_run(h, h->d_aug, 0, h->d_feat, a->n, stream));
+    } else {
+      TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, a->n, stream));
+    }
     feat = h->d_feat;
   }
   if (persist_enabled(h)) rec_begin(h);      // record the step's phases; net_update launches the persistent kernel
@@ -524,6 +537,7 @@ namespace {
 constexpr int kFeedDepth = 3;
 struct HostSlot {
   void* d_in = nullptr; float* d_hot = nullptr; float* d_loss = nullptr; float* h_loss = nullptr;
+  tcr_augment_clip* d_clips = nullptr;
   cudaEvent_t ready = nullptr, consumed = nullptr, done = nullptr;
 };
 struct HostFeedState {
@@ -539,6 +553,7 @@ static void hostfeed_destroy(tcr_handle* h) {
   for (auto& s : f->slot) {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_hot) cudaFree(s.d_hot);
+    if (s.d_clips) cudaFree(s.d_clips);
     if (s.d_loss) cudaFree(s.d_loss);
     if (s.h_loss) cudaFreeHost(s.h_loss);
     if (s.ready) cudaEventDestroy(s.ready);
@@ -559,6 +574,7 @@ static int hostfeed_get(tcr_handle* h, HostFeedState** out) {
     for (auto& s : f->slot) {
       TCR_CUDA(cudaMalloc(&s.d_in, in_bytes));
       TCR_CUDA(cudaMalloc((void**)&s.d_hot, (size_t)h->cfg.max_batch * h->cfg.num_classes * 4));
+      TCR_CUDA(cudaMalloc((void**)&s.d_clips, (size_t)h->cfg.max_batch * sizeof(tcr_augment_clip)));
       TCR_CUDA(cudaMalloc((void**)&s.d_loss, 2 * sizeof(float)));
       TCR_CUDA(cudaMallocHost((void**)&s.h_loss, 2 * sizeof(float)));
       TCR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
@@ -592,19 +608,25 @@ extern "C" int tcr_train_step_host(tcr_handle* h, const tcr_step_args* a, int32_
   size_t in_bytes;
   switch (a->input_is_features) {
     case TCR_INPUT_WAV_F32: in_bytes = (size_t)a->n * h->cfg.clip_samples * 4; break;
-    case TCR_INPUT_WAV_PCM16: in_bytes = (size_t)a->n * h->cfg.clip_samples * 2; break;
+    case TCR_INPUT_WAV_PCM16: {
+      const int64_t stride = (a->clips && a->pcm_stride > 0) ? a->pcm_stride : h->cfg.clip_samples;
+      if (stride > 2 * (int64_t)h->cfg.clip_samples) return fail(TCR_ERR_INVALID, "pcm_stride %lld exceeds 2 x clip_samples", (long long)stride);
+      in_bytes = (size_t)a->n * stride * 2;
+    } break;
     case TCR_INPUT_FEATURES: in_bytes = (size_t)a->n * h->frames * h->features * 4; break;
     default: return fail(TCR_ERR_INVALID, "unknown input kind %d", a->input_is_features);
   }
   if (f->submitted >= kFeedDepth) TCR_CUDA(cudaStreamWaitEvent(f->copy, sl.consumed, 0));   // the slot's previous step has read it
   TCR_CUDA(cudaMemcpyAsync(sl.d_in, a->input, in_bytes, cudaMemcpyHostToDevice, f->copy));
   TCR_CUDA(cudaMemcpyAsync(sl.d_hot, a->onehot, (size_t)a->n * h->cfg.num_classes * 4, cudaMemcpyHostToDevice, f->copy));
+  if (a->clips) TCR_CUDA(cudaMemcpyAsync(sl.d_clips, a->clips, (size_t)a->n * sizeof(tcr_augment_clip), cudaMemcpyHostToDevice, f->copy));
   TCR_CUDA(cudaEventRecord(sl.ready, f->copy));
   TCR_CUDA(cudaStreamWaitEvent(s, sl.ready, 0));
   tcr_step_args d = *a;
   d.input = (const float*)sl.d_in;
   d.onehot = sl.d_hot;
   d.losses = sl.d_loss;
+  if (a->clips) d.clips = sl.d_clips;          // the draws travel with the batch; the background bank is already on the device
   TCR_TRY(tcr_train_step(h, &d, stream));
   TCR_CUDA(cudaEventRecord(sl.consumed, s));
   TCR_CUDA(cudaMemcpyAsync(sl.h_loss, sl.d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -83,6 +83,7 @@ struct tcr_handle {
   int loss_gc = 0;            // cross-entropy records left by the head launch of this call
   size_t persist_smem = 0;    // dynamic shared memory the persistent kernel is opted in to on this handle's device
   int cluster = 0;            // CTAs per thread-block cluster of the conv / head launches (env TCR_CLUSTER, default 8)
+  float* d_aug = nullptr;      // [max_batch][clip_samples] fp32 output of the device input stage inside a step (lazy)
   void* hostfeed = nullptr;   // HostFeedState (tcr_api.cu): staging slots of tcr_train_step_host
   tcr::StepProgram* rec = nullptr;   // non-null while a training step is being recorded for the persistent kernel
   size_t rec_smem = 0; int persist = -1; int persist_grid = 0; unsigned* d_gridbar = nullptr;

@@ -190,10 +190,18 @@ class Engine:
                    moving: torch.Tensor, learning_rate: float, momentum: float = 0.9, weight_decay: float = 1e-4,
                    dropout_seed: int = 0, dropout_mask: Optional[torch.Tensor] = None, input_is_features: bool = False,
                    want_outputs: bool = False, want_grads: bool = False, apply_update: bool = True,
-                   losses: Optional[torch.Tensor] = None):
+                   losses: Optional[torch.Tensor] = None, clips: Optional[torch.Tensor] = None,
+                   background: Optional[torch.Tensor] = None):
+        """clips (uint8 CUDA tensor of n packed tcr_augment_clip records) + int16 `inputs` [n, stride]: the step starts with
+        the device input stage (decode, shift, background mix, clip) instead of taking decoded fp32 samples."""
         n = inputs.shape[0]
         a = L.TcrStepArgs()
-        a.input, a.input_is_features = self._input(inputs, input_is_features)
+        if clips is not None:
+            assert inputs.dtype == torch.int16 and inputs.is_cuda and inputs.is_contiguous() and clips.numel() == 24 * n
+            a.input, a.input_is_features = inputs.data_ptr(), L.TCR_INPUT_WAV_PCM16
+            a.clips, a.background, a.pcm_stride = clips.data_ptr(), self._ptr(background), inputs.shape[1]
+        else:
+            a.input, a.input_is_features = self._input(inputs, input_is_features)
         a.onehot, a.n = self._ptr(onehot), n
         a.params, a.slots, a.moving = self._ptr(params), self._ptr(slots), self._ptr(moving)
         a.learning_rate, a.momentum, a.weight_decay = float(learning_rate), float(momentum), float(weight_decay)
@@ -290,7 +298,11 @@ class HostFeed:
         return None if self._step.value < 0 else (int(self._step.value), float(self._out[0]), float(self._out[1]))
 
     def submit(self, h_inputs: torch.Tensor, h_onehot: torch.Tensor, params, slots, moving, learning_rate, momentum=0.9,
-               weight_decay=1e-4, dropout_seed=0, input_is_features=False):
+               weight_decay=1e-4, dropout_seed=0, input_is_features=False, h_clips: Optional[torch.Tensor] = None,
+               background: Optional[torch.Tensor] = None):
+        """h_clips (pinned uint8 tensor of n packed tcr_augment_clip records, datasets/device_input_stage.py) with int16
+        h_inputs [n, stride]: the wav files' samples and the per-clip draws cross the bus; the input stage runs on the device
+        (`background`: the CUDA-resident bank)."""
         eng = self.eng
         assert h_inputs.is_pinned() and h_onehot.is_pinned() and h_inputs.is_contiguous(), "HostFeed needs pinned host tensors"
         a = L.TcrStepArgs()
@@ -298,6 +310,9 @@ class HostFeed:
         a.input_is_features = (L.TCR_INPUT_FEATURES if input_is_features else
                                L.TCR_INPUT_WAV_PCM16 if h_inputs.dtype == torch.int16 else L.TCR_INPUT_WAV_F32)
         a.onehot, a.n = h_onehot.data_ptr(), h_inputs.shape[0]
+        if h_clips is not None:
+            assert h_clips.is_pinned() and h_clips.dtype == torch.uint8 and h_inputs.dtype == torch.int16
+            a.clips, a.background, a.pcm_stride = h_clips.data_ptr(), eng._ptr(background), h_inputs.shape[1]
         a.params, a.slots, a.moving = eng._ptr(params), eng._ptr(slots), eng._ptr(moving)
         a.learning_rate, a.momentum, a.weight_decay = float(learning_rate), float(momentum), float(weight_decay)
         a.dropout_seed, a.apply_update = int(dropout_seed), 1

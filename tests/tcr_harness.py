@@ -172,7 +172,7 @@ class Engine:
         return dict(logits=b.download(logits), probs=b.download(probs), losses=b.download(losses))
 
     def train_step(self, inp_np, onehot_np, params_np, slots_np, moving_np, lr=0.1, momentum=0.9, weight_decay=1e-3,
-                   is_features=False, seed=0, mask_np=None, apply_update=True):
+                   is_features=False, seed=0, mask_np=None, apply_update=True, clips_np=None, background_np=None):
         b = self.b
         n = inp_np.shape[0]
         inp, onehot = b.upload(inp_np), b.upload(onehot_np)
@@ -184,6 +184,10 @@ class Engine:
         a = L.TcrStepArgs()
         kind = 1 if is_features else (2 if np.asarray(inp_np).dtype == np.int16 else 0)
         a.input, a.input_is_features, a.onehot, a.n = b.ptr(inp), kind, b.ptr(onehot), n
+        if clips_np is not None:          # device input stage inside the step: int16 rows + packed tcr_augment_clip records
+            clips = b.upload_bytes(np.frombuffer(np.ascontiguousarray(clips_np).tobytes(), np.uint8))
+            bg = b.upload(background_np) if background_np is not None else None
+            a.clips, a.background, a.pcm_stride = b.ptr(clips), b.ptr(bg), inp_np.shape[1]
         a.params, a.slots, a.moving = b.ptr(params), b.ptr(slots), b.ptr(moving)
         a.learning_rate, a.momentum, a.weight_decay = lr, momentum, weight_decay
         a.dropout_seed, a.dropout_mask = seed, b.ptr(mask)

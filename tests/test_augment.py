@@ -50,6 +50,31 @@ def test_emulated_input_stage_is_bit_exact():
     _check(b, 3, 2, 16000, with_bg=False)      # evaluation split: no background bank
 
 
+def _step_inputs(seed, n, stride):
+    pcm, clips, background = _case(seed, n, stride)
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    pv, mv = O.init_variables(spec, 3)
+    params, moving = O.flatten_vars(spec, pv).astype(np.float32), O.flatten_moving(spec, mv).astype(np.float32)
+    onehot = np.eye(12, dtype=np.float32)[np.random.RandomState(seed).randint(0, 12, n)]
+    return pcm, clips, background, params, moving, onehot
+
+
+def _check_step_with_input_stage(backend, n, stride):
+    """A step that starts from int16 clips + draws == the input stage followed by a step on its fp32 output, bit for bit."""
+    eng = Engine(backend, max_batch=n)
+    pcm, clips, background, params, moving, onehot = _step_inputs(21, n, stride)
+    wav = eng.augment(pcm, clips, background)
+    a = eng.train_step(pcm, onehot, params, np.zeros_like(params), moving, seed=4, clips_np=clips, background_np=background)
+    b = eng.train_step(wav, onehot, params, np.zeros_like(params), moving, seed=4)
+    assert np.array_equal(a["params"], b["params"]) and np.array_equal(a["losses"], b["losses"])
+    assert np.isfinite(a["params"]).all()
+    eng.close()
+
+
+def test_emulated_step_with_the_input_stage_in_front():
+    _check_step_with_input_stage(NumpyBackend(), 3, 16500)
+
+
 def test_oracle_matches_the_host_restatement_of_the_input_pipeline():
     """The oracle and the host-side module that mirrors the reference's API agree sample for sample."""
     import tcresnet_b200  # noqa: F401
@@ -85,4 +110,39 @@ def test_cuda_input_stage_is_bit_exact_and_feeds_the_front_end():
     eng = Engine(b, max_batch=64)
     feat = eng.mfcc(wav)
     assert np.abs(feat - O.mfcc(wav.astype(np.float64), 640, 320)).max() / np.abs(feat).max() < 2e-5
+    eng.close()
+    _check_step_with_input_stage(b, 48, 16000)
+
+
+@pytest.mark.gpu
+def test_host_feed_with_the_device_input_stage():
+    """tcr_train_step_host fed int16 clips + draws from pinned host memory == device-buffer steps on the augmented fp32 wav."""
+    import torch
+    import tcresnet_b200  # noqa: F401
+    from tcresnet_b200.datasets import device_input_stage as D
+    from tcresnet_b200.engine import Engine as PublicEngine, HostFeed
+    eng = PublicEngine(max_batch=32)
+    rng = np.random.RandomState(2)
+    bg = [rng.uniform(-1, 1, 40000).astype(np.float32), rng.uniform(-1, 1, 70000).astype(np.float32)]
+    stage = D.DeviceInputStage(eng, bg)
+    pcm = [torch.from_numpy(rng.randint(-30000, 30000, (32, 16000)).astype(np.int16)).pin_memory() for _ in range(3)]
+    clips = [D.draw_clips(rng, [16000] * 32, rng.uniform(size=32) < 0.1, 16000, stage.bg_lengths) for _ in range(3)]
+    h_clips = [torch.from_numpy(np.frombuffer(c.tobytes(), np.uint8).copy()).pin_memory() for c in clips]
+    hot = [torch.nn.functional.one_hot(torch.from_numpy(rng.randint(0, 12, 32)), 12).float().pin_memory() for _ in range(3)]
+    results = {}
+    for kind in ("device", "host"):
+        params, slots, moving = eng.new_variables(seed=1)
+        if kind == "device":
+            for i in range(5):
+                wav = stage(pcm[i % 3].cuda(), clips[i % 3])
+                eng.train_step(wav, hot[i % 3].cuda(), params, slots, moving, 0.05, 0.9, 1e-3, dropout_seed=i)
+        else:
+            feed = HostFeed(eng, lag=2)
+            for i in range(5):
+                feed.submit(pcm[i % 3], hot[i % 3], params, slots, moving, 0.05, 0.9, 1e-3, dropout_seed=i, h_clips=h_clips[i % 3],
+                            background=stage.background)
+            assert len(feed.flush()) == 2
+        torch.cuda.synchronize()
+        results[kind] = params.cpu().numpy()
+    assert np.array_equal(results["host"], results["device"])
     eng.close()
