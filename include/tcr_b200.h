@@ -221,6 +221,8 @@ int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int32_t world_
  * bit-identical) — compute and collective in ONE kernel, no ncclAllReduce launch in the step. */
 int tcr_comm_p2p_export(tcr_handle* h, void* handles128);
 int tcr_comm_p2p_attach(tcr_handle* h, const void* all_handles, int32_t rank, int32_t world_size);
+/* Back to ncclAllReduce (e.g. when some rank could not map a peer): unmaps the peers and frees the exported buffers. */
+int tcr_comm_p2p_detach(tcr_handle* h);
 int tcr_comm_destroy(tcr_handle* h);
 
 /* Measured fp32 FMA peak of the device the handle lives on (TFLOP/s), used as the compute-roofline

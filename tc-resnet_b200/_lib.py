@@ -97,6 +97,7 @@ SYMBOLS = {
     "tcr_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tcr_comm_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tcr_comm_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "tcr_comm_p2p_detach": (C.c_int, [C.c_void_p]),
     "tcr_comm_destroy": (C.c_int, [C.c_void_p]),
     "tcr_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "tcr_dscnn_create": (C.c_int, [C.POINTER(TcrDscnnConfig), C.POINTER(C.c_void_p)]),

@@ -699,6 +699,11 @@ extern "C" int tcr_comm_p2p_attach(tcr_handle* h, const void* all_handles, int32
   int rc = comm_p2p_attach(h, all_handles, rank, world_size);
   return rc ? fail(rc, "peer-memory attach failed: %s", comm_error()) : TCR_OK;
 }
+extern "C" int tcr_comm_p2p_detach(tcr_handle* h) {
+  if (!h) return TCR_OK;
+  comm_p2p_destroy(h);
+  return TCR_OK;
+}
 extern "C" int tcr_comm_destroy(tcr_handle* h) {
   if (!h) return TCR_OK;
   comm_destroy(h);

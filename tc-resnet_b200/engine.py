@@ -254,8 +254,9 @@ class Engine:
             dist.all_gather_object(outcome, bool(ok))
             if all(outcome):
                 self.exchange = "peer-memory"
-            elif ok:                                  # someone failed to map a peer: everybody stays on NCCL
-                raise L.TcrError("peer-memory attach succeeded on some ranks only; set TCR_P2P=0")
+            else:                                     # someone could not export / map a peer: everybody stays on NCCL
+                with torch.cuda.device(self.device):
+                    self.lib.tcr_comm_p2p_detach(self._h)
 
     # ------------------------------------------------------------------ accounting
     def launch_count(self) -> int:
