@@ -20,7 +20,9 @@ def backend():
     dict(model="TCResNet8", wm=1.0, window=480, stride=160, n=3, keep=0.5, ls=0.1),
     dict(model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False),
     dict(model="TCResNet8", wm=1.5, window=640, stride=320, n=1, steps=2),
-], ids=["r8-T49", "r14x1.5-T49-dropout", "r8-T98-smoothing", "r14-T98-features", "r8x1.5-n1-2steps"])
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=37, keep=0.5, max_batch=512),   # plan sized for 512, ragged clusters
+    dict(model="TCResNet14", wm=2.0, window=640, stride=320, n=6),                           # 96-channel layers: filters via L1
+], ids=["r8-T49", "r14x1.5-T49-dropout", "r8-T98-smoothing", "r14-T98-features", "r8x1.5-n1-2steps", "r8-n37-of-512", "r14x2-n6"])
 def test_emulated_kernels_match_oracle(backend, kw):
     report = run_case(backend, **kw)
     assert report["features"] < 1e-6
