@@ -75,6 +75,27 @@ def test_emulated_step_with_the_input_stage_in_front():
     _check_step_with_input_stage(NumpyBackend(), 3, 16500)
 
 
+def test_emulated_host_buffer_step_with_the_input_stage():
+    """tcr_train_step_host with int16 rows + draws in host memory == the device-buffer step with the same stage in front."""
+    import ctypes as C
+    from tcresnet_b200 import _lib as Lb
+    b = NumpyBackend()
+    eng = Engine(b, max_batch=3)
+    pcm, clips, background, params, moving, onehot = _step_inputs(33, 3, 16200)
+    ref = eng.train_step(pcm, onehot, params, np.zeros_like(params), moving, seed=6, clips_np=clips, background_np=background)
+    p, sl, mv = params.copy(), np.zeros_like(params), moving.copy()
+    rec = np.frombuffer(np.ascontiguousarray(clips).tobytes(), np.uint8).copy()
+    a = Lb.TcrStepArgs()
+    a.input, a.input_is_features, a.onehot, a.n = pcm.ctypes.data, Lb.TCR_INPUT_WAV_PCM16, onehot.ctypes.data, 3
+    a.clips, a.background, a.pcm_stride = rec.ctypes.data, background.ctypes.data, pcm.shape[1]
+    a.params, a.slots, a.moving = p.ctypes.data, sl.ctypes.data, mv.ctypes.data
+    a.learning_rate, a.momentum, a.weight_decay, a.dropout_seed, a.apply_update = 0.1, 0.9, 1e-3, 6, 1
+    out, step = (C.c_float * 2)(), C.c_int64(-7)
+    Lb.check(eng.lib, eng.lib.tcr_train_step_host(eng.h, C.byref(a), 0, None, out, C.byref(step)), "tcr_train_step_host")
+    assert step.value == 0 and np.array_equal(p, ref["params"]) and (out[0], out[1]) == tuple(ref["losses"])
+    eng.close()
+
+
 def test_oracle_matches_the_host_restatement_of_the_input_pipeline():
     """The oracle and the host-side module that mirrors the reference's API agree sample for sample."""
     import tcresnet_b200  # noqa: F401
