@@ -51,6 +51,48 @@ def parse_args():
     return ap.parse_args()
 
 
+def l2_policy(a, clip=16000):
+    rot = max(1, a.rotate)
+    return f"inputs rotate over {rot} distinct batches ({rot * a.batch * clip * 4 / 1e6:.0f} MB > 126 MB L2)"
+
+
+def make_config(a, world, exchange):
+    """The SAME keys in both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "global_batch": a.batch * world, "l2": l2_policy(a), "exchange": exchange}
+
+
+def sources_sha():
+    """Hash of the kernel sources: a committed ncu capture is only quoted while it describes THESE kernels."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "tc-resnet_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "tc-resnet_b200", "csrc", "*.h"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def pin_to_gpu_numa_node(dev_index):
+    """Run this process on the CPU cores of the GPU's NUMA node (pinned-buffer copies and launches then stay local)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+    return None
+
+
 def workload_name(a):
     t = 1 + (16000 - int(16 * a.window_ms)) // int(16 * a.stride_ms)
     return (f"{a.model}-{a.width:g} train step (MFCC {t}x40 front-end + fwd + bwd + SGD-momentum), synthetic 16 kHz 1 s clips, "
@@ -192,7 +234,8 @@ def run_reference(a):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "utterances/sec", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": el / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a), "global_batch": a.batch * a.gpus, "sample_batch": batch},
+           "config": make_config(a, a.gpus, "none (1 GPU)" if a.gpus == 1 else "peer-memory | nccl (GPU arm)"),
+           "sample_batch": batch,
            "cpu_baseline": {"value": value, "unit": "utterances/sec", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "utterances/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -244,6 +287,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -263,7 +307,7 @@ def run_ours(a):
     lr, mom, wd = 0.1, 0.9, 1e-3
 
     def step(i):
-        eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i, losses=losses)
+        eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i * world + rank, losses=losses)
 
     def barrier():
         if world > 1:
@@ -295,9 +339,8 @@ def run_ours(a):
     out = {"metric": metric, "value": value, "unit": "utterances/sec", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "ours",
-           "config": {"workload": workload_name(a), "global_batch": n * world, "parallelism": f"dp{world}",
-                      "l2": f"inputs rotate over {rot} resident batches ({rot * n * plan.clip * 4 / 1e6:.0f} MB > 126 MB L2)",
-                      "final_total_loss": final_loss},
+           "config": make_config(a, world, "none (1 GPU)" if world == 1 else getattr(eng, "exchange", "nccl")),
+           "parallelism": f"dp{world}", "final_total_loss": final_loss, "numa": numa,
            "gpu_launches": int(launches), "clocks": clocks}
 
     # ---- per-kernel durations (separate pass: event brackets add overhead, so not the timed region).  Every rank runs
@@ -357,7 +400,7 @@ def run_ours(a):
         from tcresnet_b200.engine import HostFeed
         h_wavs = [w.cpu().pin_memory() for w in wavs[:min(rot, 4)]]
         h_hots = [o.cpu().pin_memory() for o in onehots[:min(rot, 4)]]
-        esteps = min(a.steps, 200)
+        esteps = max(100, min(a.steps, 200))            # never fewer than 100 timed steps, whatever --steps says
 
         def e2e_run(host_wavs, host_clips=None, background=None):
             feed = HostFeed(eng, lag=2)
@@ -365,12 +408,12 @@ def run_ours(a):
 
             def e2e_step(i):                              # returns (step, total, model) of the step submitted 2 calls earlier
                 r = feed.submit(host_wavs[i % len(host_wavs)], h_hots[i % len(h_hots)], params, slots, moving, lr, mom, wd,
-                                dropout_seed=i, h_clips=host_clips[i % len(host_clips)] if host_clips else None,
+                                dropout_seed=i * world + rank, h_clips=host_clips[i % len(host_clips)] if host_clips else None,
                                 background=background)
                 if r is not None:
                     seen.append(r)
 
-            for i in range(3):
+            for i in range(12):                           # >= 10 warm-up steps: staging slots, pinned pages and clocks settle
                 e2e_step(i)
             feed.flush()
             barrier()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCR_ABI_VERSION 3
+#define TCR_ABI_VERSION 4
 
 enum {
   TCR_OK = 0,
@@ -178,6 +178,10 @@ typedef struct tcr_augment_clip {
 } tcr_augment_clip;
 int tcr_augment_pcm16(tcr_handle* h, const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips,
                       const float* background, float* wav_out, int32_t n, tcr_stream stream);
+/* Length (floats) of the background bank the `background` pointers refer to: a clip whose crop [bg_offset, bg_offset + clip_samples)
+ * does not fit is not mixed (instead of reading past the bank).  0 (default): offsets are trusted.  The host stage pads
+ * recordings shorter than a clip, as augmentation_factory.py:60-75 does. */
+int tcr_set_background_samples(tcr_handle* h, int64_t samples);
 
 /* Forward pass.  is_training == 0: evaluate_audio.py path (BN moving statistics, dropout identity;
  * helper/base.py:52-125).  is_training == 1: the training graph's forward (batch statistics, dropout)

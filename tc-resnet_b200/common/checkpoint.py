@@ -25,12 +25,14 @@ def checkpoint_step(path) -> int:
     return int(m.group(1)) if m else 0
 
 
-def save(train_dir, model_name: str, step: int, variables: Dict[str, np.ndarray], max_to_keep: int = 5) -> str:
+def save(train_dir, model_name: str, step: int, variables: Dict[str, np.ndarray], max_to_keep: int = 5, fmt: str = "npz") -> str:
     d = Path(train_dir)
     d.mkdir(parents=True, exist_ok=True)
     path = d / f"{model_name}-{int(step)}.npz"
-    tmp = d / f".{model_name}-{int(step)}.tmp.npz"
-    np.savez(tmp, global_step=np.int64(step), **variables)
+    # unique per process and NOT matching "*.npz": neither another rank nor the watching evaluator can pick it up
+    tmp = d / f".{model_name}-{int(step)}.{os.getpid()}.tmp"
+    with open(tmp, "wb") as f:
+        np.savez(f, global_step=np.int64(step), **variables)
     os.replace(tmp, path)                       # atomic: the watching evaluator never sees a partial file
     kept = sorted(d.glob(f"{model_name}-*.npz"), key=checkpoint_step)
     for old in kept[:-max_to_keep] if max_to_keep > 0 else []:
@@ -44,7 +46,8 @@ def load(path) -> Dict[str, np.ndarray]:
 
 
 def latest_checkpoint(directory) -> Optional[str]:
-    cands = sorted(Path(directory).glob("*-*.npz"), key=checkpoint_step)
+    cands = sorted((p for p in Path(directory).glob("*-*.npz") if not p.name.startswith(".") and _STEP.search(p.name)),
+                   key=checkpoint_step)
     return str(cands[-1]) if cands else None
 
 

@@ -367,6 +367,7 @@ static void hostfeed_destroy(tcr_handle* h);
 extern "C" int tcr_destroy(tcr_handle* h) {
   if (!h) return TCR_OK;
   hostfeed_destroy(h);
+  resident_destroy(h);
   comm_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_hyper) cudaFreeHost(h->h_hyper);
@@ -459,8 +460,14 @@ extern "C" int tcr_augment_pcm16(tcr_handle* h, const int16_t* pcm, int64_t pcm_
   TCR_TRY(check_n(h, n));
   if (pcm_stride < 1) return fail(TCR_ERR_INVALID, "pcm_stride must be positive");
   if (((uintptr_t)wav_out & 15) != 0) return fail(TCR_ERR_INVALID, "wav_out must be 16-byte aligned");
-  augment_launch(pcm, pcm_stride, clips, background, wav_out, h->cfg.clip_samples, n, (cudaStream_t)stream);
+  augment_launch(pcm, pcm_stride, clips, background, h->background_samples, wav_out, h->cfg.clip_samples, n, (cudaStream_t)stream);
   TCR_CUDA(cudaGetLastError());
+  return TCR_OK;
+}
+
+extern "C" int tcr_set_background_samples(tcr_handle* h, int64_t samples) {
+  if (!h || samples < 0) return fail(TCR_ERR_INVALID, "bad background length");
+  h->background_samples = samples;
   return TCR_OK;
 }
 
@@ -505,22 +512,25 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
         h->allocs.push_back(p);
         h->d_aug = (float*)p;
       }
-      augment_launch((const int16_t*)a->input, stride, a->clips, a->background, h->d_aug, h->cfg.clip_samples, a->n, s);
+      augment_launch((const int16_t*)a->input, stride, a->clips, a->background, h->background_samples, h->d_aug, h->cfg.clip_samples, a->n, s);
       TCR_TRY(mfcc_run(h, h->d_aug, 0, h->d_feat, a->n, stream));
     } else {
       TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, a->n, stream));
     }
     feat = h->d_feat;
   }
-  if (persist_enabled(h)) rec_begin(h);      // record the step's phases; net_update launches the persistent kernel
   net_weight_transpose(h, a->params, s);
-  int rc = net_forward(h, feat, a->params, nullptr, a->n, true, a->dropout_seed, a->dropout_mask, a->onehot,
-                       a->weight_decay, a->logits, a->probs, nullptr, /*backward=*/true, s);
-  if (rc) { rec_abort(h); return fail(rc, "forward launch failed: %s", g_err); }
-  rc = net_backward(h, feat, a->params, a->n, s);
-  if (rc) { rec_abort(h); return fail(rc, "backward launch failed: %s", g_err); }
-  rc = net_update(h, a, s);
-  if (rc) { rec_abort(h); return fail(rc, "update launch failed: %s", g_err); }
+  const int resident = resident_mode(h);
+  int rc = resident >= 1 ? resident_forward(h, feat, a, s)
+                               : net_forward(h, feat, a->params, nullptr, a->n, true, a->dropout_seed, a->dropout_mask, a->onehot,
+                                             a->weight_decay, a->logits, a->probs, nullptr, /*backward=*/true, s);
+  if (rc) return fail(rc, "forward launch failed: %s", g_err);
+  if (resident < 2) {               // mode 2: net_update runs the resident backward kernel instead
+    rc = net_backward(h, feat, a->params, a->n, s);
+    if (rc) return fail(rc, "backward launch failed: %s", g_err);
+  }
+  rc = net_update(h, feat, a, s);
+  if (rc) return fail(rc, "update launch failed: %s", g_err);
   TCR_CUDA(cudaGetLastError());
   h->last_n = a->n;
   return TCR_OK;

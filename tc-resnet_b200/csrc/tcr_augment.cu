@@ -18,6 +18,7 @@ struct AugArgs {
   const int16_t* pcm; int64_t pcm_stride;      // [n][pcm_stride] int16 samples (only `length` of a row are valid)
   const tcr_augment_clip* clips;               // [n]
   const float* background;                     // concatenated background recordings (may be null: no mixing)
+  int64_t background_samples;                  // floats in `background` (0: unknown, offsets are trusted)
   float* out; int clip;                        // [n][clip]
 };
 
@@ -25,9 +26,12 @@ __global__ void __launch_bounds__(256) augment_kernel(AugArgs a) {
   pdl_wait();
   const int n = blockIdx.y;
   const tcr_augment_clip c = a.clips[n];
-  const int valid = c.silent ? 0 : min(c.length, a.clip);            // decode_wav crops / zero-pads to the clip length
+  // decode_wav crops / zero-pads to the clip length; a row never holds more than pcm_stride samples
+  const int valid = c.silent ? 0 : max(0, min(min(c.length, a.clip), (int)(a.pcm_stride < 0x7fffffff ? a.pcm_stride : 0x7fffffff)));
   const int16_t* src = a.pcm + (size_t)n * a.pcm_stride;
-  const bool mix = a.background != nullptr && c.bg_offset >= 0;
+  // a crop that would run past the end of the bank is not mixed in (the host pads short recordings, device_input_stage.py)
+  const bool mix = a.background != nullptr && c.bg_offset >= 0 &&
+                   (a.background_samples <= 0 || c.bg_offset + (int64_t)a.clip <= a.background_samples);
   const float* bg = mix ? a.background + c.bg_offset : nullptr;
   float* dst = a.out + (size_t)n * a.clip;
   for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; 4 * i4 < a.clip; i4 += gridDim.x * blockDim.x) {
@@ -50,9 +54,9 @@ __global__ void __launch_bounds__(256) augment_kernel(AugArgs a) {
   }
 }
 
-int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, float* out, int clip,
-                   int n, cudaStream_t s) {
-  AugArgs a{pcm, pcm_stride, clips, background, out, clip};
+int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, int64_t background_samples,
+                   float* out, int clip, int n, cudaStream_t s) {
+  AugArgs a{pcm, pcm_stride, clips, background, background_samples, out, clip};
   const int bx = std::max(1, std::min(8, (clip / 4 + 255) / 256));
   TCR_LAUNCH("augment", augment_kernel, dim3(bx, n), dim3(256), 0, s, a);
   return 0;

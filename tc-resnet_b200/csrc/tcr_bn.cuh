@@ -164,19 +164,6 @@ __device__ __forceinline__ void cluster_publish(const PubSeg (&seg)[NSEG], int v
   cluster_sync_all();               // nobody exits (and releases its shared memory) while a peer may still read it
 }
 
-// One channel of a BN table from its batch sums (used by the persistent kernel's finalize phase).
-__device__ __forceinline__ void bn_table_write(const BnFinalize& f, int c, double s1, double s2, double m_total, float eps) {
-  const double mean = s1 / m_total;
-  double var = s2 / m_total - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const double rstd = 1.0 / sqrt(var + (double)eps);
-  f.bnf[c] = (float)mean;
-  f.bnf[f.c + c] = (float)rstd;
-  f.bnf[2 * f.c + c] = (float)((double)f.gamma[c] * rstd);
-  f.bnf[3 * f.c + c] = f.beta[c];
-  f.var[c] = (float)var;
-}
-
 // Sum `gc` records of `cols` floats each: thread i < cols * nch takes column i % cols and records i / cols, + nch, ...
 // (loads batched 8 deep); the nch chunk sums land in scratch[chunk * cols + col].  Needs cols <= blockDim.x.
 constexpr int kRecB = 32;          // records in flight per thread: one batch covers 32 records x column chunks

@@ -45,23 +45,6 @@ struct ActSrc {
   StatSrc st;
 };
 
-// What the finalize PHASES of the opt-in persistent kernel (tcr_persist.cu) need: there the records are per CTA and a
-// phase behind a grid barrier sums them (the default multi-kernel path sums per-cluster records in the consumer, tcr_bn.cuh).
-struct BnFinalize {
-  const float* gamma;       // params + gamma_off
-  const float* beta;
-  const float* fpart;       // [G][C][2] (sum y, sum y^2)
-  float* bnf;               // [4][C]
-  float* var;               // [C] biased batch variance (moving-average update reads it)
-  int c;
-};
-
-struct BwdSumFinalize {     // sum of (sum dz, sum dz*xhat) records
-  const float* bpart;       // [G][C][2]
-  float* bsum;              // [2][C]
-  int c;
-};
-
 // ---------------- forward conv kernel (main conv + optional 1x1/stride-2 "down" conv) ----------------
 struct FwdArgs {
   // input tile
@@ -80,7 +63,6 @@ struct FwdArgs {
   const float* wd; float* yd; float* fpartd; int coutd;
   // training statistics
   int train;
-  BnFinalize fin, find;
   float eps;
 };
 
@@ -104,8 +86,6 @@ struct HeadArgs {
   const float* yb; const float* bnfb; float* bpartb;
   const float* ydn; const float* bnfd; float* bpartd;   // null when the last block has no down conv
   float* dwfc_part;         // [Gh][C*classes]
-  BwdSumFinalize finb, find;
-  float* loss_out;          // [1] sum over utterances of CE (persistent kernel's finalize phase)
 };
 
 // ---------------- backward-data kernel ----------------
@@ -135,7 +115,6 @@ struct BwdDataArgs {
   const float* out_prev;                                        // kind 2
   const float* ypd; const float* bnfpd; float* bpartpd;         // kind 2: down conv of prev block (may be null)
   float* gprev;             // [N, t_in, cin]
-  BwdSumFinalize finp, finpd;
 };
 
 // ---------------- backward-weight kernel ----------------
@@ -182,26 +161,6 @@ struct GradArgs {           // gradient finalisation (sum of partials + weight d
 };
 struct WtLayer { int64_t w_off; float* wT; int k, cin, cout; int64_t begin; };
 struct WtArgs { WtLayer layer[kMaxConvs]; int nlayers; int64_t total; const float* params; };
-
-// ---------------- persistent step kernel: phase program ----------------
-enum { PH_TRANSPOSE = 0, PH_FWD, PH_FIN_FWD, PH_HEAD, PH_BWD, PH_FIN_BWD, PH_DW, PH_GRAD };
-struct Phase { int kind, idx, nvb, k, wsmem; };
-struct FinFwd { BnFinalize f[2]; int nf, G, U, n, t_out; float eps; };
-struct FinBwd { BwdSumFinalize f[2]; int nf, G; const float* loss_part; float* loss_out; };
-constexpr int kMaxFwdPh = 16, kMaxBwdPh = 16, kMaxPhases = 80;
-struct StepProgram {
-  int nphases, nfwd, nbwd, nfinb;
-  Phase phase[kMaxPhases];
-  FwdArgs fwd[kMaxFwdPh];
-  FinFwd finf[kMaxFwdPh];
-  HeadArgs head;
-  BwdDataArgs bwd[kMaxBwdPh];
-  FinBwd finb[kMaxBwdPh + 1];
-  WtArgs wt;
-  const DwLayer* dw_layers; int n_dw_layers; int n; const float* feat; long long* tl;
-  GradArgs grad;
-  unsigned* barrier;
-};
 
 struct Hyper {              // device-resident hyper-parameters (graph replays read fresh values)
   float lr, momentum, weight_decay, one_minus_decay;

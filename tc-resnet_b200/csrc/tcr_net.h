@@ -18,28 +18,22 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
 // Backward-data chain + all weight-gradient kernels; leaves per-layer partial sums in the workspace.
 int cluster_size(tcr_handle* h);
 StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n);
-int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, float* out, int clip,
-                   int n, cudaStream_t s);
+int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, int64_t background_samples,
+                   float* out, int clip, int n, cudaStream_t s);
 int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
+// Resident forward (tcr_resident.cu): the training forward + head as one cooperative kernel with SM-resident activations.
+int resident_mode(tcr_handle* h);      // 0: per-layer kernels, 1: resident forward, 2: resident forward + backward
+int resident_forward(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s);
+int resident_backward(tcr_handle* h, const float* feat, const tcr_step_args* a, float* grads, int* l2_records, cudaStream_t s);
+void resident_destroy(tcr_handle* h);
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s);
 
 // Gradient finalisation (+ weight decay), optional NCCL all-reduce, momentum update, BN moving averages, losses.
-int net_update(tcr_handle* h, const tcr_step_args* a, cudaStream_t s);
+int net_update(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s);
 
 int launch_loss_only(tcr_handle* h, const float* params, float weight_decay, int n, float* losses, cudaStream_t s);
 int head_groups(int n);
 
-// Persistent step kernel (tcr_persist.cu): the launch sites record phases instead of launching while h->rec != nullptr.
-bool persist_enabled(tcr_handle* h);
-void rec_begin(tcr_handle* h);
-void rec_abort(tcr_handle* h);
-void rec_fwd(tcr_handle* h, const FwdArgs& a, int k, int wsm, int groups, size_t smem);
-void rec_head(tcr_handle* h, const HeadArgs& a, int groups, size_t smem);
-void rec_bwd(tcr_handle* h, const BwdDataArgs& a, int k, int wsm, int groups, size_t smem);
-void rec_transpose(tcr_handle* h, const WtArgs& w);
-void rec_dw(tcr_handle* h, int n, const float* feat);
-void rec_grad(tcr_handle* h, const GradArgs& g, int blocks);
-int rec_launch(tcr_handle* h, cudaStream_t s);
 
 int measure_fp32_peak(tcr_handle* h, double* tflops, cudaStream_t s);
 

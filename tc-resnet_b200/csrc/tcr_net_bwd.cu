@@ -644,10 +644,6 @@ static int bwd_data(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, BwdDataArgs a, co
   a.nvb = groups;
   const size_t smem = bwd_data_smem(cv, dn, U, KS, wsm != 0);
   *gc_out = 0;
-  if (h->rec) {
-    rec_bwd(h, a, cv.k, wsm, groups, smem);
-    return 0;
-  }
   const int CL = cluster_size(h);
   const int grid = (groups + CL - 1) / CL * CL;
   *gc_out = grid / CL;
@@ -670,8 +666,7 @@ int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s) {
     w.layer[w.nlayers++] = WtLayer{cv.w_off, cv.wT, cv.k, cv.cin, cv.cout, w.total};
     w.total += cv.wnumel();
   }
-  if (h->rec) rec_transpose(h, w);
-  else TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
+  TCR_LAUNCH("weight_transpose", weight_transpose_kernel, dim3((unsigned)((w.total + 255) / 256)), dim3(256), 0, s, w);
   return 0;
 }
 
@@ -688,8 +683,6 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       a.dy = make_dy(cb, b.gblk, 0, n);
       a.epi_kind = 1;
       a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
-      a.finp = BwdSumFinalize{ca.bpart, ca.bsum, ca.cout};
-      a.finpd = a.finp;
       int gc = 0;
       int rc = bwd_data(h, cb, nullptr, a, params, n, s, &gc);
       if (rc) return rc;
@@ -708,20 +701,15 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
         a.epi_kind = 2;
         a.out_prev = pb.out;
         a.yp = pcb.y; a.bnfp = pcb.bnf; a.bpartp = pcb.bpart;
-        a.finp = BwdSumFinalize{pcb.bpart, pcb.bsum, pcb.cout};
-        a.finpd = a.finp;
         if (pb.down >= 0) {
           ConvPlan& pd = h->convs[pb.down];
           a.ypd = pd.y; a.bnfpd = pd.bnf; a.bpartpd = pd.bpart;
-          a.finpd = BwdSumFinalize{pd.bpart, pd.bsum, pd.cout};
         }
         a.gprev = pb.gblk;
       } else {
         ConvPlan& c0 = h->convs[0];
         a.epi_kind = 1;
         a.yp = c0.y; a.bnfp = c0.bnf; a.bpartp = c0.bpart; a.gprev = c0.g;
-        a.finp = BwdSumFinalize{c0.bpart, c0.bsum, c0.cout};
-        a.finpd = a.finp;
       }
       int gc = 0;
       int rc = bwd_data(h, ca, dn, a, params, n, s, &gc);
@@ -736,9 +724,7 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
     }
   }
   // weight gradients: every layer's inputs are final now -> one grouped launch over all layers
-  if (h->rec) {
-    rec_dw(h, n, feat);
-  } else {
+  {
     auto kfn = dw_grouped_kernel;
 #ifndef TCR_EMU
     static SmemOptIn optin;

@@ -588,8 +588,8 @@ int net_alloc_workspace(tcr_handle* h) {
     WS(ws_alloc(h, &cv.y, act));
     WS(ws_alloc(h, &cv.bnf, 4 * (size_t)cv.cout));
     WS(ws_alloc(h, &cv.var, (size_t)cv.cout));
-    WS(ws_alloc(h, &cv.fpart, (size_t)h->g_max * cv.cout * 2));
-    WS(ws_alloc(h, &cv.bpart, (size_t)std::max(h->g_max, h->head_groups_max) * cv.cout * 2));
+    WS(ws_alloc(h, &cv.fpart, (size_t)std::max(h->g_max, 256) * cv.cout * 2));
+    WS(ws_alloc(h, &cv.bpart, (size_t)std::max(std::max(h->g_max, h->head_groups_max), 256) * cv.cout * 2));
     WS(ws_alloc(h, &cv.bsum, 2 * (size_t)cv.cout));
     WS(ws_alloc(h, &cv.dwpart, (size_t)cv.dw_R * cv.wnumel()));
     WS(ws_alloc(h, &cv.wT, (size_t)cv.wnumel()));
@@ -603,13 +603,15 @@ int net_alloc_workspace(tcr_handle* h) {
     h->convs[b.b].g = b.gblk;
     if (b.down >= 0) h->convs[b.down].g = b.gblk;
   }
-  WS(ws_alloc(h, &h->d_loss_part, (size_t)h->head_groups_max));
+  const size_t rec_max = (size_t)std::max(h->head_groups_max, 256);   // head records: per cluster, per 4 utterances, or per SM (resident kernel)
+  WS(ws_alloc(h, &h->d_loss_part, rec_max));
   WS(ws_alloc(h, &h->d_loss, 4));
-  WS(ws_alloc(h, &h->d_dwfc_part, (size_t)h->head_groups_max * h->c_last * h->cfg.num_classes));
+  WS(ws_alloc(h, &h->d_dwfc_part, rec_max * h->c_last * h->cfg.num_classes));
   WS(ws_alloc(h, &h->d_grads, (size_t)h->n_train));
   WS(ws_alloc(h, &h->d_l2part, 4096));
   WS(ws_alloc(h, &h->d_hyper, 1));
-  WS(ws_alloc(h, &h->d_gridbar, 4));
+  WS(ws_alloc(h, &h->d_gridbar, 64));
+  cudaMemset(h->d_gridbar, 0, 64 * sizeof(unsigned));
   if (getenv("TCR_DEBUG_TIMELINE")) {
     WS(ws_alloc(h, &h->d_timeline, (size_t)16 * 8192));
     cudaMemset(h->d_timeline, 0, sizeof(long long) * 16 * 8192);
@@ -629,7 +631,7 @@ int cluster_size(tcr_handle* h) {
     if (c != 1 && c != 2 && c != 4 && c != 8) c = 8;
     h->cluster = c;
   }
-  return h->rec ? 1 : h->cluster;
+  return h->cluster;
 }
 StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n) {
   return StatSrc{cv.f_gc ? cv.fpart : nullptr, cv.f_gc, params + cv.gamma_off, params + cv.beta_off, cv.bnf, cv.var,
@@ -659,24 +661,17 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
   a.cout = cv.cout; a.stride = cv.stride; a.t_out = cv.t_out; a.pad_left = cv.pad_left; a.KS = KS;
   a.wd = nullptr; a.yd = nullptr; a.fpartd = nullptr; a.coutd = 0;
   a.train = training ? 1 : 0;
-  a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline + (h->rec ? 12 * 8192 : 0) : nullptr;
-  if (h->d_timeline && !h->rec && cv.name == "block1/conv1_1") a.tl = h->d_timeline + 2048 * 8;   // its producer, rows 2048..
+  a.tl = (h->d_timeline && cv.name == "block2/conv2_0") ? h->d_timeline : nullptr;
+  if (h->d_timeline && cv.name == "block1/conv1_1") a.tl = h->d_timeline + 2048 * 8;   // its producer, rows 2048..
   a.eps = h->cfg.bn_epsilon;
-  a.fin = BnFinalize{params + cv.gamma_off, params + cv.beta_off, cv.fpart, cv.bnf, cv.var, cv.cout};
-  a.find = a.fin;
   if (dn) {
     a.wd = params + dn->w_off; a.yd = dn->y; a.fpartd = dn->fpart; a.coutd = dn->cout;
-    a.find = BnFinalize{params + dn->gamma_off, params + dn->beta_off, dn->fpart, dn->bnf, dn->var, dn->cout};
   }
   const int groups = (n + U - 1) / U;
   a.nvb = groups;
   const size_t smem = fwd_smem_bytes(cv, dn, U, KS, wsm != 0);
   cv.f_gc = 0;
   if (dn) dn->f_gc = 0;
-  if (h->rec) {
-    rec_fwd(h, a, cv.k, wsm, groups, smem);
-    return 0;
-  }
   const int CL = cluster_size(h);
   const int grid = (groups + CL - 1) / CL * CL;
   if (training) {                   // the consumers of this layer's statistics sum grid / CL records
@@ -767,21 +762,17 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
       ha.yb = cb.y; ha.bnfb = cb.bnf; ha.bpartb = cb.bpart;
       ha.ydn = dn ? dn->y : nullptr; ha.bnfd = dn ? dn->bnf : nullptr; ha.bpartd = dn ? dn->bpart : nullptr;
       ha.dwfc_part = h->d_dwfc_part;
-      ha.finb = BwdSumFinalize{cb.bpart, cb.bsum, cb.cout};
-      ha.find = dn ? BwdSumFinalize{dn->bpart, dn->bsum, dn->cout} : ha.finb;
-      ha.loss_out = h->d_loss;
       const int groups = head_groups(n);
       ha.nvb = groups;
       const int CL = cluster_size(h);
       const int grid = (groups + CL - 1) / CL * CL;
-      h->loss_gc = h->rec ? groups : grid / CL;           // CE records the loss / update kernel adds
-      cb.b_gc = (backward && !h->rec) ? grid / CL : 0;
+      h->loss_gc = grid / CL;
+      h->fc_records = groups;           // CE records the loss / update kernel adds
+      cb.b_gc = backward ? grid / CL : 0;
       if (dn) dn->b_gc = cb.b_gc;
       const size_t smem = (head_smem_floats(lb.t, lb.c, ha.classes) + 8) * 4;
       if (smem > kSmemBudget || lb.c > kHeadThreads) { set_error("head tile does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
-      if (h->rec) {
-        rec_head(h, ha, groups, smem);
-      } else {
+      {
 #ifndef TCR_EMU
         static SmemOptIn optin;
         if (optin.ensure(head_kernel, smem) != cudaSuccess) return TCR_ERR_CUDA;

@@ -81,11 +81,12 @@ struct tcr_handle {
   } p2p;
   int last_n = 0;
   int loss_gc = 0;            // cross-entropy records left by the head launch of this call
-  size_t persist_smem = 0;    // dynamic shared memory the persistent kernel is opted in to on this handle's device
   int cluster = 0;            // CTAs per thread-block cluster of the conv / head launches (env TCR_CLUSTER, default 8)
+  int64_t background_samples = 0;   // floats in the background bank (tcr_set_background_samples); 0: offsets are trusted
   float* d_aug = nullptr;      // [max_batch][clip_samples] fp32 output of the device input stage inside a step (lazy)
   void* hostfeed = nullptr;   // HostFeedState (tcr_api.cu): staging slots of tcr_train_step_host
-  tcr::StepProgram* rec = nullptr;   // non-null while a training step is being recorded for the persistent kernel
-  size_t rec_smem = 0; int persist = -1; int persist_grid = 0; unsigned* d_gridbar = nullptr;
+  void* resident = nullptr;          // ResidentState (tcr_resident.cu): layout + program of the resident forward kernel
+  int fc_records = 0;                // per-CTA records of the fc weight gradient left by the last head launch
+  unsigned* d_gridbar = nullptr;    // arrival counter of the resident kernel's grid barrier (monotonic, never reset)
   long long* d_timeline = nullptr;   // TCR_DEBUG_TIMELINE=1: per-CTA phase stamps (fwd kernels: 8 slots per CTA; dw: after)
 };

@@ -27,7 +27,15 @@ class AudioDataWrapper(DataWrapperBase):
         super().__init__(args, dataset_split_name, is_training, name)
         self.session = session
         self.desired_samples = int(args.sample_rate * args.clip_duration_ms / 1000)
-        self.rng = np.random.RandomState(1234)
+        self.rng = np.random.RandomState(1234)          # shuffle order: the SAME on every rank (ranks take disjoint slices of it)
+        # data-parallel shard of this process (train_audio.py --data_parallel under torchrun): rank r takes rows
+        # [r*B, (r+1)*B) of every global window of world*B samples; augmentation draws are per rank
+        self.rank, self.world = 0, 1
+        if getattr(args, "data_parallel", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.aug_rng = np.random.RandomState(1234 + 7919 * self.rank)
         self.setup()
         self.placeholders = (Node("filenames"), Node("labels_index"))
         self.setup_iterator(session, self.placeholders, self.data)
@@ -49,14 +57,16 @@ class AudioDataWrapper(DataWrapperBase):
 
     def _take_indices(self):
         n = self.batch_size
-        if self._cursor + n > self._num_samples:
+        window = n * self.world                       # one global batch; every rank advances the shared cursor by it
+        if self._cursor + window > self._num_samples:
             if not self.is_training:
                 raise OutOfRangeError("Finished looping dataset.")
             self._cursor = 0
             if self.shuffle:
                 self.rng.shuffle(self._order)
-        idx = self._order[self._cursor:self._cursor + n]
-        self._cursor += n
+        lo = self._cursor + self.rank * n
+        idx = self._order[lo:lo + n]
+        self._cursor += window
         return idx
 
     @staticmethod
@@ -107,6 +117,6 @@ class SingleLabelAudioDataWrapper(AudioDataWrapper):
             wavs = np.stack([np.random.RandomState(1234 + int(i)).uniform(-1, 1, self.desired_samples) for i in idx])
             return wavs.astype(np.float32)[..., None], labels
         a = self.args
-        wavs = np.stack([self.augment(self.filenames[i], self.desired_samples, self.rng, self.background_data,
+        wavs = np.stack([self.augment(self.filenames[i], self.desired_samples, self.aug_rng, self.background_data,
                                       self.is_training, a.background_frequency, a.background_max_volume) for i in idx])
         return wavs[..., None], labels

@@ -32,7 +32,8 @@ def draw_clips(rng: np.random.RandomState, lengths: Sequence[int], silent: Seque
         clips[i]["bg_offset"] = -1
         if len(bg_lengths):
             b = int(rng.randint(0, len(bg_lengths)))
-            clips[i]["bg_offset"] = int(starts[b]) + int(rng.randint(0, bg_lengths[b] - clip_samples + 1))
+            # recordings shorter than a clip are zero-padded to clip length by DeviceInputStage (tf.random_crop would raise)
+            clips[i]["bg_offset"] = int(starts[b]) + int(rng.randint(0, max(bg_lengths[b] - clip_samples, 0) + 1))
             mixed = is_training and rng.uniform() < background_frequency
             clips[i]["bg_volume"] = np.float32(rng.uniform(0.0, background_max_volume)) if mixed else np.float32(0.0)
     return clips
@@ -49,9 +50,13 @@ class DeviceInputStage:
 
     def __init__(self, engine, background_data: Optional[Sequence[np.ndarray]] = None):
         self.engine = engine
-        self.bg_lengths = [int(b.shape[0]) for b in (background_data or [])]
-        self.background = (torch.from_numpy(np.concatenate([np.asarray(b, np.float32) for b in background_data])).to(engine.device)
-                           if background_data else None)
+        clip = int(engine.cfg.clip_samples)
+        bank = [np.asarray(b, np.float32).reshape(-1) for b in (background_data or [])]
+        bank = [np.pad(b, (0, clip - b.shape[0])) if b.shape[0] < clip else b for b in bank]     # every crop fits its recording
+        self.bg_lengths = [int(b.shape[0]) for b in bank]
+        self.background = torch.from_numpy(np.concatenate(bank)).to(engine.device) if bank else None
+        if bank:                                     # the kernel refuses crops that would run past the bank
+            engine.lib.tcr_set_background_samples(engine._h, int(sum(self.bg_lengths)))
 
     def __call__(self, pcm: torch.Tensor, clips: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         return self.engine.augment(pcm, pack(clips, self.engine.device), self.background, out=out)

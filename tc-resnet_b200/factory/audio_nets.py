@@ -132,6 +132,12 @@ class AudioNetModel(TFModel):
         if slots:
             self.engine.variables_from_dict(slots, self.slots, None, strict=False)
 
+    def _dropout_seed(self):
+        """Counter-RNG seed of this step: distinct per rank under data parallelism (the kernel indexes utterances locally)."""
+        world = getattr(self.engine, "world_size", 1)
+        rank = getattr(self.dataset, "rank", 0) if world > 1 else 0
+        return self.global_step * world + rank
+
     # ------------------------------------------------------------------ one session.run
     def execute(self, names: Set[str], feed) -> Dict[str, object]:
         wav_np, hot_np = self.dataset.next_batch()
@@ -147,13 +153,13 @@ class AudioNetModel(TFModel):
         if "train_op" in names:
             lr = float(self.lr_schedule(self.global_step))
             out = self.engine.train_step(self._d_wav, self._d_hot, self.params, self.slots, self.moving, lr,
-                                         self.optimizer.get("momentum") or 0.0, wd, dropout_seed=self.global_step,
+                                         self.optimizer.get("momentum") or 0.0, wd, dropout_seed=self._dropout_seed(),
                                          want_outputs=bool(names & {"outputs", "logits"}))
             self.global_step += 1
             vals["train_op"], vals["learning_rate"] = None, np.float32(lr)
         else:
             out = self.engine.forward(self._d_wav, self.params, self.moving, is_training=bool(self.is_training),
-                                      onehot=self._d_hot, weight_decay=wd, dropout_seed=self.global_step)
+                                      onehot=self._d_hot, weight_decay=wd, dropout_seed=self._dropout_seed())
             vals["learning_rate"] = np.float32(self.lr_schedule(self.global_step))
         losses = out["losses"].cpu().numpy()                    # the D2H read synchronises the step
         vals.update(total_loss=losses[0], model_loss=losses[1], global_step=np.int64(self.global_step),

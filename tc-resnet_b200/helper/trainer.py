@@ -32,6 +32,14 @@ class TrainerBase:
         self.dataset, self.dataset_name = dataset, dataset_name
         self.log = utils.get_logger(name)
         self.timer = utils.Timer(self.log)
+        # data parallel (one process per GPU): every rank steps, rank 0 alone writes checkpoints (the replicas are identical;
+        # BN moving statistics are rank 0's) and everybody waits for it, so no rank runs ahead into the next exchange alone
+        self.rank, self.world = 0, 1
+        if getattr(args, "data_parallel", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.is_chief = self.rank == 0
 
     # ---- setup -------------------------------------------------------------------------------
     def setup_essentials(self, max_to_keep=5):
@@ -42,7 +50,7 @@ class TrainerBase:
         self.global_step = Node("global_step")
         self.model.global_step = self.global_step_from_checkpoint
         if self.args.boundaries_epoch:
-            boundaries = [b * self.dataset.num_samples // self.dataset.batch_size for b in self.args.boundaries]
+            boundaries = [b * self.dataset.num_samples // (self.dataset.batch_size * self.world) for b in self.args.boundaries]
         else:
             boundaries = list(self.args.boundaries)
         if self.args.relative:
@@ -99,7 +107,7 @@ class TrainerBase:
 
     # ---- one step ----------------------------------------------------------------------------
     def build_epoch(self, step):
-        return (step * self.dataset.batch_size) / self.dataset.num_samples
+        return (step * self.dataset.batch_size * self.world) / self.dataset.num_samples
 
     def run_single_step(self, fetch_ops, feed_dict=None):
         t0 = time.perf_counter()
@@ -117,7 +125,8 @@ class TrainerBase:
         global_step = int(vals["global_step"])
         step_from_restore = global_step - self.global_step_from_checkpoint
         epoch_from_restore = self.build_epoch(step_from_restore)
-        if step_from_restore % max(1, self.args.step_save_summaries) == 0 or step_from_restore <= self.args.step_save_first_n_summaries:
+        if self.is_chief and (step_from_restore % max(1, self.args.step_save_summaries) == 0
+                              or step_from_restore <= self.args.step_save_first_n_summaries):
             self.log.info(f"[{self.dataset_name}] GlobalStep {global_step:8d} / StepFromRestore {step_from_restore:8d} / "
                           f"EpochFromRestore {epoch_from_restore:3.3f} | TotalLoss {vals['total_loss']:.5f} / "
                           f"ModelLoss {vals['model_loss']:.5f} | SingleStep(ms) {vals['single_step']:.3f} / "
@@ -125,8 +134,14 @@ class TrainerBase:
         return vals, global_step, step_from_restore, epoch_from_restore
 
     def save_checkpoint(self, global_step):
-        path = ckpt.save(self.args.train_dir, self.args.model, global_step, self.model.get_variables(), self.args.max_to_keep)
-        self.log.info(f"save checkpoint: {path}")
+        path = None
+        if self.is_chief:
+            path = ckpt.save(self.args.train_dir, self.args.model, global_step, self.model.get_variables(), self.args.max_to_keep,
+                             fmt=getattr(self.args, "checkpoint_format", "npz"))
+            self.log.info(f"save checkpoint: {path}")
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
         return path
 
     def train(self, name: str = "Training"):
@@ -160,7 +175,8 @@ class TrainerBase:
             eval_dict = self.run_inference(global_step, iters=iters, is_training=True)
             data = self.build_non_tensor_data_from_eval_dict(eval_dict)
             self.metric_manager.evaluate_and_aggregate_metrics(step=global_step, non_tensor_data=data, eval_dict=eval_dict)
-        self.metric_manager.log_metrics(global_step, self.log.info)
+        if self.is_chief:
+            self.metric_manager.log_metrics(global_step, self.log.info)
 
     @staticmethod
     def add_arguments(parser, name: str = "TrainerBase"):

@@ -28,11 +28,13 @@ def test_emulated_kernels_match_oracle(backend, kw):
     assert report["features"] < 1e-6
 
 
-def test_emulated_persistent_step_kernel(backend, monkeypatch):
-    """The opt-in single cooperative launch (TCR_PERSISTENT=1) runs the same phase bodies behind a grid barrier."""
-    monkeypatch.setenv("TCR_PERSISTENT", "1")
-    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=5, keep=0.5)
-    run_case(backend, model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False)
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_emulated_resident_kernels(backend, monkeypatch, mode):
+    """TCR_RESIDENT = 0 / 1 / 2: per-layer kernels, resident forward kernel, resident forward + backward kernels
+    (tcr_resident.cu; the emulator runs 3 co-resident CTAs, so ownership is ragged: 7 utterances = 3 + 2 + 2)."""
+    monkeypatch.setenv("TCR_RESIDENT", mode)
+    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=7, keep=0.5, steps=2)
+    run_case(backend, model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False)      # identity-shortcut blocks
 
 
 def test_log_mel_front_end(backend):
