@@ -56,9 +56,9 @@ class Evaluator:
                 self.best[key] = value
                 target = self.watch_path / self.dataset_name / key
                 target.mkdir(parents=True, exist_ok=True)
-                for old in target.glob("*.npz"):
+                for old in list(target.glob("*.npz")) + list(target.glob("*.index")) + list(target.glob("*.data-*")):
                     old.unlink()
-                shutil.copy(checkpoint_path, target / Path(checkpoint_path).name)
+                ckpt.copy_checkpoint(checkpoint_path, target)
                 (target / "scores.txt").write_text(f"step\t{step}\n{key}\t{value}\nmodel_size\t{self.model.total_params}\n")
 
     @staticmethod

@@ -137,7 +137,7 @@ class TrainerBase:
         path = None
         if self.is_chief:
             path = ckpt.save(self.args.train_dir, self.args.model, global_step, self.model.get_variables(), self.args.max_to_keep,
-                             fmt=getattr(self.args, "checkpoint_format", "npz"))
+                             fmt=getattr(self.args, "checkpoint_format", "tf"))
             self.log.info(f"save checkpoint: {path}")
         if self.world > 1:
             import torch.distributed as dist
@@ -210,6 +210,8 @@ class TrainerBase:
         g.add_argument("--relative_schedule", dest="relative", action="store_true")
         g.add_argument("--absolute_schedule", dest="relative", action="store_false")
         g.set_defaults(relative=True, boundaries_epoch=True)
+        g.add_argument("--checkpoint_format", default="tf", choices=["tf", "npz"],
+                       help="tf: tensor-bundle files like tf.train.Saver (<Model>-<step>.index/.data-*); npz: one NumPy archive")
         g = parser.add_argument_group("B200 data-parallel (no reference counterpart)")
         g.add_argument("--data_parallel", action="store_true",
                        help="one process per GPU under torchrun; gradients are averaged with one NCCL all-reduce per step")

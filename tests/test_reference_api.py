@@ -72,17 +72,33 @@ def test_registries_expose_the_reference_names():
     assert node.shape == [None, 98, 40, 1] and pre.preprocessed_node is node
 
 
-def test_learning_rate_schedule_and_checkpoints(tmp_path):
+@pytest.mark.parametrize("fmt", ["tf", "npz"])
+def test_learning_rate_schedule_and_checkpoints(tmp_path, fmt):
     assert [piecewise_constant(s, [10000, 20000], [0.1, 0.01, 0.001]) for s in (0, 10000, 10001, 20001)] == [0.1, 0.1, 0.01, 0.001]
     var = {"TCResNet8/conv0/weights": np.arange(6, dtype=np.float32).reshape(3, 1, 2, 1)}
     for step in (500, 1000, 1500):
-        path = ckpt.save(tmp_path, "TCResNet8Model", step, var, max_to_keep=2)
+        path = ckpt.save(tmp_path, "TCResNet8Model", step, var, max_to_keep=2, fmt=fmt)
     assert ckpt.checkpoint_step(path) == 1500 and ckpt.latest_checkpoint(tmp_path) == path
-    assert len(list(tmp_path.glob("*.npz"))) == 2                  # max_to_keep
+    assert len(list(tmp_path.glob("*.npz" if fmt == "npz" else "*.index"))) == 2      # max_to_keep
+    assert not list(tmp_path.glob("*-500*"))
     back = ckpt.load(path)
     assert int(back["global_step"]) == 1500
     np.testing.assert_array_equal(back["TCResNet8/conv0/weights"], var["TCResNet8/conv0/weights"])
     assert next(ckpt.checkpoints_iterator(tmp_path, timeout=0)) == path
+    (tmp_path / ".TCResNet8Model-9999.123.tmp").write_bytes(b"partial")              # an in-progress save is never picked up
+    assert ckpt.latest_checkpoint(tmp_path) == path
+
+
+def test_concurrent_saves_into_one_directory_do_not_collide(tmp_path):
+    """Several processes saving the same step (a mis-configured data-parallel run) must not trip over each other's temporary files."""
+    import multiprocessing as mp
+    var = {"v": np.arange(1000, dtype=np.float32)}
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=lambda: [ckpt.save(tmp_path, "M", s, var, fmt="tf") for s in range(1, 11)]) for _ in range(4)]
+    [p.start() for p in procs]
+    [p.join() for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    np.testing.assert_array_equal(ckpt.load(ckpt.latest_checkpoint(tmp_path))["v"], var["v"])
 
 
 def test_session_requires_a_bound_model():
