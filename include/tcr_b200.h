@@ -192,6 +192,18 @@ int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_features, co
                 const float* dropout_mask, const float* onehot, float weight_decay,
                 float* logits, float* probs, float* losses, tcr_stream stream);
 
+/* The evaluation consumer behind the forward pass, on the device: reduces one batch of scores and
+ * one-hot labels to the integers every count-based metric of the reference is a function of, instead of shipping
+ * [n, classes] arrays to the host per batch (helper/base.py:52-143, metrics/parser.py:135-147; accuracy, top-5, precision,
+ * recall, F1, classification report: metrics/ops/non_tensor_ops.py:64-142, :146-295, :346-).
+ *   scores  device [n, classes]: logits or softmax outputs of tcr_forward (arg-max and ranks are the same for both)
+ *   onehot  device [n, classes]
+ *   counts  device int64 [classes*classes + 2], ACCUMULATED (zero it before the first batch):
+ *           [y*classes + p] confusion matrix (true row, predicted column; first maximum wins like np.argmax),
+ *           [classes*classes] utterances whose true class is among the `topk` best scores, [classes*classes + 1] utterances */
+int tcr_eval_accumulate(tcr_handle* h, const float* scores, const float* onehot, int32_t n, int32_t topk, int64_t* counts,
+                        tcr_stream stream);
+
 /* Forward + backward + SGD-momentum + BN moving-average update (helper/trainer.py:171-222,
  * slim.learning.create_train_op).  With a communicator attached (tcr_comm_init) gradients are
  * averaged over ranks with one ncclAllReduce before the update. */

@@ -494,6 +494,16 @@ extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_f
   return TCR_OK;
 }
 
+extern "C" int tcr_eval_accumulate(tcr_handle* h, const float* scores, const float* onehot, int32_t n, int32_t topk, int64_t* counts,
+                                   tcr_stream stream) {
+  if (!h || !scores || !onehot || !counts) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (n <= 0) return fail(TCR_ERR_INVALID, "n must be positive (got %d)", n);
+  if (topk < 1) return fail(TCR_ERR_INVALID, "topk must be at least 1");
+  eval_accumulate_launch(scores, onehot, n, h->cfg.num_classes, topk, counts, (cudaStream_t)stream);
+  TCR_CUDA(cudaGetLastError());
+  return TCR_OK;
+}
+
 extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream stream) {
   pdl_chain_reset();
   if (!h || !a || !a->input || !a->onehot || !a->params) return fail(TCR_ERR_INVALID, "NULL argument");

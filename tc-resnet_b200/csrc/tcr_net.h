@@ -20,6 +20,7 @@ int cluster_size(tcr_handle* h);
 StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n);
 int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_clip* clips, const float* background, int64_t background_samples,
                    float* out, int clip, int n, cudaStream_t s);
+int eval_accumulate_launch(const float* scores, const float* onehot, int n, int classes, int topk, int64_t* counts, cudaStream_t s);
 int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
 // Resident forward (tcr_resident.cu): the training forward + head as one cooperative kernel with SM-resident activations.
 int resident_mode(tcr_handle* h);      // 0: per-layer kernels, 1: resident forward, 2: resident forward + backward

@@ -219,6 +219,17 @@ class Engine:
         L.check(self.lib, self.lib.tcr_train_step(self._h, C.byref(a), self._stream), "tcr_train_step")
         return out
 
+    def eval_accumulate(self, scores: torch.Tensor, onehot: torch.Tensor, counts: Optional[torch.Tensor] = None, topk: int = 5) -> torch.Tensor:
+        """Adds one batch to the device-resident evaluation counts (int64 [C*C + 2]: confusion matrix, top-k hits, samples);
+        see tcr_eval_accumulate in include/tcr_b200.h.  metrics.manager.metrics_from_counts turns them into the reference's metrics."""
+        n, c = scores.shape[0], self.num_classes
+        if counts is None:
+            counts = torch.zeros(c * c + 2, dtype=torch.int64, device=self.device)
+        assert counts.is_cuda and counts.dtype == torch.int64 and counts.numel() == c * c + 2
+        L.check(self.lib, self.lib.tcr_eval_accumulate(self._h, self._ptr(scores), self._ptr(onehot), n, int(topk), counts.data_ptr(),
+                                                       self._stream), "tcr_eval_accumulate")
+        return counts
+
     # ------------------------------------------------------------------ data parallel
     def attach_process_group(self):
         """One NCCL communicator per handle; the 128-byte unique id travels through torch.distributed."""

@@ -39,6 +39,7 @@ class AudioNetModel(TFModel):
         self.var_names_to_values = None                            # in-memory weight injection hook (trainer.py:145-154)
         self.endpoints_loss: Dict[str, Node] = {}
         self._last: Dict[str, np.ndarray] = {}
+        self._counts = None                                        # device int64 [classes^2 + 2] (tcr_eval_accumulate)
 
     # ------------------------------------------------------------------ graph-construction API of the reference
     def build(self, wavs, labels, is_training):
@@ -138,6 +139,15 @@ class AudioNetModel(TFModel):
         rank = getattr(self.dataset, "rank", 0) if world > 1 else 0
         return self.global_step * world + rank
 
+    def read_metric_counts(self, reset: bool = True) -> np.ndarray:
+        """Confusion matrix / top-5 hits / sample count accumulated by the forward passes since the last reset (one D2H read)."""
+        if self._counts is None:
+            return np.zeros(self.args.num_classes ** 2 + 2, np.int64)
+        out = self._counts.cpu().numpy()
+        if reset:
+            self._counts.zero_()
+        return out
+
     # ------------------------------------------------------------------ one session.run
     def execute(self, names: Set[str], feed) -> Dict[str, object]:
         wav_np, hot_np = self.dataset.next_batch()
@@ -161,6 +171,11 @@ class AudioNetModel(TFModel):
             out = self.engine.forward(self._d_wav, self.params, self.moving, is_training=bool(self.is_training),
                                       onehot=self._d_hot, weight_decay=wd, dropout_seed=self._dropout_seed())
             vals["learning_rate"] = np.float32(self.lr_schedule(self.global_step))
+        if "metric_counts" in names:                            # evaluation counts stay on the device until read_metric_counts()
+            if self._counts is None:
+                self._counts = torch.zeros(self.args.num_classes ** 2 + 2, dtype=torch.int64, device=self.engine.device)
+            self.engine.eval_accumulate(out["probs"], self._d_hot, self._counts, topk=5)
+            vals["metric_counts"] = None
         losses = out["losses"].cpu().numpy()                    # the D2H read synchronises the step
         vals.update(total_loss=losses[0], model_loss=losses[1], global_step=np.int64(self.global_step),
                     labels=hot_np, audio_original=wav_np)

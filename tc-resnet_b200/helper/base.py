@@ -50,11 +50,14 @@ class Base(ABC):
                 self.log.error(f"Invalid instance is detected: {e}")
                 continue
             for k, v in vals.items():
-                if k in agg:
+                if k in agg and v is not None:
                     agg[k].append(np.atleast_1d(v))
             agg["batch_infer_time"].append(np.atleast_1d(ms))
             agg["unit_infer_time"].append(np.atleast_1d(ms / self.args.batch_size))
-        return {k: np.vstack(v) for k, v in agg.items() if v}
+        out = {k: np.vstack(v) for k, v in agg.items() if v}
+        if "metric_counts" in fetch_ops:                               # ONE device-to-host read per evaluation
+            out["metric_counts"] = self.model.read_metric_counts(reset=True)
+        return out
 
     def run_evaluation(self, global_step: int, iters: int = None, is_training: bool = False):
         eval_dict = self.run_inference(global_step, iters, is_training, do_eval=True)
@@ -76,8 +79,12 @@ class AudioBase(Base):
     def build_evaluation_fetch_ops(self, do_eval):
         if not do_eval:
             return {"predictions_onehot": self.model.outputs}
-        ops = {"labels_onehot": self.model.labels, "predictions_onehot": self.model.outputs,
-               "total_loss": self.model.total_loss}
+        if getattr(self.args, "device_metrics", False):
+            from ..runtime import Node
+            ops = {"metric_counts": Node("metric_counts"), "total_loss": self.model.total_loss}
+        else:
+            ops = {"labels_onehot": self.model.labels, "predictions_onehot": self.model.outputs,
+                   "total_loss": self.model.total_loss}
         ops.update(self.metric_tf_op)
         return ops
 
@@ -88,4 +95,5 @@ class AudioBase(Base):
 
     def build_non_tensor_data_from_eval_dict(self, eval_dict, **kwargs):
         return {"dataset_split_name": self.dataset.dataset_split_name, "label_names": self.dataset.label_names,
-                "predictions_onehot": eval_dict["predictions_onehot"], "labels_onehot": eval_dict["labels_onehot"]}
+                "predictions_onehot": eval_dict.get("predictions_onehot"), "labels_onehot": eval_dict.get("labels_onehot"),
+                "metric_counts": eval_dict.get("metric_counts")}

@@ -26,12 +26,36 @@ def average_precision(y_true, score):
     return float(np.sum((hits / (np.arange(len(y)) + 1)) * y) / y.sum())
 
 
+def metrics_from_counts(counts, label_names=None, use_class_metrics: bool = False) -> Dict[str, object]:
+    """The count-based metrics of the reference (accuracy, top-5, per-class precision / recall / F1, confusion matrix:
+    metrics/ops/non_tensor_ops.py:64-295) from the integers tcr_eval_accumulate leaves on the device:
+    counts[:C*C] confusion matrix (true row, predicted column), counts[C*C] top-k hits, counts[C*C+1] samples."""
+    counts = np.asarray(counts, np.int64)
+    c = int(round((counts.size - 2) ** 0.5))
+    cm = counts[:c * c].reshape(c, c)
+    n = max(int(counts[c * c + 1]), 1)
+    res: Dict[str, object] = {"accuracy": float(np.trace(cm)) / n, "top5_accuracy": float(counts[c * c]) / n}
+    if use_class_metrics:
+        for k, name in enumerate(label_names or [str(i) for i in range(c)]):
+            tp = float(cm[k, k])
+            prec = tp / max(float(cm[:, k].sum()), 1.0)
+            rec = tp / max(float(cm[k, :].sum()), 1.0)
+            res[f"precision/{name}"], res[f"recall/{name}"] = prec, rec
+            res[f"f1score/{name}"] = 2 * prec * rec / max(prec + rec, 1e-12)
+    res["confusion_matrix"] = cm.astype(np.float64)
+    return res
+
+
 class MetricManagerBase:
     @staticmethod
     def add_arguments(parser):
         g = parser.add_argument_group("Metric Manager Arguments")
         g.add_argument("--exclude_metric_names", nargs="*", default=[], type=str)
         g.add_argument("--max_summary_outputs", default=3, type=int)
+        g.add_argument("--host_metrics", dest="device_metrics", action="store_false",
+                       help="ship every batch's [batch, classes] outputs to the host and compute the metrics there (adds mAP, which "
+                            "needs the full score ranking); default: confusion-matrix counts accumulated on the device")
+        g.set_defaults(device_metrics=True)
 
 
 class AudioMetricManager(MetricManagerBase):
@@ -48,6 +72,12 @@ class AudioMetricManager(MetricManagerBase):
         return {"accuracy": "max"}
 
     def evaluate_and_aggregate_metrics(self, step, non_tensor_data, eval_dict):
+        if non_tensor_data.get("metric_counts") is not None:          # device path: classes^2 + 2 integers per evaluation
+            res = metrics_from_counts(non_tensor_data["metric_counts"], non_tensor_data["label_names"], self.use_class_metrics)
+            if "total_loss" in eval_dict:
+                res["total_loss"] = float(np.mean(eval_dict["total_loss"]))
+            self.results[int(step)] = {k: v for k, v in res.items() if k not in self.exclude}
+            return
         labels, preds = non_tensor_data["labels_onehot"], non_tensor_data["predictions_onehot"]
         y, p = labels.argmax(1), preds.argmax(1)
         res = {"accuracy": float(np.mean(y == p)), "top5_accuracy": topn_accuracy(labels, preds, 5)}

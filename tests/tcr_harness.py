@@ -199,6 +199,22 @@ class Engine:
                     grads=b.download(grads), params=b.download(params), slots=b.download(slots),
                     moving=b.download(moving))
 
+    def eval_accumulate(self, scores_np, onehot_np, topk=5, counts_np=None):
+        """tcr_eval_accumulate through the C ABI: returns the accumulated int64 counts [C*C + 2]."""
+        b = self.b
+        n, c = scores_np.shape
+        scores, onehot = b.upload(scores_np), b.upload(onehot_np)
+        init = np.zeros(c * c + 2, np.int64) if counts_np is None else np.asarray(counts_np, np.int64)
+        if b.name == "cuda":
+            counts = b.torch.from_numpy(init.copy()).to(b.dev)
+            ptr = counts.data_ptr()
+        else:
+            counts = init.copy()
+            ptr = counts.ctypes.data
+        L.check(self.lib, self.lib.tcr_eval_accumulate(self.h, b.ptr(scores), b.ptr(onehot), n, topk, ptr, b.stream), "tcr_eval_accumulate")
+        b.sync()
+        return counts.cpu().numpy() if b.name == "cuda" else counts
+
     def workspace(self, name):
         p = C.c_void_p()
         numel = C.c_int64()
