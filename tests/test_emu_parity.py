@@ -37,6 +37,19 @@ def test_emulated_resident_kernels(backend, monkeypatch, mode):
     run_case(backend, model="TCResNet14", wm=1.0, window=480, stride=160, n=2, use_wav=False)      # identity-shortcut blocks
 
 
+def test_mask_forced_gradient_comparison(backend):
+    """The oracle run with the CUDA path's own ReLU decisions (rebuilt from the workspace tensors): same bounds, no fp32 floor."""
+    report = run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=6, keep=0.5, force_masks=True)
+    assert report["grads0"] < 1e-4
+
+
+def test_unsupported_width_status(backend):
+    """Channel counts that are not multiples of 4 (width 0.75 -> 18) are refused with TCR_ERR_UNSUPPORTED, never computed wrongly."""
+    from tcresnet_b200._lib import TcrError
+    with pytest.raises(TcrError, match=r"status 3.*multiple of 4"):
+        Engine(backend, width_multiplier=0.75)
+
+
 def test_log_mel_front_end(backend):
     eng = Engine(backend, feature_kind=1, max_batch=4)
     wav, _ = O.synthetic_batch(2, adversarial=True)
