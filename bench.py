@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--rotate", type=int, default=8, help="distinct resident input batches (footprint > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of BASELINE.json configs 3 and 5 carried in `extra`")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer", "augment"],
                     help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point); "
@@ -270,8 +271,13 @@ def kernel_work(plan, name, n):
     if name == "weight_transpose":
         w = sum(c.weights for c in plan.convs())
         return 8.0 * w, 0.0
-    if name == "step_persistent":     # the whole step behind the front-end in one cooperative launch
-        return n * (plan.min_bytes(n) - 4 * plan.clip), n * (plan.train_flops() - plan.frontend_flops())
+    fwd_flops = 2.0 * n * sum(c.macs for c in plan.convs())
+    if name == "resident_fwd":        # all forward convs + head in one cooperative launch: reads the features, writes every pre-BN output
+        b = n * (4 * plan.frames * plan.features + sum(4 * c.t_out * c.cout for c in plan.convs())) + 4 * sum(c.weights for c in plan.convs())
+        return b, fwd_flops
+    if name == "resident_bwd":        # backward-data chain + all weight gradients + gradient reduction
+        b = n * (4 * plan.frames * plan.features + sum(4 * c.t_out * c.cout for c in plan.convs())) + 12 * sum(c.weights for c in plan.convs())
+        return b, 2 * fwd_flops - 2.0 * n * plan.convs()[0].macs
     return 12.0 * plan.num_trainable, 4.0 * plan.num_trainable      # grad_finalize / update: params, slots, grads
 
 
@@ -375,21 +381,29 @@ def run_ours(a):
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_tcresnet8_b512.json")))
-            if a.model == "TCResNet8" and a.width == 1.0 and n == 512:
+            if tj.get("kernels_sha") != sources_sha():           # a capture of OTHER kernels is not evidence for these
+                traffic_src = f"stale capture ignored ({tj.get('source')}: kernels_sha {tj.get('kernels_sha')} != {sources_sha()})"
+            elif a.model == "TCResNet8" and a.width == 1.0 and n == 512:
                 ncu_name = {"mfcc": "mfcc_kernel", "dw_grouped": "dw_grouped_kernel", "head": "head_kernel",
-                            "step_persistent": "step_kernel"}.get(dom["name"])
+                            "resident_fwd": "resident_fwd_kernel", "resident_bwd": "resident_bwd_kernel"}.get(dom["name"])
                 for k, v in tj["bytes_per_launch"].items():
                     if ncu_name and k.startswith(ncu_name):
                         traffic, traffic_src = v, f"profiles/ncu_traffic_tcresnet8_b512.json ({tj['source']})"
         except Exception:
             pass
-        alg_bytes = kernel_work(plan, dom["name"], n)[0]
-        out["roofline"] = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                           "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                           "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                           "kernel_share_of_step": dom["share"],
-                           "fp32": {"achieved_tflops": dom["TFLOPs"], "peak_tflops": fp32_peak, "frac": dom["TFLOPs"] / max(fp32_peak, 1e-9),
-                                    "peak_source": "measured in this run (tcr_measure_fp32_peak, FMA loop on all SMs)"},
+        alg_bytes, alg_flops = kernel_work(plan, dom["name"], n)
+        # which pipe binds this kernel: the larger of its two floors (bytes / HBM peak, flops / fp32-FMA peak)
+        t_hbm, t_fma = alg_bytes / (hbm_peak * 1e9), alg_flops / max(fp32_peak * 1e12, 1.0)
+        hbm_form = {"achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["GBps"] / hbm_peak, "peak_source": peak_src}
+        fma_form = {"achieved": dom["TFLOPs"], "peak": fp32_peak, "unit": "TFLOP/s", "frac": dom["TFLOPs"] / max(fp32_peak, 1e-9),
+                    "peak_source": "fp32 FMA pipe, measured in this run (tcr_measure_fp32_peak: FMA loop on all SMs); the convolutions run on "
+                                   "the FMA pipe because single TF32 / BF16 products miss the 1e-4 logit bound (DESIGN.md)"}
+        binding = fma_form if t_fma > t_hbm else hbm_form
+        out["roofline"] = {"bound": "fp32-fma" if t_fma > t_hbm else "hbm", "kernel": dom["name"], "achieved": binding["achieved"],
+                           "peak": binding["peak"], "unit": binding["unit"], "frac": binding["frac"], "traffic": traffic,
+                           "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
+                           "algorithmic_flops_per_launch": alg_flops, "floors_us": {"hbm": t_hbm * 1e6, "fp32_fma": t_fma * 1e6},
+                           "kernel_us": dom["us"], "kernel_share_of_step": dom["share"], "hbm": hbm_form, "fp32": fma_form,
                            "step": {"train_flops_per_utt": plan.train_flops(), "min_bytes_per_utt": plan.min_bytes(n),
                                     "fp32_frac": plan.train_flops() * (value / world) / 1e12 / max(fp32_peak, 1e-9),
                                     "hbm_frac": plan.min_bytes(n) * (value / world) / 1e9 / hbm_peak}}
@@ -467,6 +481,19 @@ def run_ours(a):
                       "api": "C ABI tcr_train_step_host (tcresnet_b200.engine.HostFeed.submit, lag 2): pinned host fp32 wav + one-hot -> H2D on "
                              "the library's copy stream every step, the step, both losses of every step read back to the host"}
 
+    # ---- BASELINE.json configs 3 and 5, short device-timed runs carried inside the N = 1 line (so a driver-run record exists) ----
+    if rank == 0 and world == 1 and not a.no_extra and a.model == "TCResNet8" and a.width == 1.0:
+        out["extra"] = {}
+        try:
+            del wavs, onehots
+            torch.cuda.empty_cache()
+            out["extra"]["TCResNet14-1.5_b1024_train"] = quick_train(torch, dev, "TCResNet14", 1.5, 1024, a.window_ms, a.stride_ms, fp32_peak)
+        except Exception as e:
+            out["extra"]["TCResNet14-1.5_b1024_train"] = {"error": str(e)[:200]}
+        try:
+            out["extra"]["DSCNN-S_b512_forward"] = quick_dscnn(torch, dev, 512)
+        except Exception as e:
+            out["extra"]["DSCNN-S_b512_forward"] = {"error": str(e)[:200]}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             try:
@@ -477,6 +504,59 @@ def run_ours(a):
         emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def quick_train(torch, dev, model, width, batch, window_ms, stride_ms, fp32_peak, steps=40, warmup=6, rot=4):
+    """Short device-timed training-step run of another configuration (inputs rotate over `rot` resident batches)."""
+    from tcresnet_b200.engine import Engine
+    from tcresnet_b200.plan import build_plan
+    eng = Engine(model=model, width_multiplier=width, window_size_ms=window_ms, window_stride_ms=stride_ms, max_batch=batch, dropout_keep_prob=0.5)
+    plan = build_plan(model, width, window_size_ms=window_ms, window_stride_ms=stride_ms)
+    params, slots, moving = eng.new_variables(seed=0)
+    gen = torch.Generator(device=dev).manual_seed(99)
+    wavs = [torch.rand(batch, plan.clip, device=dev, generator=gen) * 2 - 1 for _ in range(rot)]
+    hots = [torch.nn.functional.one_hot(torch.randint(0, 12, (batch,), device=dev, generator=gen), 12).float().contiguous() for _ in range(rot)]
+    losses = torch.zeros(2, device=dev)
+    for i in range(warmup):
+        eng.train_step(wavs[i % rot], hots[i % rot], params, slots, moving, 0.1, 0.9, 1e-3, dropout_seed=i, losses=losses)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.train_step(wavs[i % rot], hots[i % rot], params, slots, moving, 0.1, 0.9, 1e-3, dropout_seed=i, losses=losses)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    value = batch / (ms * 1e-3)
+    eng.close()
+    return {"metric": f"utterances/sec (fwd+bwd+update) {model}-{width:g}", "value": value, "ms_per_step": ms, "batch": batch, "steps": steps,
+            "warmup": warmup, "l2": f"inputs rotate over {rot} resident batches ({rot * batch * plan.clip * 4 / 1e6:.0f} MB > 126 MB L2)",
+            "final_total_loss": float(losses[0].item()), "train_flops_per_utt": plan.train_flops(),
+            "fp32_frac": plan.train_flops() * value / 1e12 / max(fp32_peak, 1e-9)}
+
+
+def quick_dscnn(torch, dev, n, steps=40, warmup=6, rot=8):
+    from tcresnet_b200.dscnn import DsCnn
+    net = DsCnn("S", 49, 40, 12, max_batch=n)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    params = torch.randn(net.num_params, device=dev, generator=gen) * 0.1
+    for d in net.table:
+        if d["name"].endswith("moving_variance"):
+            params[d["offset"]:d["offset"] + d["numel"]] = 1.0
+    feats = [torch.randn(n, 49, 40, device=dev, generator=gen) for _ in range(rot)]
+    for i in range(warmup):
+        net.forward(feats[i % rot], params)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        net.forward(feats[i % rot], params)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "utterances/sec (forward) DS-CNN-S", "value": n / (ms * 1e-3), "ms_per_step": ms, "batch": n, "steps": steps,
+            "forward_flops_per_utt": net.forward_flops, "tflops": n / (ms * 1e-3) * net.forward_flops / 1e12,
+            "pointwise": "tcgen05 3xTF32 (csrc/tcr_dscnn.cu)" if os.environ.get("TCR_DSCNN_TC", "1") != "0" else "fp32 FMA"}
 
 
 def run_infer(a):

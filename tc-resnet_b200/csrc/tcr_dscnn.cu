@@ -9,6 +9,7 @@
 // BatchNorm here has no gamma (slim default scale=False) and uses the moving statistics; bias + BN fold into one
 // per-channel (scale, shift) pair computed while staging.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -179,6 +180,197 @@ __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH
   }
 }
 
+// ---- depthwise-separable block with the pointwise 1x1 conv on the 5th-generation tensor cores (tcgen05 / UMMA) ----
+// The pointwise conv IS a dense [positions, C] x [C, CO] contraction (audio_nets/ds_cnn.py:56-59), 77 % of DS-CNN-S's FLOPs.
+// Per CTA: 128 accumulator rows (RH output rows x wout positions, RH * wout <= 128) x CO columns in TMEM.
+//   * single TF32 products miss the 1e-4 logit bound (6.7e-4 relative on a K = 64 dot product, tools/ubench/umma_tf32.cu), so every
+//     operand is split x = hi + lo with hi = x truncated to TF32 (low 13 mantissa bits cleared, lo = x - hi exact) and three MMAs
+//     accumulate lo*hi + hi*lo + hi*hi in fp32: 4e-7 relative, the same as the FMA kernel;
+//   * operands sit in shared memory in UMMA's canonical K-major no-swizzle layout, element (row, k) at float offset
+//     (k / 4) * LBO + row * 4 + k % 4: an 8-row core matrix is 128 contiguous bytes, 8-row groups are 128 B apart (SBO) and the
+//     K-chunk stride LBO is padded by 16 B so that neither the depthwise stage's float4 stores nor the filter staging conflict;
+//   * one thread issues the 3 * C/8 tcgen05.mma (M = 128, N = CO, K = 8) and commits them to an mbarrier; all 8 warps then read
+//     their TMEM lane quarter (warp % 4) and column half (warp / 4) with tcgen05.ld, apply the folded BatchNorm + ReLU, store.
+// The input rows are staged channel-chunk-major ([C/4][rows*wp][4]) so that lanes walking positions read conflict-free float4s.
+#ifndef TCR_EMU
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);                  // start address >> 4, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;         // leading (K-chunk) byte offset >> 4, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;         // stride (8-row group) byte offset >> 4, bits [32,46)
+  d |= (uint64_t)1 << 46;                                   // descriptor version 1 (sm_100); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void tf32_split(float4 v, float4& hi, float4& lo) {
+  hi = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                   __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+  lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+}
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
+  const uint32_t bytes = valid ? 16u : 0u;                        // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes) : "memory");
+}
+
+// Persistent: a CTA keeps the split filter bank, the TMEM allocation and the per-channel tables for all its tiles
+// (tile = RH output rows of one utterance), and the next tile's input rows travel (cp.async) while the current tile is computed.
+__global__ void __launch_bounds__(256, 1) dscnn_dsblock_tc_kernel(DsLayerDev L, int RH, int tmem_cols, int n_utt, const float* __restrict__ params,
+                                                                  const float* __restrict__ in, float* __restrict__ out, float eps) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int C = L.cin, CO = L.cout, C4 = C >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hin_t = (RH - 1) * L.sh + L.kh;
+  const int wp = (L.wout - 1) * L.sw + L.kw;
+  const int XP = hin_t * wp * 4 + 4;                              // floats per channel chunk of the input tile (+16 B against conflicts)
+  const int LBA = 128 * 4 + 4, LBB = CO * 4 + 4;                  // K-chunk strides of the A / B operand tiles (floats)
+  float* xs0 = smem;                                              // [2][C4][XP]
+  float* a_hi = xs0 + (size_t)2 * C4 * XP;                        // [C4][LBA]
+  float* a_lo = a_hi + (size_t)C4 * LBA;
+  float* b_hi = a_lo + (size_t)C4 * LBA;                          // [C4][LBB]
+  float* b_lo = b_hi + (size_t)C4 * LBB;
+  float* dws = b_lo + (size_t)C4 * LBB;                           // [kh*kw][C]
+  float* sc1 = dws + L.kh * L.kw * C;
+  float* sf1 = sc1 + C;
+  float* sc2 = sf1 + C;
+  float* sf2 = sc2 + CO;
+  const int tpu = (L.hout + RH - 1) / RH;                         // tiles per utterance
+  const int ntiles = tpu * n_utt;
+  if (tid == 0) mbar_init(&mma_bar, 1);
+  if (warp == 0) {                                               // TMEM: 128 lanes x tmem_cols fp32 columns for the accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // pointwise filters pw[ci][co] -> B operand [n = co][k = ci], hi / lo parts (params are caller-owned: independent of the producer)
+  for (int i0 = tid; i0 < C * CO; i0 += 256 * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = i0 + 256 * j < C * CO ? __ldg(params + L.pw + i0 + 256 * j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + 256 * j;
+      if (i < C * CO) {
+        const int ci = i / CO, co = i - ci * CO;
+        const float hi = __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+        const int o = (ci >> 2) * LBB + co * 4 + (ci & 3);
+        b_hi[o] = hi;
+        b_lo[o] = v[j] - hi;
+      }
+    }
+  }
+  for (int i = tid; i < L.kh * L.kw * C / 4; i += 256) st4(dws + 4 * i, ldg4(params + L.w + 4 * i));
+  for (int c = tid; c < C; c += 256) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc1, sf1);
+  for (int c = tid; c < CO; c += 256) fold_bn(params, L.pb, L.pbeta, L.pmm, L.pmv, c, eps, sc2, sf2);
+  pdl_wait();
+  // input rows (+halo) of a tile, channel-chunk-major, asynchronously
+  auto fetch_tile = [&](int tile, float* xs) {
+    const int n = tile / tpu, h0 = (tile - n * tpu) * RH;
+    const RowWalk w = row_walk(tid, 256, C4);
+    const int rows = hin_t * wp;
+    if (w.row < rows) {
+      int r = w.row / wp, col = w.row - r * wp;
+      for (int row = w.row; row < rows; row += w.rstep) {
+        const int h = h0 * L.sh - L.pt + r, x = col - L.pl;
+        const bool ok = h >= 0 && h < L.hin && x >= 0 && x < L.win;
+        cp_async16_zfill(xs + (size_t)w.c4 * XP + 4 * row, ok ? in + (((size_t)n * L.hin + h) * L.win + x) * C + 4 * w.c4 : in, ok);
+        col += w.rstep;
+        while (col >= wp) { col -= wp; ++r; }
+      }
+    }
+  };
+  int tile = blockIdx.x, cur = 0;
+  uint32_t parity = 0;
+  if (tile < ntiles) fetch_tile(tile, xs0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+    const int n = tile / tpu, h0 = (tile - n * tpu) * RH, rh = imin(RH, L.hout - h0);
+    float* xs = xs0 + (size_t)cur * C4 * XP;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                             // this tile's rows have landed; the previous epilogue is done
+    if (tile + (int)gridDim.x < ntiles) fetch_tile(tile + gridDim.x, xs0 + (size_t)(cur ^ 1) * C4 * XP);
+    // depthwise conv + folded BN + ReLU, written as the A operand (hi / lo); lanes walk positions, a warp keeps one channel chunk
+    const int npos = rh * L.wout;
+    for (int task = tid; task < 128 * C4; task += 256) {
+      const int m = task & 127, c4 = task >> 7;
+      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+      if (m < npos) {
+        const int oh = m / L.wout, ow = m - oh * L.wout;
+        const float* xb = xs + (size_t)c4 * XP + 4 * ((oh * L.sh) * wp + ow * L.sw);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < L.kh; ++i)
+          for (int j = 0; j < L.kw; ++j) {
+            const float4 x = ld4(xb + 4 * (i * wp + j));
+            const float4 k = ld4(dws + (i * L.kw + j) * C + 4 * c4);
+            acc.x = fmaf(x.x, k.x, acc.x); acc.y = fmaf(x.y, k.y, acc.y); acc.z = fmaf(x.z, k.z, acc.z); acc.w = fmaf(x.w, k.w, acc.w);
+          }
+        const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
+        tf32_split(make_float4(fmaxf(fmaf(acc.x, s.x, t.x), 0.f), fmaxf(fmaf(acc.y, s.y, t.y), 0.f), fmaxf(fmaf(acc.z, s.z, t.z), 0.f),
+                               fmaxf(fmaf(acc.w, s.w, t.w), 0.f)), hi, lo);
+      }
+      st4(a_hi + (size_t)c4 * LBA + 4 * m, hi);                  // rows past npos are zero: their accumulator rows are never stored
+      st4(a_lo + (size_t)c4 * LBA + 4 * m, lo);
+    }
+    fence_proxy_async();                                         // generic-proxy stores of the operands -> visible to the async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      uint32_t accumulate = 0;
+      for (int pass = 0; pass < 3; ++pass) {                     // lo*hi, hi*lo, hi*hi: the small terms first
+        const float* ap = pass == 0 ? a_lo : a_hi;
+        const float* bp = pass == 1 ? b_lo : b_hi;
+        for (int ks = 0; ks < C / 8; ++ks) {                     // one MMA covers K = 8 = two 4-wide chunks
+          const uint64_t da = umma_desc(smem_u32(ap + (size_t)2 * ks * LBA), (uint32_t)LBA * 4u, 128u);
+          const uint64_t db = umma_desc(smem_u32(bp + (size_t)2 * ks * LBB), (uint32_t)LBB * 4u, 128u);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+          accumulate = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)) : "memory");
+    }
+    mbar_wait(&mma_bar, parity);
+    parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: accumulator row m = 32 * (warp % 4) + lane, columns [(warp / 4) * CO / 2, + CO / 2) in batches of 16
+    {
+      const int m = 32 * (warp & 3) + lane, cbase = (warp >> 2) * (CO >> 1);
+      const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
+      for (int c0 = 0; c0 < (CO >> 1); c0 += 16) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cbase + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < npos) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int co = cbase + c0 + j;
+            const float4 s = ld4(sc2 + co), t = ld4(sf2 + co);
+            st4(out + (gbase + m) * CO + co,
+                make_float4(fmaxf(fmaf(__uint_as_float(r[j]), s.x, t.x), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 1]), s.y, t.y), 0.f),
+                            fmaxf(fmaf(__uint_as_float(r[j + 2]), s.z, t.z), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 3]), s.w, t.w), 0.f)));
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the TMEM reads are ordered before the next tile's MMAs (sync at loop top)
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+#endif
+
 // ---- head: one CTA per utterance ----
 __global__ void __launch_bounds__(256) dscnn_head_kernel(int npos, int C, int classes, int64_t fcw, int64_t fcb,
                                                          const float* __restrict__ params, const float* __restrict__ in,
@@ -230,6 +422,8 @@ struct tcr_dscnn {
   int64_t n_params = 0, flops = 0;
   float* act[2] = {nullptr, nullptr};
   size_t act_floats = 0;
+  int sms = 148;
+  bool use_tc = true;        // pointwise convs on tcgen05 where they fit (env TCR_DSCNN_TC=0: register-tiled FMA everywhere)
 };
 
 static void ds_same(int len, int k, int s, int* out, int* lead) {
@@ -248,6 +442,7 @@ extern "C" int tcr_dscnn_create(const tcr_dscnn_config* cfg, tcr_dscnn** out) {
   }
   tcr_dscnn* d = new tcr_dscnn();
   d->cfg = *cfg;
+  if (const char* e = getenv("TCR_DSCNN_TC")) d->use_tc = e[0] != '0';
   struct Def { int type, depth, kh, kw, sh, sw; const char* scope; };
   std::vector<Def> defs;
   if (cfg->size == 'S') {
@@ -316,6 +511,9 @@ extern "C" int tcr_dscnn_create(const tcr_dscnn_config* cfg, tcr_dscnn** out) {
   d->flops += 2ll * cin * cfg->num_classes;
   d->n_params = off;
   if (cudaSetDevice(cfg->device) != cudaSuccess) { delete d; set_error("cudaSetDevice failed"); return TCR_ERR_CUDA; }
+#ifndef TCR_EMU
+  cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+#endif
   for (int i = 0; i < 2; ++i)
     if (cudaMalloc((void**)&d->act[i], d->act_floats * cfg->max_batch * sizeof(float)) != cudaSuccess) {
       tcr_dscnn_destroy(d);
@@ -371,6 +569,29 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
         return (size_t)((size_t)hin_t * wp * L.cin + (size_t)RH * L.wout * L.cin + (size_t)L.cin * L.cout + L.kh * L.kw * L.cin +
                         2 * L.cin + 2 * L.cout) * 4;
       };
+#ifndef TCR_EMU
+      // pointwise conv on the tensor cores (tcgen05, 3xTF32) when the operand tiles fit: channel counts multiples of 8 / 32, <= 128
+      if (d->use_tc && L.cin % 8 == 0 && L.cout % 32 == 0 && L.cout <= 128 && L.wout <= 128) {
+        int RHt = std::min(L.hout, 128 / L.wout);
+        // balanced chunks of rows: 25 rows at <= 6 per tile -> 5 tiles of 5
+        RHt = (L.hout + ((L.hout + RHt - 1) / RHt) - 1) / ((L.hout + RHt - 1) / RHt);
+        const int hin_t = (RHt - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw, C4 = L.cin / 4;
+        const size_t smem_tc = (2 * (size_t)C4 * (hin_t * wp * 4 + 4) + 2 * (size_t)C4 * (128 * 4 + 4) + 2 * (size_t)C4 * (L.cout * 4 + 4) +
+                                (size_t)L.kh * L.kw * L.cin + 2 * L.cin + 2 * L.cout) * 4;
+        if (smem_tc <= 200 * 1024) {
+          int cols = 32;
+          while (cols < L.cout) cols <<= 1;
+          auto ktc = dscnn_dsblock_tc_kernel;
+          static SmemOptIn optin_tc;
+          if (optin_tc.ensure(ktc, smem_tc) != cudaSuccess) return TCR_ERR_CUDA;
+          const int tiles = ((L.hout + RHt - 1) / RHt) * n;
+          TCR_LAUNCH("dscnn_dsblock_tc", ktc, dim3(std::min(tiles, d->sms)), dim3(256), smem_tc, s, L, RHt, cols, n, params, in, out, eps);
+          in = out;
+          cur ^= 1;
+          continue;
+        }
+      }
+#endif
       int RH = std::min(L.hout, 8);
       while (RH > 1 && smem_for(RH) > 100 * 1024) --RH;
       const size_t smem = smem_for(RH);

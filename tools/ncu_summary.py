@@ -53,7 +53,11 @@ def main():
         w.writerow(["kernel", "duration_us_under_ncu", "dram_read_bytes", "dram_write_bytes", "grid", "block", "regs", "warps_active_pct",
                     "issue_active_pct", "fma_pipe_active_pct", "warp_instructions", "top_stalls_per_issue"])
         w.writerows(table)
-    json.dump({"source": rep.split("/")[-1], "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import sources_sha          # hash of the kernel sources this capture describes; bench.py refuses a stale one
+    json.dump({"source": rep.split("/")[-1], "kernels_sha": sources_sha(),
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
                "bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}}, open(out + "_traffic.json", "w"), indent=1)
     print(f"{len(table)} launches -> {out}.csv")
 
