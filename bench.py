@@ -291,6 +291,7 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_dev = local
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = pin_to_gpu_numa_node(local)
@@ -348,6 +349,33 @@ def run_ours(a):
            "config": make_config(a, world, "none (1 GPU)" if world == 1 else getattr(eng, "exchange", "nccl")),
            "parallelism": f"dp{world}", "final_total_loss": final_loss, "numa": numa,
            "gpu_launches": int(launches), "clocks": clocks}
+
+    # ---- data-parallel self-check, outside the timed region (the driver's GPU-test box has one GPU and skips tests/test_dist.py):
+    # (1) replicas are still bit-identical after the timed steps; (2) on a 16-utterance shard per rank, the gradient the exchange
+    # hands to the update (averaged over ranks, fused into the update kernel over peer memory or all-reduced by NCCL) equals the mean
+    # of the ranks' LOCAL gradients, each computed by an unattached handle of the same library and gathered through torch.distributed.
+    if world > 1:
+        import torch.distributed as dist
+        digest = torch.stack([params.double().sum(), params.double().abs().sum(), moving.double().sum()])
+        gathered = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        m = 16
+        p_chk = params.clone()
+        local = Engine(model=a.model, width_multiplier=a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms, max_batch=m,
+                       dropout_keep_prob=0.5, device=local_dev)
+        sl, mv = torch.zeros_like(params), moving.clone()
+        seed = 12345 * world + rank                                  # the same dropout draws in both handles
+        g_local = local.train_step(wavs[0][:m], onehots[0][:m], p_chk, sl, mv, lr, mom, wd, dropout_seed=seed, want_grads=True, apply_update=False)["grads"]
+        g_avg = eng.train_step(wavs[0][:m], onehots[0][:m], p_chk, sl, mv, lr, mom, wd, dropout_seed=seed, want_grads=True, apply_update=False)["grads"]
+        parts = [torch.zeros_like(g_local) for _ in range(world)]
+        dist.all_gather(parts, g_local)
+        mean = torch.stack([q.double() for q in parts]).mean(0)
+        err = float((g_avg.double() - mean).abs().max() / mean.abs().max().clamp_min(1e-30))
+        out["dp_check"] = {"replicas_bit_identical": identical, "averaged_gradient_rel_err_vs_mean_of_local": err,
+                           "shard": f"{m} utterances per rank", "exchange": getattr(eng, "exchange", "nccl"), "ok": bool(identical and err < 1e-5)}
+        local.close()
+        barrier()
 
     # ---- per-kernel durations (separate pass: event brackets add overhead, so not the timed region).  Every rank runs
     # the steps (they contain the gradient all-reduce); rank 0 reports.

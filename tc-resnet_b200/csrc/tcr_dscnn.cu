@@ -214,43 +214,51 @@ __device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* s
 
 // Persistent: a CTA keeps the split filter bank, the TMEM allocation and the per-channel tables for all its tiles
 // (tile = RH output rows of one utterance), and the next tile's input rows travel (cp.async) while the current tile is computed.
-__global__ void __launch_bounds__(256, 1) dscnn_dsblock_tc_kernel(DsLayerDev L, int RH, int tmem_cols, int n_utt, const float* __restrict__ params,
+// Specialised for the 3x3 / stride-1 depthwise stage (every separable block of DS-CNN-S, audio_nets/ds_cnn.py:20-26):
+//   * depthwise: a thread owns (4 channels, one output column) and slides down the rows, so every input float4 is read once
+//     per thread (3 loads per output instead of 9) and the 9 taps stay in registers;
+//   * two TMEM accumulators: the MMAs of tile i run while the epilogue of tile i-1 drains the other one;
+//   * the UMMA descriptors are formed once; a k-step only adds its byte offset to the start-address field.
+constexpr int kTcThreads = 512;
+template <int C, int CO>
+__global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_tc_kernel(DsLayerDev L, int RH, int n_utt, const float* __restrict__ params,
                                                                   const float* __restrict__ in, float* __restrict__ out, float eps) {
   TCR_DYNAMIC_SMEM(smem_raw);
-  __shared__ uint64_t mma_bar;
+  __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_s;
   float* smem = reinterpret_cast<float*>(smem_raw);
-  const int C = L.cin, CO = L.cout, C4 = C >> 2;
+  constexpr int C4 = C / 4, KS = C / 8;
+  constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hin_t = (RH - 1) * L.sh + L.kh;
-  const int wp = (L.wout - 1) * L.sw + L.kw;
+  const int hin_t = RH + 2;                                       // 3x3, stride 1
+  const int wp = L.wout + 2;
   const int XP = hin_t * wp * 4 + 4;                              // floats per channel chunk of the input tile (+16 B against conflicts)
-  const int LBA = 128 * 4 + 4, LBB = CO * 4 + 4;                  // K-chunk strides of the A / B operand tiles (floats)
+  constexpr int LBA = 128 * 4 + 4, LBB = CO * 4 + 4;              // K-chunk strides of the A / B operand tiles (floats)
   float* xs0 = smem;                                              // [2][C4][XP]
   float* a_hi = xs0 + (size_t)2 * C4 * XP;                        // [C4][LBA]
   float* a_lo = a_hi + (size_t)C4 * LBA;
   float* b_hi = a_lo + (size_t)C4 * LBA;                          // [C4][LBB]
   float* b_lo = b_hi + (size_t)C4 * LBB;
-  float* dws = b_lo + (size_t)C4 * LBB;                           // [kh*kw][C]
-  float* sc1 = dws + L.kh * L.kw * C;
+  float* dws = b_lo + (size_t)C4 * LBB;                           // [9][C]
+  float* sc1 = dws + 9 * C;
   float* sf1 = sc1 + C;
   float* sc2 = sf1 + C;
   float* sf2 = sc2 + CO;
   const int tpu = (L.hout + RH - 1) / RH;                         // tiles per utterance
   const int ntiles = tpu * n_utt;
-  if (tid == 0) mbar_init(&mma_bar, 1);
-  if (warp == 0) {                                               // TMEM: 128 lanes x tmem_cols fp32 columns for the accumulator
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
+  if (tid == 0) { mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1); }
+  if (warp == 0) {                                               // TMEM: two accumulators of 128 lanes x CO fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // pointwise filters pw[ci][co] -> B operand [n = co][k = ci], hi / lo parts (params are caller-owned: independent of the producer)
-  for (int i0 = tid; i0 < C * CO; i0 += 256 * 8) {
+  for (int i0 = tid; i0 < C * CO; i0 += kTcThreads * 8) {
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = i0 + 256 * j < C * CO ? __ldg(params + L.pw + i0 + 256 * j) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = i0 + kTcThreads * j < C * CO ? __ldg(params + L.pw + i0 + kTcThreads * j) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int i = i0 + 256 * j;
+      const int i = i0 + kTcThreads * j;
       if (i < C * CO) {
         const int ci = i / CO, co = i - ci * CO;
         const float hi = __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
@@ -260,102 +268,365 @@ __global__ void __launch_bounds__(256, 1) dscnn_dsblock_tc_kernel(DsLayerDev L, 
       }
     }
   }
-  for (int i = tid; i < L.kh * L.kw * C / 4; i += 256) st4(dws + 4 * i, ldg4(params + L.w + 4 * i));
-  for (int c = tid; c < C; c += 256) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc1, sf1);
-  for (int c = tid; c < CO; c += 256) fold_bn(params, L.pb, L.pbeta, L.pmm, L.pmv, c, eps, sc2, sf2);
+  for (int i = tid; i < 9 * C / 4; i += kTcThreads) st4(dws + 4 * i, ldg4(params + L.w + 4 * i));
+  for (int c = tid; c < C; c += kTcThreads) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc1, sf1);
+  for (int c = tid; c < CO; c += kTcThreads) fold_bn(params, L.pb, L.pbeta, L.pmm, L.pmv, c, eps, sc2, sf2);
   pdl_wait();
-  // input rows (+halo) of a tile, channel-chunk-major, asynchronously
+  // input rows (+halo) of a tile, channel-chunk-major, asynchronously.  A thread copies the same (row, column) cells of every
+  // tile (cell = tid / C4 + j * (threads / C4)), so the walk is worked out once: cell -> (tile row, column validity, element offset).
+  constexpr int kCells = 8, kRowStep = kTcThreads / C4;
+  const int f_c4 = tid % C4, f_row0 = tid / C4, f_rows = hin_t * wp;
+  int f_pk[kCells];
+#pragma unroll
+  for (int j = 0; j < kCells; ++j) {
+    const int row = f_row0 + j * kRowStep;
+    const int r = row / wp, col = row - r * wp, x = col - 1;
+    const int okx = (row < f_rows && x >= 0 && x < L.win) ? 1 : 0;
+    f_pk[j] = ((r * L.win + x + 1) << 9) | (r << 1) | okx;         // position offset + 1 (>= 0), tile row, column-valid bit
+  }
   auto fetch_tile = [&](int tile, float* xs) {
     const int n = tile / tpu, h0 = (tile - n * tpu) * RH;
-    const RowWalk w = row_walk(tid, 256, C4);
-    const int rows = hin_t * wp;
-    if (w.row < rows) {
-      int r = w.row / wp, col = w.row - r * wp;
-      for (int row = w.row; row < rows; row += w.rstep) {
-        const int h = h0 * L.sh - L.pt + r, x = col - L.pl;
-        const bool ok = h >= 0 && h < L.hin && x >= 0 && x < L.win;
-        cp_async16_zfill(xs + (size_t)w.c4 * XP + 4 * row, ok ? in + (((size_t)n * L.hin + h) * L.win + x) * C + 4 * w.c4 : in, ok);
-        col += w.rstep;
-        while (col >= wp) { col -= wp; ++r; }
+    const float* base = in + (((int64_t)n * L.hin + (h0 - 1)) * L.win - 1) * C + 4 * f_c4;      // never dereferenced out of range
+    float* dst = xs + (size_t)f_c4 * XP + 4 * f_row0;
+#pragma unroll
+    for (int j = 0; j < kCells; ++j) {
+      if (f_row0 + j * kRowStep < f_rows) {
+        const int pk = f_pk[j], h = h0 - 1 + ((pk >> 1) & 0xFF);
+        const bool ok = (pk & 1) && h >= 0 && h < L.hin;
+        cp_async16_zfill(dst + 4 * j * kRowStep, ok ? base + (int64_t)(pk >> 9) * C : in, ok);
       }
     }
   };
-  int tile = blockIdx.x, cur = 0;
-  uint32_t parity = 0;
+  // epilogue of one tile: accumulator row m = 32 * (warp % 4) + lane, columns [(warp / 4) * CO / NG, + CO / NG), batches of 16
+  auto epilogue = [&](uint32_t tacc, int tile_e) {
+    const int n = tile_e / tpu, h0 = (tile_e - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
+    constexpr int NG = kTcThreads / 128;                           // column groups: every warp reads its TMEM lane quarter
+    const int m = 32 * (warp & 3) + lane, cbase = (warp >> 2) * (CO / NG);
+    const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
+#pragma unroll
+    for (int c0 = 0; c0 < CO / NG; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tacc + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cbase + c0);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                     "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < npos) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int co = cbase + c0 + j;
+          const float4 s = ld4(sc2 + co), t = ld4(sf2 + co);
+          st4(out + (gbase + m) * CO + co,
+              make_float4(fmaxf(fmaf(__uint_as_float(r[j]), s.x, t.x), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 1]), s.y, t.y), 0.f),
+                          fmaxf(fmaf(__uint_as_float(r[j + 2]), s.z, t.z), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 3]), s.w, t.w), 0.f)));
+        }
+      }
+    }
+  };
+  int tile = blockIdx.x, cur = 0, it = 0, prev_tile = -1;
+  uint32_t parity[2] = {0u, 0u};
   if (tile < ntiles) fetch_tile(tile, xs0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
   // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t da_hi = umma_desc(smem_u32(a_hi), LBA * 4u, 128u), da_lo = umma_desc(smem_u32(a_lo), LBA * 4u, 128u);
+  const uint64_t db_hi = umma_desc(smem_u32(b_hi), LBB * 4u, 128u), db_lo = umma_desc(smem_u32(b_lo), LBB * 4u, 128u);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1, ++it) {
     const int n = tile / tpu, h0 = (tile - n * tpu) * RH, rh = imin(RH, L.hout - h0);
+    (void)n;
     float* xs = xs0 + (size_t)cur * C4 * XP;
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                             // this tile's rows have landed; the previous epilogue is done
+    __syncthreads();                                             // this tile's rows have landed
     if (tile + (int)gridDim.x < ntiles) fetch_tile(tile + gridDim.x, xs0 + (size_t)(cur ^ 1) * C4 * XP);
-    // depthwise conv + folded BN + ReLU, written as the A operand (hi / lo); lanes walk positions, a warp keeps one channel chunk
-    const int npos = rh * L.wout;
-    for (int task = tid; task < 128 * C4; task += 256) {
-      const int m = task & 127, c4 = task >> 7;
-      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-      if (m < npos) {
-        const int oh = m / L.wout, ow = m - oh * L.wout;
-        const float* xb = xs + (size_t)c4 * XP + 4 * ((oh * L.sh) * wp + ow * L.sw);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = 0; i < L.kh; ++i)
-          for (int j = 0; j < L.kw; ++j) {
-            const float4 x = ld4(xb + 4 * (i * wp + j));
-            const float4 k = ld4(dws + (i * L.kw + j) * C + 4 * c4);
-            acc.x = fmaf(x.x, k.x, acc.x); acc.y = fmaf(x.y, k.y, acc.y); acc.z = fmaf(x.z, k.z, acc.z); acc.w = fmaf(x.w, k.w, acc.w);
-          }
-        const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
-        tf32_split(make_float4(fmaxf(fmaf(acc.x, s.x, t.x), 0.f), fmaxf(fmaf(acc.y, s.y, t.y), 0.f), fmaxf(fmaf(acc.z, s.z, t.z), 0.f),
-                               fmaxf(fmaf(acc.w, s.w, t.w), 0.f)), hi, lo);
-      }
-      st4(a_hi + (size_t)c4 * LBA + 4 * m, hi);                  // rows past npos are zero: their accumulator rows are never stored
-      st4(a_lo + (size_t)c4 * LBA + 4 * m, lo);
+    // the previous tile's MMAs read the A tiles: they must be done before the depthwise stage overwrites them
+    if (prev_tile >= 0) {
+      mbar_wait(&mma_bar[(it - 1) & 1], parity[(it - 1) & 1]);
+      parity[(it - 1) & 1] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    // depthwise 3x3 + folded BN + ReLU -> A operand (hi / lo): thread = (channel chunk, output column), sliding down the rows
+    // row segments keep every thread busy: (segment, channel chunk, column) tasks, a segment re-reads its two halo rows
+    const int ntask0 = C4 * L.wout;
+    const int nseg = imax(1, imin(rh, kTcThreads / ntask0)), srows = (rh + nseg - 1) / nseg;
+    for (int task = tid; task < ntask0 * nseg; task += kTcThreads) {
+      const int seg = task / ntask0, t0 = task - seg * ntask0;
+      const int c4 = t0 / L.wout, ow = t0 - c4 * L.wout;
+      const int rb = seg * srows, re = imin(rh, rb + srows);       // output rows [rb, re) of the tile
+      if (rb >= re) continue;
+      float4 k[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) k[j] = ld4(dws + j * C + 4 * c4);
+      const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
+      const float* xb = xs + (size_t)c4 * XP + 4 * ow;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;      // outputs r-2, r-1, r while input row r arrives
+      for (int r = rb; r < re + 2; ++r) {
+        const float4 x0 = ld4(xb + 4 * (r * wp)), x1 = ld4(xb + 4 * (r * wp + 1)), x2 = ld4(xb + 4 * (r * wp + 2));
+#define TCR_DW3(acc, kr)                                                                                                                   \
+  acc.x = fmaf(x0.x, k[3 * (kr)].x, fmaf(x1.x, k[3 * (kr) + 1].x, fmaf(x2.x, k[3 * (kr) + 2].x, acc.x)));                                  \
+  acc.y = fmaf(x0.y, k[3 * (kr)].y, fmaf(x1.y, k[3 * (kr) + 1].y, fmaf(x2.y, k[3 * (kr) + 2].y, acc.y)));                                  \
+  acc.z = fmaf(x0.z, k[3 * (kr)].z, fmaf(x1.z, k[3 * (kr) + 1].z, fmaf(x2.z, k[3 * (kr) + 2].z, acc.z)));                                  \
+  acc.w = fmaf(x0.w, k[3 * (kr)].w, fmaf(x1.w, k[3 * (kr) + 1].w, fmaf(x2.w, k[3 * (kr) + 2].w, acc.w)));
+        TCR_DW3(acc0, 2)              // input row r is the bottom tap row of output r-2, the middle of r-1, the top of r
+        TCR_DW3(acc1, 1)
+        TCR_DW3(acc2, 0)
+#undef TCR_DW3
+        if (r >= rb + 2) {
+          float4 hi, lo;
+          tf32_split(make_float4(fmaxf(fmaf(acc0.x, s.x, t.x), 0.f), fmaxf(fmaf(acc0.y, s.y, t.y), 0.f), fmaxf(fmaf(acc0.z, s.z, t.z), 0.f),
+                                 fmaxf(fmaf(acc0.w, s.w, t.w), 0.f)), hi, lo);
+          const int m = (r - 2) * L.wout + ow;
+          st4(a_hi + (size_t)c4 * LBA + 4 * m, hi);
+          st4(a_lo + (size_t)c4 * LBA + 4 * m, lo);
+        }
+        acc0 = acc1; acc1 = acc2; acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // accumulator rows past rh * wout are never stored, whatever the A rows there hold (each output row depends on its own A row only)
     fence_proxy_async();                                         // generic-proxy stores of the operands -> visible to the async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {
-      uint32_t accumulate = 0;
+      const uint32_t tacc = tmem + (uint32_t)((it & 1) * CO);
+#pragma unroll
       for (int pass = 0; pass < 3; ++pass) {                     // lo*hi, hi*lo, hi*hi: the small terms first
-        const float* ap = pass == 0 ? a_lo : a_hi;
-        const float* bp = pass == 1 ? b_lo : b_hi;
-        for (int ks = 0; ks < C / 8; ++ks) {                     // one MMA covers K = 8 = two 4-wide chunks
-          const uint64_t da = umma_desc(smem_u32(ap + (size_t)2 * ks * LBA), (uint32_t)LBA * 4u, 128u);
-          const uint64_t db = umma_desc(smem_u32(bp + (size_t)2 * ks * LBB), (uint32_t)LBB * 4u, 128u);
+        const uint64_t da0 = pass == 0 ? da_lo : da_hi, db0 = pass == 1 ? db_lo : db_hi;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {                        // one MMA covers K = 8 = two 4-wide chunks
+          const uint64_t da = da0 + (uint64_t)((2 * ks * LBA * 4) >> 4), db = db0 + (uint64_t)((2 * ks * LBB * 4) >> 4);
+          const uint32_t accumulate = (pass | ks) ? 1u : 0u;
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                       ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-          accumulate = 1;
+                       ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar[it & 1])) : "memory");
     }
-    mbar_wait(&mma_bar, parity);
-    parity ^= 1u;
+    // while these MMAs run: drain the previous tile's accumulator (its MMAs were waited for above)
+    if (prev_tile >= 0) epilogue(tmem + (uint32_t)(((it - 1) & 1) * CO), prev_tile);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    mbar_wait(&mma_bar[(it - 1) & 1], parity[(it - 1) & 1]);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: accumulator row m = 32 * (warp % 4) + lane, columns [(warp / 4) * CO / 2, + CO / 2) in batches of 16
+    epilogue(tmem + (uint32_t)(((it - 1) & 1) * CO), prev_tile);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+// Warp-specialised version of the block above (the default): the stages of a tile run on different warps and meet on mbarriers,
+// so the input fetch, the depthwise stage, the MMAs and the epilogue of neighbouring tiles overlap instead of taking turns.
+//   warps 0-9   depthwise producers: input tile -> A operand (hi / lo), double-buffered
+//   warp  10    one elected thread issues the 3 * C/8 tcgen05.mma of a tile and commits them to `mma_done`
+//   warps 12-15 cp.async fetch of the tile two ahead (as soon as the producers release its buffer) + epilogue (TMEM lane quarter
+//               = warp % 4, all CO columns)
+// Barriers (index = tile parity): in_full (the fetch warps' cp.async arrive-on), a_full (producers), mma_done (tcgen05.commit),
+// tmem_empty (epilogue warps).  A rows are packed to the tile's own row count (rounded to 8): the M = 128 MMA then reads a few
+// rows of the next K chunk as rows >= npos, whose accumulator rows are never stored.
+constexpr int kWsProducerWarps = 10, kWsProducers = 32 * kWsProducerWarps, kWsFetchers = 128;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {       // arrives when this thread's earlier cp.asyncs have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int C, int CO>
+__global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayerDev L, int RH, int n_utt, const float* __restrict__ params,
+                                                                         const float* __restrict__ in, float* __restrict__ out, float eps) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  __shared__ uint64_t in_full[2], a_full[2], mma_done[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  constexpr int C4 = C / 4, KS = C / 8;
+  constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hin_t = RH + 2, wp = L.wout + 2;
+  const int XP = hin_t * wp * 4 + 4;                              // floats per channel chunk of an input tile
+  const int LBA = ((RH * L.wout + 7) & ~7) * 4 + 4;               // K-chunk stride of the A tiles (floats): the tile's rows, +16 B
+  constexpr int LBB = CO * 4 + 4;
+  float* xs0 = smem;                                              // [2][C4][XP]
+  float* a0 = xs0 + (size_t)2 * C4 * XP;                          // [2][hi, lo][C4][LBA]
+  float* b_hi = a0 + (size_t)4 * C4 * LBA;                        // [C4][LBB]  (also absorbs the last A chunk's over-read)
+  float* b_lo = b_hi + (size_t)C4 * LBB;
+  float* dws = b_lo + (size_t)C4 * LBB;                           // [9][C]
+  float* sc1 = dws + 9 * C;
+  float* sf1 = sc1 + C;
+  float* sc2 = sf1 + C;
+  float* sf2 = sc2 + CO;
+  const int tpu = (L.hout + RH - 1) / RH;
+  const int ntiles = tpu * n_utt;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&in_full[b], kWsFetchers);
+      mbar_init(&a_full[b], kWsProducers);
+      mbar_init(&mma_done[b], 1);
+      mbar_init(&tmem_empty[b], kWsFetchers);
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i0 = tid; i0 < C * CO; i0 += kTcThreads * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = i0 + kTcThreads * j < C * CO ? __ldg(params + L.pw + i0 + kTcThreads * j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + kTcThreads * j;
+      if (i < C * CO) {
+        const int ci = i / CO, co = i - ci * CO;
+        const float hi = __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+        const int o = (ci >> 2) * LBB + co * 4 + (ci & 3);
+        b_hi[o] = hi;
+        b_lo[o] = v[j] - hi;
+      }
+    }
+  }
+  for (int i = tid; i < 9 * C / 4; i += kTcThreads) st4(dws + 4 * i, ldg4(params + L.w + 4 * i));
+  for (int c = tid; c < C; c += kTcThreads) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc1, sf1);
+  for (int c = tid; c < CO; c += kTcThreads) fold_bn(params, L.pb, L.pbeta, L.pmm, L.pmv, c, eps, sc2, sf2);
+  pdl_wait();
+  fence_proxy_async();                                           // the B operand was written through the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < kWsProducerWarps) {
+    // ---- depthwise 3x3 + folded BN + ReLU -> A operand: thread = (channel chunk, output column), sliding down the rows ----
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it & 1, k = it >> 1;
+      const int h0 = (tile % tpu) * RH, rh = imin(RH, L.hout - h0);
+      const float* xs = xs0 + (size_t)b * C4 * XP;
+      float* a_hi = a0 + (size_t)b * 2 * C4 * LBA;
+      float* a_lo = a_hi + (size_t)C4 * LBA;
+      mbar_wait(&in_full[b], (uint32_t)(k & 1));
+      if (it >= 2) mbar_wait(&mma_done[b], (uint32_t)((k - 1) & 1));             // the MMAs of tile it-2 have read this A buffer
+      for (int task = tid; task < C4 * L.wout; task += kWsProducers) {
+        const int c4 = task / L.wout, ow = task - c4 * L.wout;
+        float4 kk[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) kk[j] = ld4(dws + j * C + 4 * c4);
+        const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
+        const float* xb = xs + (size_t)c4 * XP + 4 * ow;
+        float* ah = a_hi + (size_t)c4 * LBA + 4 * ow;
+        float* al = a_lo + (size_t)c4 * LBA + 4 * ow;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;    // outputs r-2, r-1, r while input row r arrives
+        for (int r = 0; r < rh + 2; ++r) {
+          const float4 x0 = ld4(xb + 4 * (r * wp)), x1 = ld4(xb + 4 * (r * wp + 1)), x2 = ld4(xb + 4 * (r * wp + 2));
+#define TCR_DW3(acc, kr)                                                                                                                   \
+  acc.x = fmaf(x0.x, kk[3 * (kr)].x, fmaf(x1.x, kk[3 * (kr) + 1].x, fmaf(x2.x, kk[3 * (kr) + 2].x, acc.x)));                               \
+  acc.y = fmaf(x0.y, kk[3 * (kr)].y, fmaf(x1.y, kk[3 * (kr) + 1].y, fmaf(x2.y, kk[3 * (kr) + 2].y, acc.y)));                               \
+  acc.z = fmaf(x0.z, kk[3 * (kr)].z, fmaf(x1.z, kk[3 * (kr) + 1].z, fmaf(x2.z, kk[3 * (kr) + 2].z, acc.z)));                               \
+  acc.w = fmaf(x0.w, kk[3 * (kr)].w, fmaf(x1.w, kk[3 * (kr) + 1].w, fmaf(x2.w, kk[3 * (kr) + 2].w, acc.w)));
+          TCR_DW3(acc0, 2)            // input row r is the bottom tap row of output r-2, the middle of r-1, the top of r
+          TCR_DW3(acc1, 1)
+          TCR_DW3(acc2, 0)
+#undef TCR_DW3
+          if (r >= 2) {
+            float4 hi, lo;
+            tf32_split(make_float4(fmaxf(fmaf(acc0.x, s.x, t.x), 0.f), fmaxf(fmaf(acc0.y, s.y, t.y), 0.f),
+                                   fmaxf(fmaf(acc0.z, s.z, t.z), 0.f), fmaxf(fmaf(acc0.w, s.w, t.w), 0.f)), hi, lo);
+            st4(ah + 4 * (r - 2) * L.wout, hi);
+            st4(al + 4 * (r - 2) * L.wout, lo);
+          }
+          acc0 = acc1; acc1 = acc2; acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      fence_proxy_async();                                       // operand stores -> visible to the async proxy (UMMA)
+      mbar_arrive(&a_full[b]);
+    }
+  } else if (warp == kWsProducerWarps) {
+    // ---- MMA issue: one thread ----
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t db_hi = umma_desc(smem_u32(b_hi), LBB * 4u, 128u), db_lo = umma_desc(smem_u32(b_lo), LBB * 4u, 128u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it & 1, k = it >> 1;
+        const float* a_hi = a0 + (size_t)b * 2 * C4 * LBA;
+        const uint64_t da_hi = umma_desc(smem_u32(a_hi), (uint32_t)LBA * 4u, 128u);
+        const uint64_t da_lo = umma_desc(smem_u32(a_hi + (size_t)C4 * LBA), (uint32_t)LBA * 4u, 128u);
+        mbar_wait(&a_full[b], (uint32_t)(k & 1));
+        if (it >= 2) mbar_wait(&tmem_empty[b], (uint32_t)((k - 1) & 1));          // the epilogue of tile it-2 has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem + (uint32_t)(b * CO);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {                   // lo*hi, hi*lo, hi*hi: the small terms first
+          const uint64_t da0 = pass == 0 ? da_lo : da_hi, db0 = pass == 1 ? db_lo : db_hi;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t da = da0 + (uint64_t)((2 * ks * LBA * 4) >> 4), db = db0 + (uint64_t)((2 * ks * LBB * 4) >> 4);
+            const uint32_t accumulate = (pass | ks) ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[b])) : "memory");
+      }
+    }
+  } else if (warp >= kTcThreads / 32 - 4) {
+    // ---- fetch + epilogue: 4 warps ----
+    const int ft = tid - (kTcThreads - kWsFetchers);              // 0 .. 127
+    const int f_c4 = ft % C4, f_row0 = ft / C4, f_rows = hin_t * wp;
+    constexpr int kRowStep = kWsFetchers / C4;
+    auto fetch_tile = [&](int tile, float* xs) {
+      const int n = tile / tpu, h0 = (tile - n * tpu) * RH;
+      const float* base = in + (((int64_t)n * L.hin + (h0 - 1)) * L.win - 1) * C + 4 * f_c4;     // (tile row 0, column 0); never read out of range
+      float* dst = xs + (size_t)f_c4 * XP;
+      int r = f_row0 / wp, col = f_row0 - r * wp;
+      for (int row = f_row0; row < f_rows; row += kRowStep) {
+        const int h = h0 - 1 + r, x = col - 1;
+        const bool ok = h >= 0 && h < L.hin && x >= 0 && x < L.win;
+        cp_async16_zfill(dst + 4 * row, ok ? base + (int64_t)(r * L.win + col) * C : in, ok);
+        col += kRowStep;
+        while (col >= wp) { col -= wp; ++r; }
+      }
+    };
+    const int q = warp & 3;                                       // TMEM lane quarter this warp may read
+    const int m = 32 * q + lane;
+    int it = 0;
     {
-      const int m = 32 * (warp & 3) + lane, cbase = (warp >> 2) * (CO >> 1);
+      int t0 = blockIdx.x;
+      if (t0 < ntiles) { fetch_tile(t0, xs0); cp_async_mbar_arrive(&in_full[0]); }
+      t0 += gridDim.x;
+      if (t0 < ntiles) { fetch_tile(t0, xs0 + (size_t)C4 * XP); cp_async_mbar_arrive(&in_full[1]); }
+    }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it & 1, k = it >> 1;
+      const int nxt = tile + 2 * (int)gridDim.x;
+      if (nxt < ntiles) {                                         // the producers are done with this input buffer once A is full
+        mbar_wait(&a_full[b], (uint32_t)(k & 1));
+        fetch_tile(nxt, xs0 + (size_t)b * C4 * XP);
+        cp_async_mbar_arrive(&in_full[b]);
+      }
+      mbar_wait(&mma_done[b], (uint32_t)(k & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int n = tile / tpu, h0 = (tile - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
       const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
-      for (int c0 = 0; c0 < (CO >> 1); c0 += 16) {
+      const uint32_t tacc = tmem + (uint32_t)(b * CO) + ((uint32_t)(32 * q) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < CO; c0 += 16) {
         uint32_t r[16];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cbase + c0);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                     : "r"(taddr));
+                     : "r"(tacc + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < npos) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const int co = cbase + c0 + j;
+            const int co = c0 + j;
             const float4 s = ld4(sc2 + co), t = ld4(sf2 + co);
             st4(out + (gbase + m) * CO + co,
                 make_float4(fmaxf(fmaf(__uint_as_float(r[j]), s.x, t.x), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 1]), s.y, t.y), 0.f),
@@ -363,11 +634,183 @@ __global__ void __launch_bounds__(256, 1) dscnn_dsblock_tc_kernel(DsLayerDev L, 
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty[b]);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the TMEM reads are ordered before the next tile's MMAs (sync at loop top)
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+// First layer (kh x kw conv from the single-channel feature map, audio_nets/ds_cnn.py:21 `conv_1`) as an implicit GEMM on
+// tcgen05: A[m][k] = x[oh*sh + k / kw, ow*sw + k % kw] is gathered from the staged input rows straight into the canonical
+// operand layout (hi / lo), B = the filter bank [co][k], K = kh * kw (40), same persistent / double-TMEM structure as above.
+template <int CO>
+__global__ void __launch_bounds__(kTcThreads, 1) dscnn_conv_tc_kernel(DsLayerDev L, int RH, int n_utt, const float* __restrict__ params,
+                                                                      const float* __restrict__ in, float* __restrict__ out, float eps) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  __shared__ uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = L.kh * L.kw, K4 = K >> 2, KS = K >> 3;
+  const int hin_t = (RH - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw;
+  const int XT = (hin_t * wp + 3) & ~3;
+  constexpr int LBA = 128 * 4 + 4, LBB = CO * 4 + 4;
+  float* xs0 = smem;                                              // [2][hin_t][wp]
+  float* a_hi = xs0 + 2 * XT;                                     // [K4][LBA]
+  float* a_lo = a_hi + (size_t)K4 * LBA;
+  float* b_hi = a_lo + (size_t)K4 * LBA;                          // [K4][LBB]
+  float* b_lo = b_hi + (size_t)K4 * LBB;
+  float* sc = b_lo + (size_t)K4 * LBB;
+  float* sf = sc + CO;
+  const int tpu = (L.hout + RH - 1) / RH;
+  const int ntiles = tpu * n_utt;
+  if (tid == 0) { mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < K * CO; i += kTcThreads) {                // filters w[k][co] -> B operand [n = co][k]
+    const int k = i / CO, co = i - k * CO;
+    const float x = __ldg(params + L.w + i);
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const int o = (k >> 2) * LBB + co * 4 + (k & 3);
+    b_hi[o] = hi;
+    b_lo[o] = x - hi;
+  }
+  for (int c = tid; c < CO; c += kTcThreads) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc, sf);
+  pdl_wait();
+  // The cells a thread copies and the (position, tap chunk) operands it gathers are the same for every tile: worked out once.
+  constexpr int kCells = 4, kTasks = 4;                           // host side: hin_t * wp <= 4 * threads, 128 * K4 <= 4 * threads
+  int f_pk[kCells];
+#pragma unroll
+  for (int j = 0; j < kCells; ++j) {
+    const int i = tid + j * kTcThreads, r = i / wp, col = i - r * wp, x = col - L.pl;
+    f_pk[j] = ((r * L.win + x + L.pl) << 10) | (r << 1) | ((i < hin_t * wp && x >= 0 && x < L.win) ? 1 : 0);
+  }
+  auto fetch_tile = [&](int tile, float* xs) {
+    const int n = tile / tpu, h0 = (tile - n * tpu) * RH, hb = h0 * L.sh - L.pt;
+    const float* base = in + ((int64_t)n * L.hin + hb) * L.win - L.pl;
+#pragma unroll
+    for (int j = 0; j < kCells; ++j) {
+      if (tid + j * kTcThreads < hin_t * wp) {
+        const int pk = f_pk[j], h = hb + ((pk >> 1) & 0x1FF);
+        const bool ok = (pk & 1) && h >= 0 && h < L.hin;
+        const uint32_t bytes = ok ? 4u : 0u;
+        const float* src = ok ? base + (pk >> 10) : in;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(xs + tid + j * kTcThreads)), "l"(src), "r"(bytes) : "memory");
+      }
+    }
+  };
+  int g_x01[kTasks], g_x23[kTasks], g_a[kTasks];                  // tile offsets of the four taps of a chunk (16 bits each), A offset | row
+#pragma unroll
+  for (int j = 0; j < kTasks; ++j) {
+    const int task = tid + j * kTcThreads, m = task & 127, kc = task >> 7;
+    const int oh = m / L.wout, ow = m - oh * L.wout;
+    int e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 4 * kc + q, ki = k / L.kw, kj = k - ki * L.kw;
+      e[q] = (oh * L.sh + ki) * wp + ow * L.sw + kj;
+    }
+    g_x01[j] = e[0] | (e[1] << 16);
+    g_x23[j] = e[2] | (e[3] << 16);
+    g_a[j] = ((kc * LBA + 4 * m) << 7) | m;
+  }
+  auto epilogue = [&](uint32_t tacc, int tile_e) {
+    const int n = tile_e / tpu, h0 = (tile_e - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
+    constexpr int NG = kTcThreads / 128;
+    const int m = 32 * (warp & 3) + lane, cbase = (warp >> 2) * (CO / NG);
+    const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
+#pragma unroll
+    for (int c0 = 0; c0 < CO / NG; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tacc + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cbase + c0);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                     "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < npos) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int co = cbase + c0 + j;
+          const float4 s = ld4(sc + co), t = ld4(sf + co);
+          st4(out + (gbase + m) * CO + co,
+              make_float4(fmaxf(fmaf(__uint_as_float(r[j]), s.x, t.x), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 1]), s.y, t.y), 0.f),
+                          fmaxf(fmaf(__uint_as_float(r[j + 2]), s.z, t.z), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 3]), s.w, t.w), 0.f)));
+        }
+      }
+    }
+  };
+  int tile = blockIdx.x, cur = 0, it = 0, prev_tile = -1;
+  uint32_t parity[2] = {0u, 0u};
+  if (tile < ntiles) fetch_tile(tile, xs0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t da_hi = umma_desc(smem_u32(a_hi), LBA * 4u, 128u), da_lo = umma_desc(smem_u32(a_lo), LBA * 4u, 128u);
+  const uint64_t db_hi = umma_desc(smem_u32(b_hi), LBB * 4u, 128u), db_lo = umma_desc(smem_u32(b_lo), LBB * 4u, 128u);
+  for (; tile < ntiles; tile += gridDim.x, cur ^= 1, ++it) {
+    const int n = tile / tpu, h0 = (tile - n * tpu) * RH, rh = imin(RH, L.hout - h0);
+    (void)n;
+    const float* xs = xs0 + cur * XT;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) fetch_tile(tile + gridDim.x, xs0 + (cur ^ 1) * XT);
+    if (prev_tile >= 0) {
+      mbar_wait(&mma_bar[(it - 1) & 1], parity[(it - 1) & 1]);
+      parity[(it - 1) & 1] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // im2col gather: task = (position, 4-wide chunk of taps)
+    const int npos = rh * L.wout;
+#pragma unroll
+    for (int j = 0; j < kTasks; ++j) {
+      if (tid + j * kTcThreads < 128 * K4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((g_a[j] & 127) < npos) v = make_float4(xs[g_x01[j] & 0xFFFF], xs[g_x01[j] >> 16], xs[g_x23[j] & 0xFFFF], xs[g_x23[j] >> 16]);
+        float4 hi, lo;
+        tf32_split(v, hi, lo);
+        st4(a_hi + (g_a[j] >> 7), hi);
+        st4(a_lo + (g_a[j] >> 7), lo);
+      }
+    }
+    fence_proxy_async();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      const uint32_t tacc = tmem + (uint32_t)((it & 1) * CO);
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t da0 = pass == 0 ? da_lo : da_hi, db0 = pass == 1 ? db_lo : db_hi;
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint64_t da = da0 + (uint64_t)((2 * ks * LBA * 4) >> 4), db = db0 + (uint64_t)((2 * ks * LBB * 4) >> 4);
+          const uint32_t accumulate = (pass | ks) ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar[it & 1])) : "memory");
+    }
+    if (prev_tile >= 0) epilogue(tmem + (uint32_t)(((it - 1) & 1) * CO), prev_tile);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    mbar_wait(&mma_bar[(it - 1) & 1], parity[(it - 1) & 1]);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue(tmem + (uint32_t)(((it - 1) & 1) * CO), prev_tile);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
 #endif
 
@@ -376,15 +819,34 @@ __global__ void __launch_bounds__(256) dscnn_head_kernel(int npos, int C, int cl
                                                          const float* __restrict__ params, const float* __restrict__ in,
                                                          float* __restrict__ logits, float* __restrict__ probs) {
   pdl_wait();
-  __shared__ float s_red[256];
+  __shared__ __align__(16) float s_red[1024];
   __shared__ float s_pool[320];
   __shared__ float s_logit[kMaxClasses];
   const int n = blockIdx.x, tid = threadIdx.x;
-  const int nseg = imax(1, (int)blockDim.x / C), seg = tid / C, c = tid - seg * C;
-  float s = 0.f;
-  if (seg < nseg)
-    for (int p = seg; p < npos; p += nseg) s += in[((size_t)n * npos + p) * C + c];
-  if (seg < nseg) s_red[seg * C + c] = s;
+  int nseg;
+  if ((C & 3) == 0) {                                             // float4 loads: thread = (segment of positions, 4 channels)
+    const int C4 = C >> 2;
+    nseg = imax(1, imin((int)blockDim.x / C4, 1024 / C));
+    const int seg = tid / C4, c4 = tid - seg * C4;
+    if (seg < nseg) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = in + (size_t)n * npos * C + 4 * c4;
+#pragma unroll 4
+      for (int p = seg; p < npos; p += nseg) {
+        const float4 v = ldg4(src + (size_t)p * C);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      st4(s_red + seg * C + 4 * c4, s);
+    }
+  } else {
+    nseg = imax(1, imin((int)blockDim.x / C, 1024 / C));
+    const int seg = tid / C, c = tid - seg * C;
+    if (seg < nseg) {
+      float s = 0.f;
+      for (int p = seg; p < npos; p += nseg) s += in[((size_t)n * npos + p) * C + c];
+      s_red[seg * C + c] = s;
+    }
+  }
   __syncthreads();
   if (tid < C) {
     float tot = 0.f;
@@ -424,6 +886,7 @@ struct tcr_dscnn {
   size_t act_floats = 0;
   int sms = 148;
   bool use_tc = true;        // pointwise convs on tcgen05 where they fit (env TCR_DSCNN_TC=0: register-tiled FMA everywhere)
+  bool tc_ws = true;         // warp-specialised tcgen05 block kernel (env TCR_DSCNN_TC=1: the lock-step version)
 };
 
 static void ds_same(int len, int k, int s, int* out, int* lead) {
@@ -442,7 +905,7 @@ extern "C" int tcr_dscnn_create(const tcr_dscnn_config* cfg, tcr_dscnn** out) {
   }
   tcr_dscnn* d = new tcr_dscnn();
   d->cfg = *cfg;
-  if (const char* e = getenv("TCR_DSCNN_TC")) d->use_tc = e[0] != '0';
+  if (const char* e = getenv("TCR_DSCNN_TC")) { d->use_tc = e[0] != '0'; d->tc_ws = e[0] != '1'; }
   struct Def { int type, depth, kh, kw, sh, sw; const char* scope; };
   std::vector<Def> defs;
   if (cfg->size == 'S') {
@@ -555,6 +1018,25 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
     const DsLayerDev& L = d->net.layer[l];
     float* out = d->act[cur];
     if (L.type == 0) {
+#ifndef TCR_EMU
+      int RHt = std::min(L.hout, 128 / std::max(1, std::min(L.wout, 128)));
+      RHt = std::max(1, RHt);
+      RHt = (L.hout + ((L.hout + RHt - 1) / RHt) - 1) / ((L.hout + RHt - 1) / RHt);
+      const int K4 = L.kh * L.kw / 4, hin_t = (RHt - 1) * L.sh + L.kh, wpt = (L.wout - 1) * L.sw + L.kw;
+      // implicit GEMM on tcgen05 (3xTF32); the limits are the kernel's precomputed per-thread walks (4 cells, 4 gather tasks)
+      if (d->use_tc && L.cin == 1 && L.cout == 64 && (L.kh * L.kw) % 8 == 0 && L.wout <= 64 && hin_t * wpt <= 4 * kTcThreads &&
+          128 * K4 <= 4 * kTcThreads && hin_t < 512) {
+        const size_t smem_tc = (2 * (size_t)((hin_t * wpt + 3) & ~3) + 2 * (size_t)K4 * (128 * 4 + 4) + 2 * (size_t)K4 * (L.cout * 4 + 4) + 2 * L.cout) * 4;
+        auto ktc = dscnn_conv_tc_kernel<64>;
+        static SmemOptIn optin_tc;
+        if (optin_tc.ensure(ktc, smem_tc) != cudaSuccess) return TCR_ERR_CUDA;
+        const int tiles = ((L.hout + RHt - 1) / RHt) * n;
+        TCR_LAUNCH("dscnn_conv_tc", ktc, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_tc, s, L, RHt, n, params, in, out, eps);
+        in = out;
+        cur ^= 1;
+        continue;
+      }
+#endif
       const int hp = (L.hout - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw;
       const size_t smem = (size_t)(((hp * wp + 3) & ~3) + L.kh * L.kw * L.cout + 2 * L.cout) * 4;
       auto kfn = dscnn_conv_kernel;
@@ -570,22 +1052,33 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
                         2 * L.cin + 2 * L.cout) * 4;
       };
 #ifndef TCR_EMU
-      // pointwise conv on the tensor cores (tcgen05, 3xTF32) when the operand tiles fit: channel counts multiples of 8 / 32, <= 128
-      if (d->use_tc && L.cin % 8 == 0 && L.cout % 32 == 0 && L.cout <= 128 && L.wout <= 128) {
+      // pointwise conv on the tensor cores (tcgen05, 3xTF32): the 64 -> 64 channel blocks with a 3x3 / stride-1 depthwise stage
+      if (d->use_tc && L.cin == 64 && L.cout == 64 && L.kh == 3 && L.kw == 3 && L.sh == 1 && L.sw == 1 && L.wout <= 64) {
         int RHt = std::min(L.hout, 128 / L.wout);
-        // balanced chunks of rows: 25 rows at <= 6 per tile -> 5 tiles of 5
-        RHt = (L.hout + ((L.hout + RHt - 1) / RHt) - 1) / ((L.hout + RHt - 1) / RHt);
-        const int hin_t = (RHt - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw, C4 = L.cin / 4;
-        const size_t smem_tc = (2 * (size_t)C4 * (hin_t * wp * 4 + 4) + 2 * (size_t)C4 * (128 * 4 + 4) + 2 * (size_t)C4 * (L.cout * 4 + 4) +
-                                (size_t)L.kh * L.kw * L.cin + 2 * L.cin + 2 * L.cout) * 4;
-        if (smem_tc <= 200 * 1024) {
-          int cols = 32;
-          while (cols < L.cout) cols <<= 1;
-          auto ktc = dscnn_dsblock_tc_kernel;
+        RHt = (L.hout + ((L.hout + RHt - 1) / RHt) - 1) / ((L.hout + RHt - 1) / RHt);     // balanced: 25 rows -> 5 tiles of 5
+        const int C4 = L.cin / 4;
+        const bool walk_ok = (RHt + 2) * (L.wout + 2) <= 8 * (kTcThreads / C4);      // the kernel's precomputed fetch walk: 8 cells
+        const size_t smem_tc = (2 * (size_t)C4 * ((RHt + 2) * (L.wout + 2) * 4 + 4) + 2 * (size_t)C4 * (128 * 4 + 4) + 2 * (size_t)C4 * (L.cout * 4 + 4) +
+                                (size_t)9 * L.cin + 2 * L.cin + 2 * L.cout) * 4;
+        const int lba = ((RHt * L.wout + 7) & ~7) * 4 + 4;
+        const size_t smem_ws = (2 * (size_t)C4 * ((RHt + 2) * (L.wout + 2) * 4 + 4) + 4 * (size_t)C4 * lba + 2 * (size_t)C4 * (L.cout * 4 + 4) +
+                                (size_t)9 * L.cin + 2 * L.cin + 2 * L.cout) * 4;
+        if (d->tc_ws && smem_ws <= 227 * 1024) {
+          auto kws = dscnn_dsblock_ws_kernel<64, 64>;
+          static SmemOptIn optin_ws;
+          if (optin_ws.ensure(kws, smem_ws) != cudaSuccess) return TCR_ERR_CUDA;
+          const int tiles = ((L.hout + RHt - 1) / RHt) * n;
+          TCR_LAUNCH("dscnn_dsblock_ws", kws, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_ws, s, L, RHt, n, params, in, out, eps);
+          in = out;
+          cur ^= 1;
+          continue;
+        }
+        if (smem_tc <= 200 * 1024 && walk_ok) {
+          auto ktc = dscnn_dsblock_tc_kernel<64, 64>;
           static SmemOptIn optin_tc;
           if (optin_tc.ensure(ktc, smem_tc) != cudaSuccess) return TCR_ERR_CUDA;
           const int tiles = ((L.hout + RHt - 1) / RHt) * n;
-          TCR_LAUNCH("dscnn_dsblock_tc", ktc, dim3(std::min(tiles, d->sms)), dim3(256), smem_tc, s, L, RHt, cols, n, params, in, out, eps);
+          TCR_LAUNCH("dscnn_dsblock_tc", ktc, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_tc, s, L, RHt, n, params, in, out, eps);
           in = out;
           cur ^= 1;
           continue;

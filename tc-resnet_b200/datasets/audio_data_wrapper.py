@@ -108,14 +108,37 @@ class SingleLabelAudioDataWrapper(AudioDataWrapper):
         assert a.num_classes == self.num_labels, f"--num_classes {a.num_classes} != {self.num_labels} label directories"
         self.data = (self.filenames, self.labels)
 
+    def _synthetic_wavs(self, idx):
+        """Seeded U(-1,1) clips; clip i is always the same samples (a pool of up to 4096 distinct clips, generated once)."""
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            rng = np.random.default_rng(1234)
+            pool = self._pool = rng.uniform(-1.0, 1.0, (min(self._num_samples, 4096), self.desired_samples)).astype(np.float32)
+        return pool[np.asarray(idx) % pool.shape[0]]
+
+    def next_batch_pinned(self):
+        """Training fast path for `synthetic:` data: pre-built batches in PINNED host memory (built once, cycled), so that a
+        session.run(train_op) is one tcr_train_step_host call with no per-step host work; None for datasets read from disk
+        (their decode / augment pipeline is the reference's tf.data stage, outside the hot path).  Advances the same cursor."""
+        if not self.synthetic or not self.is_training:
+            return None
+        import torch
+        idx = self._take_indices()
+        key = int(self._cursor // max(self.batch_size * self.world, 1)) % 8
+        cache = self.__dict__.setdefault("_pinned", {})
+        if key not in cache:
+            labels = np.zeros((len(idx), self.num_labels), np.float32)
+            labels[np.arange(len(idx)), [self.labels[i] for i in idx]] = 1.0
+            cache[key] = (torch.from_numpy(self._synthetic_wavs(idx)).pin_memory(), torch.from_numpy(labels).pin_memory())
+        return cache[key]
+
     def next_batch(self):
         idx = self._take_indices()
         n = len(idx)
         labels = np.zeros((n, self.num_labels), np.float32)
         labels[np.arange(n), [self.labels[i] for i in idx]] = 1.0
         if self.synthetic:
-            wavs = np.stack([np.random.RandomState(1234 + int(i)).uniform(-1, 1, self.desired_samples) for i in idx])
-            return wavs.astype(np.float32)[..., None], labels
+            return self._synthetic_wavs(idx)[..., None], labels
         a = self.args
         wavs = np.stack([self.augment(self.filenames[i], self.desired_samples, self.aug_rng, self.background_data,
                                       self.is_training, a.background_frequency, a.background_max_volume) for i in idx])

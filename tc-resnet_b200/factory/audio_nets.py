@@ -39,6 +39,9 @@ class AudioNetModel(TFModel):
         self.var_names_to_values = None                            # in-memory weight injection hook (trainer.py:145-154)
         self.endpoints_loss: Dict[str, Node] = {}
         self._last: Dict[str, np.ndarray] = {}
+        self._feed, self._feed_last = None, (0, np.float32("nan"), np.float32("nan"))
+        self._feed_steps = []                                       # global step numbers of the submitted, not yet reported steps
+        self._feed_slots = []
         self._counts = None                                        # device int64 [classes^2 + 2] (tcr_eval_accumulate)
 
     # ------------------------------------------------------------------ graph-construction API of the reference
@@ -80,23 +83,41 @@ class AudioNetModel(TFModel):
                              window_size_ms=a.window_size_ms, window_stride_ms=a.window_stride_ms,
                              num_mel_bins=a.num_mel_bins, num_mfccs=a.num_mfccs, lower_edge_hertz=a.lower_edge_hertz,
                              upper_edge_hertz=a.upper_edge_hertz, preprocess_method=a.preprocess_method,
-                             max_batch=a.batch_size, dropout_keep_prob=a.dropout_keep_prob,
+                             max_batch=max(int(getattr(a, 'batch_size', 1) or 1), int(getattr(a, 'input_batch_size', 1) or 1)),
+                             dropout_keep_prob=a.dropout_keep_prob,
                              label_smoothing=getattr(a, "label_smoothing", 0.0))
         self.params, self.slots, self.moving = self.engine.new_variables(seed=getattr(a, "seed", 0) or 0)
         if getattr(a, "data_parallel", False):
             self.engine.attach_process_group()
-        n = a.batch_size
+        n = int(getattr(a, 'batch_size', 1) or 1)
         dev = self.engine.device
         self._h_wav = torch.empty(n, self.engine.cfg.clip_samples, dtype=torch.float32).pin_memory()
         self._h_hot = torch.empty(n, a.num_classes, dtype=torch.float32).pin_memory()
         self._d_wav, self._d_hot = self._h_wav.to(dev), self._h_hot.to(dev)
+        self._feed_slots = [(torch.empty_like(self._h_wav).pin_memory(), torch.empty_like(self._h_hot).pin_memory()) for _ in range(4)]
         return Node("logits", [None, a.num_classes]), {"ranges": Node("ranges")}
 
     def build_loss(self, logits, scores, labels):
         return Node("total_loss", []), Node("model_loss", []), {}
 
     def build_deployable_model(self, include_preprocess=True):
-        raise NotImplementedError("TFLite freezing (freeze.py) is outside the accelerated path")
+        """The deploy graph of the reference (factory/audio_nets.py:87-125: placeholder [input_batch_size, samples, 1] ->
+        preprocessing -> network in inference mode -> softmax) as a callable on the CUDA engine: returns
+        ([input node], DeployedModel).  include_preprocess=False takes features [1, height, width, 1] like the profiling graph.
+        The front-end is the TRAINING front-end (tf.contrib.signal path, datasets/preprocessors.py:64-96): the reference's deploy
+        front-end (audio_ops.mfcc, :98-158) is a different approximation of the same features and is not reproduced; TFLite
+        conversion itself (freeze.py) stays out of scope."""
+        a = self.args
+        n = int(getattr(a, "input_batch_size", 1) or 1)
+        if self.engine is None or int(self.engine.cfg.max_batch) < n:
+            self.build_inference(None, is_training=False)
+        samples = int(a.sample_rate * a.clip_duration_ms / 1000)
+        if include_preprocess:
+            node = Node("input/audio/before_preprocessing", [n, samples, 1])
+        else:
+            assert a.height > 0 and a.width > 0 and a.channels > 0
+            node = Node("input", [1, a.height, a.width, a.channels])
+        return [node], DeployedModel(self, n, include_preprocess)
 
     # ------------------------------------------------------------------ attribute surface
     @property
@@ -121,6 +142,7 @@ class AudioNetModel(TFModel):
 
     # ------------------------------------------------------------------ variables by TF name
     def get_variables(self, with_slots=True) -> Dict[str, np.ndarray]:
+        self.flush_feed()
         out = self.engine.variables_to_dict(self.params, self.moving)
         if with_slots:
             for k, v in self.engine.variables_to_dict(self.slots).items():
@@ -128,6 +150,7 @@ class AudioNetModel(TFModel):
         return out
 
     def set_variables(self, values: Dict[str, np.ndarray], strict=True):
+        self.flush_feed()
         self.engine.variables_from_dict(values, self.params, self.moving, strict=strict)
         slots = {k[:-len("/Momentum")]: v for k, v in values.items() if k.endswith("/Momentum")}
         if slots:
@@ -149,10 +172,59 @@ class AudioNetModel(TFModel):
         return out
 
     # ------------------------------------------------------------------ one session.run
+    def _execute_train_fast(self, names: Set[str]) -> Optional[Dict[str, object]]:
+        """session.run(train_op) through the host-buffer step of the C ABI (tcr_train_step_host via engine.HostFeed): the batch goes
+        H2D on the library's copy stream, the step is queued behind it and the call returns without waiting for it.  The losses
+        handed back are those of the step `feed_lag` calls earlier (`loss_global_step` says which), exactly the overlap the
+        reference gets from tf.data prefetching + an asynchronous session (helper/trainer.py:312-321).  Used when nothing but
+        the train op, losses, step and learning rate is fetched; metric / output fetches take the synchronous path below."""
+        if names - {"train_op", "global_step", "total_loss", "model_loss", "learning_rate"}:
+            return None
+        lag = int(getattr(self.args, "feed_lag", 2))
+        if lag <= 0:
+            return None
+        pinned = self.dataset.next_batch_pinned() if hasattr(self.dataset, "next_batch_pinned") else None
+        if pinned is None:
+            wav_np, hot_np = self.dataset.next_batch()
+            n = wav_np.shape[0]
+            if n != self.args.batch_size:
+                raise InvalidArgumentError(f"bad batch: {wav_np.shape}")
+            slot = self._feed_slots[self.global_step % len(self._feed_slots)]       # reused only after lag + 1 later calls
+            slot[0].copy_(torch.from_numpy(wav_np.reshape(n, -1)))
+            slot[1].copy_(torch.from_numpy(hot_np))
+            pinned = slot
+        if self._feed is None:
+            from ..engine import HostFeed
+            self._feed = HostFeed(self.engine, lag=lag)
+        lr = float(self.lr_schedule(self.global_step))
+        r = self._feed.submit(pinned[0], pinned[1], self.params, self.slots, self.moving, lr, self.optimizer.get("momentum") or 0.0,
+                              self.args.weight_decay, dropout_seed=self._dropout_seed())
+        self.global_step += 1
+        self._feed_steps.append(self.global_step)
+        if r is not None:
+            self._feed_last = (self._feed_steps.pop(0), np.float32(r[1]), np.float32(r[2]))
+            if not np.isfinite(r[1]):
+                raise InvalidArgumentError(f"non-finite loss at step {self._feed_last[0]} (malformed input batch?)")
+        step, total, model = self._feed_last
+        return {"train_op": None, "learning_rate": np.float32(lr), "global_step": np.int64(self.global_step), "total_loss": total,
+                "model_loss": model, "loss_global_step": np.int64(step)}
+
+    def flush_feed(self):
+        """Drain the host-feed pipeline (before anything reads the variables: checkpoints, evaluation, get_variables)."""
+        if self._feed is not None:
+            for r in self._feed.flush():
+                self._feed_last = (self._feed_steps.pop(0), np.float32(r[1]), np.float32(r[2]))
+
     def execute(self, names: Set[str], feed) -> Dict[str, object]:
+        if "train_op" in names:
+            fast = self._execute_train_fast(names)
+            if fast is not None:
+                self._last = fast
+                return fast
+        self.flush_feed()
         wav_np, hot_np = self.dataset.next_batch()
         n = wav_np.shape[0]
-        if n != self.args.batch_size or not np.isfinite(wav_np).all():
+        if n != self.args.batch_size:
             raise InvalidArgumentError(f"bad batch: {wav_np.shape}")
         self._h_wav.copy_(torch.from_numpy(wav_np.reshape(n, -1)))
         self._h_hot.copy_(torch.from_numpy(hot_np))
@@ -192,12 +264,51 @@ class AudioNetModel(TFModel):
     @staticmethod
     def add_arguments(parser):
         parser.add_argument("--label_smoothing", default=0.0, type=float)
+        parser.add_argument("--feed_lag", default=2, type=int,
+                            help="steps a training session.run may run ahead of the losses it reports (host-buffer step of the C ABI; "
+                                 "0: synchronous steps, the loss returned is this step's)")
 
 
 def _tc_flags(parser):
     parser.add_argument("--weight_decay", default=0.0001, type=float)
     parser.add_argument("--dropout_keep_prob", default=0.5, type=float)
     parser.add_argument("--width_multiplier", default=1.0, type=float)
+
+
+class DeployedModel:
+    """Batch-n (default 1) inference entry: wav [n, samples(,1)] or features [n, T, F(,1)] in, softmax outputs [n, classes] out.
+    After the first call the launch sequence (front-end + every layer) is replayed from a CUDA graph: at batch 1 the forward is
+    launch-latency bound, and a graph replay is one submission instead of ~11 launches."""
+
+    def __init__(self, model: "AudioNetModel", batch: int, include_preprocess: bool, use_graph: bool = True):
+        self.model, self.batch, self.include_preprocess, self.use_graph = model, int(batch), include_preprocess, use_graph
+        eng = model.engine
+        shape = (self.batch, eng.cfg.clip_samples) if include_preprocess else (self.batch, eng.frames, eng.features)
+        self._in = torch.zeros(shape, dtype=torch.float32, device=eng.device)
+        self._graph, self._out, self._calls = None, None, 0
+
+    def _run(self):
+        m = self.model
+        return m.engine.forward(self._in, m.params, m.moving, is_training=False, input_is_features=not self.include_preprocess)
+
+    def __call__(self, x) -> np.ndarray:
+        x = torch.as_tensor(np.asarray(x, np.float32)).reshape(self._in.shape)
+        self._in.copy_(x, non_blocking=True)
+        if not self.use_graph or self._calls < 2:                  # two eager calls first: lazy per-kernel attributes are set outside capture
+            self._out = self._run()
+        else:
+            if self._graph is None:
+                stream = torch.cuda.Stream(device=self._in.device)
+                stream.wait_stream(torch.cuda.current_stream(self._in.device))
+                with torch.cuda.stream(stream):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        self._out = self._run()
+                torch.cuda.current_stream(self._in.device).wait_stream(stream)
+                self._graph = g
+            self._graph.replay()
+        self._calls += 1
+        return self._out["probs"].cpu().numpy()
 
 
 class TCResNet8Model(AudioNetModel):

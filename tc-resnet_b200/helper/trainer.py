@@ -125,10 +125,13 @@ class TrainerBase:
         global_step = int(vals["global_step"])
         step_from_restore = global_step - self.global_step_from_checkpoint
         epoch_from_restore = self.build_epoch(step_from_restore)
+        lstep = int(getattr(self.model, "_last", {}).get("loss_global_step", global_step))   # host-feed pipeline: losses lag the submission
         if self.is_chief and (step_from_restore % max(1, self.args.step_save_summaries) == 0
                               or step_from_restore <= self.args.step_save_first_n_summaries):
             self.log.info(f"[{self.dataset_name}] GlobalStep {global_step:8d} / StepFromRestore {step_from_restore:8d} / "
-                          f"EpochFromRestore {epoch_from_restore:3.3f} | TotalLoss {vals['total_loss']:.5f} / "
+                          f"EpochFromRestore {epoch_from_restore:3.3f} | "
+                          + (f"(losses of step {int(lstep)}) " if lstep != global_step else "")
+                          + f"TotalLoss {vals['total_loss']:.5f} / "
                           f"ModelLoss {vals['model_loss']:.5f} | SingleStep(ms) {vals['single_step']:.3f} / "
                           f"SingleStepPerInstance(ms) {vals['single_step_per_instance']:.5f}")
         return vals, global_step, step_from_restore, epoch_from_restore

@@ -128,3 +128,71 @@ def test_train_then_evaluate_through_the_reference_cli(tmp_path):
     results = evaluate_audio.main(eval_args)
     assert len(results) == 1 and 0.0 <= results[0]["accuracy"] <= 1.0 and np.isfinite(results[0]["total_loss"])
     assert (tmp_path / "valid" / "accuracy").is_dir()              # best-checkpoint directory the test recipe reads
+
+
+@pytest.mark.gpu
+def test_trainer_loop_runs_at_the_host_feed_rate(tmp_path):
+    """train_audio.train on `synthetic:` data goes through the C ABI's host-buffer step (tcr_train_step_host): its per-step wall
+    time must stay within 1.3x of the same steps driven directly through engine.HostFeed (what bench.py's e2e measures)."""
+    import time
+    import torch
+    from tcresnet_b200.engine import HostFeed
+    common = ("--dataset_path synthetic:4096 --output_name output/softmax --num_classes 12 --preprocess_method mfcc --num_mfccs 40 "
+              "--clip_duration_ms 1000 --window_size_ms 40 --window_stride_ms 20 ")
+    steps = 260
+    args = train_audio.parse_arguments(shlex.split(
+        common + f"--dataset_split_name train --train_dir {tmp_path} --augmentation_method anchored_slice_or_pad_with_shift "
+        f"--batch_size 512 --boundaries 100000 --max_step_from_restore {steps} --lr_list 0.1 0.01 --absolute_schedule --no-boundaries_epoch "
+        "--step_save_checkpoint 100000 --step_evaluation 100000 --step_save_summaries 100000 --step_save_first_n_summaries 0 "
+        "--optimizer mom --momentum 0.9 TCResNet8Model --weight_decay 0.001 --width_multiplier 1.0"))
+    trainer = train_audio.train(args)                                        # warm-up run (also exercises the final flush + checkpoint)
+    model = trainer.model
+    assert model.global_step == steps and np.isfinite(model._feed_last[1])
+    fetch = {"step_op": trainer.train_op, "global_step": trainer.global_step, "total_loss": model.total_loss, "model_loss": model.model_loss}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        trainer.session.run(fetch)
+    model.flush_feed()
+    torch.cuda.synchronize()
+    trainer_ms = (time.perf_counter() - t0) / 200 * 1e3
+    eng, feed = model.engine, HostFeed(model.engine, lag=2)
+    batches = [model.dataset.next_batch_pinned() for _ in range(8)]
+    for i in range(20):
+        feed.submit(batches[i % 8][0], batches[i % 8][1], model.params, model.slots, model.moving, 0.1, 0.9, 1e-3, dropout_seed=i)
+    feed.flush()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(200):
+        feed.submit(batches[i % 8][0], batches[i % 8][1], model.params, model.slots, model.moving, 0.1, 0.9, 1e-3, dropout_seed=i)
+    feed.flush()
+    torch.cuda.synchronize()
+    direct_ms = (time.perf_counter() - t0) / 200 * 1e3
+    print(f"trainer loop {trainer_ms:.3f} ms/step, HostFeed directly {direct_ms:.3f} ms/step")
+    assert trainer_ms <= 1.3 * direct_ms + 0.05
+
+
+@pytest.mark.gpu
+def test_deployable_model_batch1_inference(tmp_path):
+    """build_deployable_model(include_preprocess=True / False): wav -> softmax for one clip, equal to the evaluation forward of the
+    engine, eagerly and when the launch sequence is replayed from a CUDA graph (third call onwards)."""
+    import argparse
+    args = argparse.Namespace(width_multiplier=1.0, num_classes=12, sample_rate=16000, clip_duration_ms=1000, window_size_ms=40.0,
+                              window_stride_ms=20.0, num_mel_bins=64, num_mfccs=40, lower_edge_hertz=80.0, upper_edge_hertz=7600.0,
+                              preprocess_method="mfcc", batch_size=1, input_batch_size=1, dropout_keep_prob=0.5, output_name="output/softmax",
+                              weight_decay=1e-3, height=-1, width=-1, channels=-1)
+    model = audio_nets.TCResNet8Model(args, None)
+    inputs, deployed = model.build_deployable_model(include_preprocess=True)
+    assert inputs[0].shape == [1, 16000, 1]
+    rng = np.random.default_rng(0)
+    clips = rng.uniform(-1, 1, (5, 16000)).astype(np.float32)
+    import torch
+    ref = model.engine.forward(torch.from_numpy(clips).cuda(), model.params, model.moving)["probs"].cpu().numpy()
+    got = np.concatenate([deployed(c) for c in clips])                     # calls 3-5 replay the captured graph
+    assert deployed._graph is not None
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+    assert np.array_equal(got.argmax(1), ref.argmax(1))
+    args.height, args.width, args.channels = 49, 40, 1
+    _, deployed_f = model.build_deployable_model(include_preprocess=False)
+    feat = model.engine.mfcc(torch.from_numpy(clips[:1]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(deployed_f(feat), ref[:1], rtol=0, atol=1e-6)
