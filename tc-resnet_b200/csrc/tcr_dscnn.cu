@@ -8,6 +8,9 @@
 //   dscnn_head_kernel      global average pool + fully connected (+bias) + softmax
 // BatchNorm here has no gamma (slim default scale=False) and uses the moving statistics; bias + BN fold into one
 // per-channel (scale, shift) pair computed while staging.
+#ifndef TCR_EMU
+#include <cuda.h>   // CUtensorMap (types only: the encoder is looked up through the runtime)
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -423,11 +426,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_tc_kernel(DsLayer
 
 // Warp-specialised version of the block above (the default): the stages of a tile run on different warps and meet on mbarriers,
 // so the input fetch, the depthwise stage, the MMAs and the epilogue of neighbouring tiles overlap instead of taking turns.
-//   warps 0-9   depthwise producers: input tile -> A operand (hi / lo), double-buffered
+//   warps 0-9   producers: TMA fetch of the tile two ahead (cp.async.bulk.tensor into the input buffer they have just left) and
+//               the depthwise stage, input tile -> A operand (hi / lo); both double-buffered
 //   warp  10    one elected thread issues the 3 * C/8 tcgen05.mma of a tile and commits them to `mma_done`
-//   warps 12-15 cp.async fetch of the tile two ahead (as soon as the producers release its buffer) + epilogue (TMEM lane quarter
-//               = warp % 4, all CO columns)
-// Barriers (index = tile parity): in_full (the fetch warps' cp.async arrive-on), a_full (producers), mma_done (tcgen05.commit),
+//   warps 12-15 epilogue (TMEM lane quarter = warp % 4, all CO columns)
+// Barriers (index = tile parity): in_full (TMA complete_tx), a_full (producers), mma_done (tcgen05.commit),
 // tmem_empty (epilogue warps).  A rows are packed to the tile's own row count (rounded to 8): the M = 128 MMA then reads a few
 // rows of the next K chunk as rows >= npos, whose accumulator rows are never stored.
 constexpr int kWsProducerWarps = 10, kWsProducers = 32 * kWsProducerWarps, kWsFetchers = 128;
@@ -438,8 +441,8 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {       // a
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 template <int C, int CO>
-__global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayerDev L, int RH, int n_utt, const float* __restrict__ params,
-                                                                         const float* __restrict__ in, float* __restrict__ out, float eps) {
+__global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(const __grid_constant__ CUtensorMap in_map, DsLayerDev L, int RH, int n_utt,
+                                                                         const float* __restrict__ params, float* __restrict__ out, float eps) {
   TCR_DYNAMIC_SMEM(smem_raw);
   __shared__ uint64_t in_full[2], a_full[2], mma_done[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -448,11 +451,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayer
   constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hin_t = RH + 2, wp = L.wout + 2;
-  const int XP = hin_t * wp * 4 + 4;                              // floats per channel chunk of an input tile
+  constexpr int CH = C / 2, CH4 = CH / 4;                         // channels per TMA box: 32 fp32 = one 128-byte swizzle row
+  static_assert(CH * 4 == 128, "the input halves are 128-byte rows (SWIZZLE_128B)");
+  const int XH = ((hin_t * wp * CH * 4 + 1023) & ~1023) / 4;      // floats per half tile, a multiple of the 1024-byte swizzle atom
   const int LBA = ((RH * L.wout + 7) & ~7) * 4 + 4;               // K-chunk stride of the A tiles (floats): the tile's rows, +16 B
   constexpr int LBB = CO * 4 + 4;
-  float* xs0 = smem;                                              // [2][C4][XP]
-  float* a0 = xs0 + (size_t)2 * C4 * XP;                          // [2][hi, lo][C4][LBA]
+  float* xs0 = smem;                                              // [2 buffers][2 channel halves][XH], TMA destination (1024-aligned)
+  float* a0 = xs0 + (size_t)4 * XH;                               // [2][hi, lo][C4][LBA]
   float* b_hi = a0 + (size_t)4 * C4 * LBA;                        // [C4][LBB]  (also absorbs the last A chunk's over-read)
   float* b_lo = b_hi + (size_t)C4 * LBB;
   float* dws = b_lo + (size_t)C4 * LBB;                           // [9][C]
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayer
   const int ntiles = tpu * n_utt;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&in_full[b], kWsFetchers);
+      mbar_init(&in_full[b], 1);
       mbar_init(&a_full[b], kWsProducers);
       mbar_init(&mma_done[b], 1);
       mbar_init(&tmem_empty[b], kWsFetchers);
@@ -501,28 +506,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayer
   const uint32_t tmem = tmem_base_s;
 
   if (warp < kWsProducerWarps) {
-    // ---- depthwise 3x3 + folded BN + ReLU -> A operand: thread = (channel chunk, output column), sliding down the rows ----
+    // ---- input fetch (TMA) + depthwise 3x3 + folded BN + ReLU -> A operand ----
+    // One thread issues two 4-D tensor loads per tile (channel halves; box = 32 channels x (wout + 2) columns x (RH + 2) rows,
+    // start (., -1, h0 - 1, n): the halo outside the feature map arrives as zeros) and the bytes land on `in_full`.  The box rows
+    // are 128 bytes, SWIZZLE_128B: the 16-byte chunk j of position p sits at chunk j ^ (p & 7), so the 8 lanes of a quarter warp,
+    // which read the same channel chunk of 8 consecutive positions, hit 8 different bank groups.
+    const uint32_t tile_bytes = (uint32_t)(2 * hin_t * wp * CH * 4);
+    auto fetch_tile = [&](int tile, float* xs, uint64_t* bar) {
+      const int n = tile / tpu, h0 = (tile - n * tpu) * RH;
+      mbar_expect_tx(bar, tile_bytes);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(smem_u32(xs + (size_t)half * XH)), "l"(&in_map), "r"(half * CH), "r"(-1), "r"(h0 - 1), "r"(n), "r"(smem_u32(bar))
+                     : "memory");
+    };
+    if (tid == 0) {
+      int t0 = blockIdx.x;
+      if (t0 < ntiles) fetch_tile(t0, xs0, &in_full[0]);
+      t0 += gridDim.x;
+      if (t0 < ntiles) fetch_tile(t0, xs0 + (size_t)2 * XH, &in_full[1]);
+    }
+    // thread = (channel chunk, output column), the same for every tile (host side: C4 * wout <= producers): its nine taps and
+    // the folded BatchNorm stay in registers
+    const bool active = tid < C4 * L.wout;
+    const int c4 = active ? tid / L.wout : 0, ow = active ? tid - c4 * L.wout : 0;
+    const int half = c4 / CH4, cl = c4 - half * CH4;
+    float4 kk[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) kk[j] = ld4(dws + j * C + 4 * c4);
+    const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = it & 1, k = it >> 1;
       const int h0 = (tile % tpu) * RH, rh = imin(RH, L.hout - h0);
-      const float* xs = xs0 + (size_t)b * C4 * XP;
+      float* xs = xs0 + (size_t)b * 2 * XH;
       float* a_hi = a0 + (size_t)b * 2 * C4 * LBA;
       float* a_lo = a_hi + (size_t)C4 * LBA;
       mbar_wait(&in_full[b], (uint32_t)(k & 1));
       if (it >= 2) mbar_wait(&mma_done[b], (uint32_t)((k - 1) & 1));             // the MMAs of tile it-2 have read this A buffer
-      for (int task = tid; task < C4 * L.wout; task += kWsProducers) {
-        const int c4 = task / L.wout, ow = task - c4 * L.wout;
-        float4 kk[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) kk[j] = ld4(dws + j * C + 4 * c4);
-        const float4 s = ld4(sc1 + 4 * c4), t = ld4(sf1 + 4 * c4);
-        const float* xb = xs + (size_t)c4 * XP + 4 * ow;
+      if (active) {
+        const float* xh = xs + (size_t)half * XH;
         float* ah = a_hi + (size_t)c4 * LBA + 4 * ow;
         float* al = a_lo + (size_t)c4 * LBA + 4 * ow;
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;    // outputs r-2, r-1, r while input row r arrives
-        for (int r = 0; r < rh + 2; ++r) {
-          const float4 x0 = ld4(xb + 4 * (r * wp)), x1 = ld4(xb + 4 * (r * wp + 1)), x2 = ld4(xb + 4 * (r * wp + 2));
+        int p = ow;                                               // position (tile row r, column ow) of the padded tile
+        for (int r = 0; r < rh + 2; ++r, p += wp) {
+          const float4 x0 = ld4(xh + p * CH + (((cl ^ p) & 7) << 2)), x1 = ld4(xh + (p + 1) * CH + (((cl ^ (p + 1)) & 7) << 2)),
+                       x2 = ld4(xh + (p + 2) * CH + (((cl ^ (p + 2)) & 7) << 2));
 #define TCR_DW3(acc, kr)                                                                                                                   \
   acc.x = fmaf(x0.x, kk[3 * (kr)].x, fmaf(x1.x, kk[3 * (kr) + 1].x, fmaf(x2.x, kk[3 * (kr) + 2].x, acc.x)));                               \
   acc.y = fmaf(x0.y, kk[3 * (kr)].y, fmaf(x1.y, kk[3 * (kr) + 1].y, fmaf(x2.y, kk[3 * (kr) + 2].y, acc.y)));                               \
@@ -544,6 +575,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayer
       }
       fence_proxy_async();                                       // operand stores -> visible to the async proxy (UMMA)
       mbar_arrive(&a_full[b]);
+      const int nxt = tile + 2 * (int)gridDim.x;                  // refill this input buffer once every producer has left it
+      if (nxt < ntiles) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kWsProducers) : "memory");
+        if (tid == 0) fetch_tile(nxt, xs, &in_full[b]);
+      }
     }
   } else if (warp == kWsProducerWarps) {
     // ---- MMA issue: one thread ----
@@ -576,40 +612,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(DsLayer
       }
     }
   } else if (warp >= kTcThreads / 32 - 4) {
-    // ---- fetch + epilogue: 4 warps ----
-    const int ft = tid - (kTcThreads - kWsFetchers);              // 0 .. 127
-    const int f_c4 = ft % C4, f_row0 = ft / C4, f_rows = hin_t * wp;
-    constexpr int kRowStep = kWsFetchers / C4;
-    auto fetch_tile = [&](int tile, float* xs) {
-      const int n = tile / tpu, h0 = (tile - n * tpu) * RH;
-      const float* base = in + (((int64_t)n * L.hin + (h0 - 1)) * L.win - 1) * C + 4 * f_c4;     // (tile row 0, column 0); never read out of range
-      float* dst = xs + (size_t)f_c4 * XP;
-      int r = f_row0 / wp, col = f_row0 - r * wp;
-      for (int row = f_row0; row < f_rows; row += kRowStep) {
-        const int h = h0 - 1 + r, x = col - 1;
-        const bool ok = h >= 0 && h < L.hin && x >= 0 && x < L.win;
-        cp_async16_zfill(dst + 4 * row, ok ? base + (int64_t)(r * L.win + col) * C : in, ok);
-        col += kRowStep;
-        while (col >= wp) { col -= wp; ++r; }
-      }
-    };
+    // ---- epilogue: 4 warps ----
     const int q = warp & 3;                                       // TMEM lane quarter this warp may read
     const int m = 32 * q + lane;
     int it = 0;
-    {
-      int t0 = blockIdx.x;
-      if (t0 < ntiles) { fetch_tile(t0, xs0); cp_async_mbar_arrive(&in_full[0]); }
-      t0 += gridDim.x;
-      if (t0 < ntiles) { fetch_tile(t0, xs0 + (size_t)C4 * XP); cp_async_mbar_arrive(&in_full[1]); }
-    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = it & 1, k = it >> 1;
-      const int nxt = tile + 2 * (int)gridDim.x;
-      if (nxt < ntiles) {                                         // the producers are done with this input buffer once A is full
-        mbar_wait(&a_full[b], (uint32_t)(k & 1));
-        fetch_tile(nxt, xs0 + (size_t)b * C4 * XP);
-        cp_async_mbar_arrive(&in_full[b]);
-      }
       mbar_wait(&mma_done[b], (uint32_t)(k & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int n = tile / tpu, h0 = (tile - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
@@ -887,7 +895,39 @@ struct tcr_dscnn {
   int sms = 148;
   bool use_tc = true;        // pointwise convs on tcgen05 where they fit (env TCR_DSCNN_TC=0: register-tiled FMA everywhere)
   bool tc_ws = true;         // warp-specialised tcgen05 block kernel (env TCR_DSCNN_TC=1: the lock-step version)
+#ifndef TCR_EMU
+  struct InMap { CUtensorMap map; const void* ptr = nullptr; int rh = 0; };
+  std::vector<InMap> in_maps;   // per layer: TMA descriptor of the block's input activations (re-encoded if the buffer changes)
+#endif
 };
+
+#ifndef TCR_EMU
+// 4-D tensor map over the NHWC activations [n][h][w][c] (innermost first: c, w, h, n), box = 32 channels x wp columns x hin_t rows,
+// 128-byte swizzle; out-of-range coordinates (the SAME-padding halo) are filled with zeros.  The driver entry point is looked up at
+// run time (no link against libcuda).
+static int ds_encode_in_map(CUtensorMap* map, const float* base, int c, int w, int h, int n, int box_w, int box_h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available");
+      return TCR_ERR_CUDA;
+    }
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t gstride[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed"); return TCR_ERR_CUDA; }
+  return TCR_OK;
+}
+#endif
 
 static void ds_same(int len, int k, int s, int* out, int* lead) {
   *out = (len + s - 1) / s;
@@ -1061,14 +1101,22 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
         const size_t smem_tc = (2 * (size_t)C4 * ((RHt + 2) * (L.wout + 2) * 4 + 4) + 2 * (size_t)C4 * (128 * 4 + 4) + 2 * (size_t)C4 * (L.cout * 4 + 4) +
                                 (size_t)9 * L.cin + 2 * L.cin + 2 * L.cout) * 4;
         const int lba = ((RHt * L.wout + 7) & ~7) * 4 + 4;
-        const size_t smem_ws = (2 * (size_t)C4 * ((RHt + 2) * (L.wout + 2) * 4 + 4) + 4 * (size_t)C4 * lba + 2 * (size_t)C4 * (L.cout * 4 + 4) +
-                                (size_t)9 * L.cin + 2 * L.cin + 2 * L.cout) * 4;
-        if (d->tc_ws && smem_ws <= 227 * 1024) {
+        const size_t xh = (((size_t)(RHt + 2) * (L.wout + 2) * 128 + 1023) & ~(size_t)1023) / 4;       // floats per half input tile
+        const size_t smem_ws = (4 * xh + 4 * (size_t)C4 * lba + 2 * (size_t)C4 * (L.cout * 4 + 4) + (size_t)9 * L.cin + 2 * L.cin + 2 * L.cout) * 4;
+        if (d->tc_ws && smem_ws <= 226 * 1024 && C4 * L.wout <= kWsProducers && L.wout + 2 <= 256 && RHt + 2 <= 256 && in != features) {
           auto kws = dscnn_dsblock_ws_kernel<64, 64>;
           static SmemOptIn optin_ws;
           if (optin_ws.ensure(kws, smem_ws) != cudaSuccess) return TCR_ERR_CUDA;
+          if ((int)d->in_maps.size() < d->net.nlayers) d->in_maps.resize(d->net.nlayers);
+          tcr_dscnn::InMap& im = d->in_maps[l];
+          if (im.ptr != in || im.rh != RHt) {                    // the activations ping-pong between two buffers: encoded once per layer
+            const int rc = ds_encode_in_map(&im.map, in, L.cin, L.win, L.hin, d->cfg.max_batch, L.wout + 2, RHt + 2);
+            if (rc != TCR_OK) return rc;
+            im.ptr = in;
+            im.rh = RHt;
+          }
           const int tiles = ((L.hout + RHt - 1) / RHt) * n;
-          TCR_LAUNCH("dscnn_dsblock_ws", kws, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_ws, s, L, RHt, n, params, in, out, eps);
+          TCR_LAUNCH("dscnn_dsblock_ws", kws, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_ws, s, im.map, L, RHt, n, params, out, eps);
           in = out;
           cur ^= 1;
           continue;
