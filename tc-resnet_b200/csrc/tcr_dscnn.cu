@@ -440,6 +440,82 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {       // arrives when this thread's earlier cp.asyncs have landed
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The MMA and epilogue roles of the warp-specialised kernels (shared by the separable block and the first conv).
+// MMA role, one thread: per tile 3 * K4/2 tcgen05.mma (M = 128, N = CO, K = 8) on A buffer it % 2 -> TMEM accumulator it % 2.
+template <int CO>
+__device__ __forceinline__ void ws_mma_role(int ntiles, int K4, int LBA, const float* a0, const float* b_hi, const float* b_lo, uint32_t tmem,
+                                            uint64_t* a_full, uint64_t* tmem_empty, uint64_t* mma_done) {
+  constexpr int LBB = CO * 4 + 4;
+  // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t db_hi = umma_desc(smem_u32(b_hi), LBB * 4u, 128u), db_lo = umma_desc(smem_u32(b_lo), LBB * 4u, 128u);
+  const int KS = K4 >> 1;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = it & 1, k = it >> 1;
+    const float* a_hi = a0 + (size_t)b * 2 * K4 * LBA;
+    const uint64_t da_hi = umma_desc(smem_u32(a_hi), (uint32_t)LBA * 4u, 128u);
+    const uint64_t da_lo = umma_desc(smem_u32(a_hi + (size_t)K4 * LBA), (uint32_t)LBA * 4u, 128u);
+    mbar_wait(&a_full[b], (uint32_t)(k & 1));
+    if (it >= 2) mbar_wait(&tmem_empty[b], (uint32_t)((k - 1) & 1));              // the epilogue of tile it-2 has drained this accumulator
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = tmem + (uint32_t)(b * CO);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {                       // lo*hi, hi*lo, hi*hi: the small terms first
+      const uint64_t da0 = pass == 0 ? da_lo : da_hi, db0 = pass == 1 ? db_lo : db_hi;
+#pragma unroll 4
+      for (int ks = 0; ks < KS; ++ks) {                          // one MMA covers K = 8 = two 4-wide chunks
+        const uint64_t da = da0 + (uint64_t)((2 * ks * LBA * 4) >> 4), db = db0 + (uint64_t)((2 * ks * LBB * 4) >> 4);
+        const uint32_t accumulate = (pass | ks) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[b])) : "memory");
+  }
+}
+// Epilogue role, 4 warps: warp quarter q reads TMEM lanes [32 q, 32 q + 32) = accumulator rows, all CO columns in batches of 16,
+// applies the folded BatchNorm + ReLU and stores the NHWC row; then hands the accumulator back (tmem_empty).
+template <int CO>
+__device__ __forceinline__ void ws_epilogue_role(const DsLayerDev& L, int RH, int tpu, int ntiles, uint32_t tmem, const float* sc, const float* sf,
+                                                 float* __restrict__ out, uint64_t* mma_done, uint64_t* tmem_empty, int q, int lane) {
+  const int m = 32 * q + lane;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = it & 1, k = it >> 1;
+    mbar_wait(&mma_done[b], (uint32_t)(k & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int n = tile / tpu, h0 = (tile - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
+    const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
+    const uint32_t tacc = tmem + (uint32_t)(b * CO) + ((uint32_t)(32 * q) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += 16) {
+      uint32_t r[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                     "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(tacc + (uint32_t)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < npos) {                                             // a lane owns a whole NHWC row: 32-byte stores (one full sector each)
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          const int co = c0 + j;
+          const float4 s0 = ld4(sc + co), t0 = ld4(sf + co), s1 = ld4(sc + co + 4), t1 = ld4(sf + co + 4);
+          asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + (gbase + m) * CO + co),
+                       "f"(fmaxf(fmaf(__uint_as_float(r[j]), s0.x, t0.x), 0.f)), "f"(fmaxf(fmaf(__uint_as_float(r[j + 1]), s0.y, t0.y), 0.f)),
+                       "f"(fmaxf(fmaf(__uint_as_float(r[j + 2]), s0.z, t0.z), 0.f)), "f"(fmaxf(fmaf(__uint_as_float(r[j + 3]), s0.w, t0.w), 0.f)),
+                       "f"(fmaxf(fmaf(__uint_as_float(r[j + 4]), s1.x, t1.x), 0.f)), "f"(fmaxf(fmaf(__uint_as_float(r[j + 5]), s1.y, t1.y), 0.f)),
+                       "f"(fmaxf(fmaf(__uint_as_float(r[j + 6]), s1.z, t1.z), 0.f)), "f"(fmaxf(fmaf(__uint_as_float(r[j + 7]), s1.w, t1.w), 0.f))
+                       : "memory");
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&tmem_empty[b]);
+  }
+}
+
 template <int C, int CO>
 __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(const __grid_constant__ CUtensorMap in_map, DsLayerDev L, int RH, int n_utt,
                                                                          const float* __restrict__ params, float* __restrict__ out, float eps) {
@@ -583,68 +659,145 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_ws_kernel(const _
     }
   } else if (warp == kWsProducerWarps) {
     // ---- MMA issue: one thread ----
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t db_hi = umma_desc(smem_u32(b_hi), LBB * 4u, 128u), db_lo = umma_desc(smem_u32(b_lo), LBB * 4u, 128u);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int b = it & 1, k = it >> 1;
-        const float* a_hi = a0 + (size_t)b * 2 * C4 * LBA;
-        const uint64_t da_hi = umma_desc(smem_u32(a_hi), (uint32_t)LBA * 4u, 128u);
-        const uint64_t da_lo = umma_desc(smem_u32(a_hi + (size_t)C4 * LBA), (uint32_t)LBA * 4u, 128u);
-        mbar_wait(&a_full[b], (uint32_t)(k & 1));
-        if (it >= 2) mbar_wait(&tmem_empty[b], (uint32_t)((k - 1) & 1));          // the epilogue of tile it-2 has drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem + (uint32_t)(b * CO);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {                   // lo*hi, hi*lo, hi*hi: the small terms first
-          const uint64_t da0 = pass == 0 ? da_lo : da_hi, db0 = pass == 1 ? db_lo : db_hi;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t da = da0 + (uint64_t)((2 * ks * LBA * 4) >> 4), db = db0 + (uint64_t)((2 * ks * LBB * 4) >> 4);
-            const uint32_t accumulate = (pass | ks) ? 1u : 0u;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                         ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[b])) : "memory");
-      }
-    }
+    if (lane == 0) ws_mma_role<CO>(ntiles, C4, LBA, a0, b_hi, b_lo, tmem, a_full, tmem_empty, mma_done);
   } else if (warp >= kTcThreads / 32 - 4) {
     // ---- epilogue: 4 warps ----
-    const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-    const int m = 32 * q + lane;
+    ws_epilogue_role<CO>(L, RH, tpu, ntiles, tmem, sc2, sf2, out, mma_done, tmem_empty, warp & 3, lane);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+// First conv, warp-specialised (same roles and barriers as the block kernel): the producers copy the tile's input rows
+// (cp.async, 4-byte cells, zero-filled halo), gather the im2col operand A[m][k] = x[oh*sh + k / kw][ow*sw + k % kw] (hi / lo) into
+// the A buffer of the tile, and refill the input buffer for the tile two ahead; K = kh * kw (40).
+template <int CO>
+__global__ void __launch_bounds__(kTcThreads, 1) dscnn_conv_ws_kernel(DsLayerDev L, int RH, int n_utt, const float* __restrict__ params,
+                                                                      const float* __restrict__ in, float* __restrict__ out, float eps) {
+  TCR_DYNAMIC_SMEM(smem_raw);
+  __shared__ uint64_t in_full[2], a_full[2], mma_done[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = L.kh * L.kw, K4 = K >> 2;
+  const int hin_t = (RH - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw;
+  const int XT = (hin_t * wp + 3) & ~3;
+  constexpr int LBA = 128 * 4 + 4, LBB = CO * 4 + 4;
+  float* a0 = smem;                                               // [2][hi, lo][K4][LBA]
+  float* b_hi = a0 + (size_t)4 * K4 * LBA;                        // [K4][LBB]
+  float* b_lo = b_hi + (size_t)K4 * LBB;
+  float* sc = b_lo + (size_t)K4 * LBB;
+  float* sf = sc + CO;
+  float* xs0 = sf + CO;                                           // [2][hin_t][wp]
+  const int tpu = (L.hout + RH - 1) / RH;
+  const int ntiles = tpu * n_utt;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&in_full[b], kWsProducers);
+      mbar_init(&a_full[b], kWsProducers);
+      mbar_init(&mma_done[b], 1);
+      mbar_init(&tmem_empty[b], kWsFetchers);
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < K * CO; i += kTcThreads) {                // filters w[k][co] -> B operand [n = co][k]
+    const int k = i / CO, co = i - k * CO;
+    const float x = __ldg(params + L.w + i);
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const int o = (k >> 2) * LBB + co * 4 + (k & 3);
+    b_hi[o] = hi;
+    b_lo[o] = x - hi;
+  }
+  for (int c = tid; c < CO; c += kTcThreads) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc, sf);
+  pdl_wait();
+  fence_proxy_async();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < kWsProducerWarps) {
+    // the cells a thread copies and the (position, tap chunk) operands it gathers are the same for every tile: worked out once
+    constexpr int kCells = 4, kTasks = 4;                         // host side: hin_t * wp <= 4 * producers, 128 * K4 <= 4 * producers
+    int f_pk[kCells];
+#pragma unroll
+    for (int j = 0; j < kCells; ++j) {
+      const int i = tid + j * kWsProducers, r = i / wp, col = i - r * wp, x = col - L.pl;
+      f_pk[j] = ((r * L.win + x + L.pl) << 10) | (r << 1) | ((i < hin_t * wp && x >= 0 && x < L.win) ? 1 : 0);
+    }
+    auto fetch_tile = [&](int tile, float* xs) {
+      const int n = tile / tpu, h0 = (tile - n * tpu) * RH, hb = h0 * L.sh - L.pt;
+      const float* base = in + ((int64_t)n * L.hin + hb) * L.win - L.pl;
+#pragma unroll
+      for (int j = 0; j < kCells; ++j) {
+        if (tid + j * kWsProducers < hin_t * wp) {
+          const int pk = f_pk[j], h = hb + ((pk >> 1) & 0x1FF);
+          const bool ok = (pk & 1) && h >= 0 && h < L.hin;
+          const uint32_t bytes = ok ? 4u : 0u;
+          const float* src = ok ? base + (pk >> 10) : in;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(xs + tid + j * kWsProducers)), "l"(src), "r"(bytes) : "memory");
+        }
+      }
+    };
+    int g_x01[kTasks], g_x23[kTasks], g_a[kTasks];                // tile offsets of the four taps of a chunk (16 bits each), A offset | row
+#pragma unroll
+    for (int j = 0; j < kTasks; ++j) {
+      const int task = tid + j * kWsProducers, m = task & 127, kc = task >> 7;
+      const int oh = m / L.wout, ow = m - oh * L.wout;
+      int e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kq = 4 * kc + q, ki = kq / L.kw, kj = kq - ki * L.kw;
+        e[q] = (oh * L.sh + ki) * wp + ow * L.sw + kj;
+      }
+      g_x01[j] = e[0] | (e[1] << 16);
+      g_x23[j] = e[2] | (e[3] << 16);
+      g_a[j] = ((kc * LBA + 4 * m) << 7) | m;
+    }
+    {
+      int t0 = blockIdx.x;
+      if (t0 < ntiles) { fetch_tile(t0, xs0); cp_async_mbar_arrive(&in_full[0]); }
+      t0 += gridDim.x;
+      if (t0 < ntiles) { fetch_tile(t0, xs0 + XT); cp_async_mbar_arrive(&in_full[1]); }
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = it & 1, k = it >> 1;
-      mbar_wait(&mma_done[b], (uint32_t)(k & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int n = tile / tpu, h0 = (tile - n * tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
-      const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
-      const uint32_t tacc = tmem + (uint32_t)(b * CO) + ((uint32_t)(32 * q) << 16);
+      const int h0 = (tile % tpu) * RH, npos = imin(RH, L.hout - h0) * L.wout;
+      float* xs = xs0 + b * XT;
+      float* a_hi = a0 + (size_t)b * 2 * K4 * LBA;
+      float* a_lo = a_hi + (size_t)K4 * LBA;
+      mbar_wait(&in_full[b], (uint32_t)(k & 1));
+      if (it >= 2) mbar_wait(&mma_done[b], (uint32_t)((k - 1) & 1));             // the MMAs of tile it-2 have read this A buffer
 #pragma unroll
-      for (int c0 = 0; c0 < CO; c0 += 16) {
-        uint32_t r[16];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                     : "r"(tacc + (uint32_t)c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < npos) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int co = c0 + j;
-            const float4 s = ld4(sc2 + co), t = ld4(sf2 + co);
-            st4(out + (gbase + m) * CO + co,
-                make_float4(fmaxf(fmaf(__uint_as_float(r[j]), s.x, t.x), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 1]), s.y, t.y), 0.f),
-                            fmaxf(fmaf(__uint_as_float(r[j + 2]), s.z, t.z), 0.f), fmaxf(fmaf(__uint_as_float(r[j + 3]), s.w, t.w), 0.f)));
-          }
+      for (int j = 0; j < kTasks; ++j) {
+        if (tid + j * kWsProducers < 128 * K4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((g_a[j] & 127) < npos) v = make_float4(xs[g_x01[j] & 0xFFFF], xs[g_x01[j] >> 16], xs[g_x23[j] & 0xFFFF], xs[g_x23[j] >> 16]);
+          float4 hi, lo;
+          tf32_split(v, hi, lo);
+          st4(a_hi + (g_a[j] >> 7), hi);
+          st4(a_lo + (g_a[j] >> 7), lo);
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tmem_empty[b]);
+      fence_proxy_async();
+      mbar_arrive(&a_full[b]);
+      const int nxt = tile + 2 * (int)gridDim.x;
+      if (nxt < ntiles) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kWsProducers) : "memory");
+        fetch_tile(nxt, xs);
+        cp_async_mbar_arrive(&in_full[b]);
+      }
     }
+  } else if (warp == kWsProducerWarps) {
+    if (lane == 0) ws_mma_role<CO>(ntiles, K4, LBA, a0, b_hi, b_lo, tmem, a_full, tmem_empty, mma_done);
+  } else if (warp >= kTcThreads / 32 - 4) {
+    ws_epilogue_role<CO>(L, RH, tpu, ntiles, tmem, sc, sf, out, mma_done, tmem_empty, warp & 3, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -1066,6 +1219,17 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
       // implicit GEMM on tcgen05 (3xTF32); the limits are the kernel's precomputed per-thread walks (4 cells, 4 gather tasks)
       if (d->use_tc && L.cin == 1 && L.cout == 64 && (L.kh * L.kw) % 8 == 0 && L.wout <= 64 && hin_t * wpt <= 4 * kTcThreads &&
           128 * K4 <= 4 * kTcThreads && hin_t < 512) {
+        const size_t smem_cws = (2 * (size_t)((hin_t * wpt + 3) & ~3) + 4 * (size_t)K4 * (128 * 4 + 4) + 2 * (size_t)K4 * (L.cout * 4 + 4) + 2 * L.cout) * 4;
+        if (d->tc_ws && smem_cws <= 220 * 1024 && hin_t * wpt <= 4 * kWsProducers && 128 * K4 <= 4 * kWsProducers && (K4 & 1) == 0) {
+          auto kws = dscnn_conv_ws_kernel<64>;
+          static SmemOptIn optin_cws;
+          if (optin_cws.ensure(kws, smem_cws) != cudaSuccess) return TCR_ERR_CUDA;
+          const int tiles = ((L.hout + RHt - 1) / RHt) * n;
+          TCR_LAUNCH("dscnn_conv_ws", kws, dim3(std::min(tiles, d->sms)), dim3(kTcThreads), smem_cws, s, L, RHt, n, params, in, out, eps);
+          in = out;
+          cur ^= 1;
+          continue;
+        }
         const size_t smem_tc = (2 * (size_t)((hin_t * wpt + 3) & ~3) + 2 * (size_t)K4 * (128 * 4 + 4) + 2 * (size_t)K4 * (L.cout * 4 + 4) + 2 * L.cout) * 4;
         auto ktc = dscnn_conv_tc_kernel<64>;
         static SmemOptIn optin_tc;
