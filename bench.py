@@ -356,13 +356,15 @@ def run_ours(a):
     # of the ranks' LOCAL gradients, each computed by an unattached handle of the same library and gathered through torch.distributed.
     if world > 1:
         import torch.distributed as dist
-        digest = torch.stack([params.double().sum(), params.double().abs().sum(), moving.double().sum()])
+        digest = torch.stack([params.double().sum(), params.double().abs().sum(), slots.double().sum(), slots.double().abs().sum()])
         gathered = [torch.zeros_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
-        identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
-        m = 16
+        identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)     # trainables + momentum slots (BN moving statistics
+        m = 16                                                                    # are per-replica batch statistics: no SyncBN)
         p_chk = params.clone()
-        local = Engine(model=a.model, width_multiplier=a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms, max_batch=m,
+        # the unattached handle has the attached one's geometry (same max_batch -> same tilings and summation orders), so its local
+        # gradient is bit-for-bit what the attached handle computes before the exchange
+        local = Engine(model=a.model, width_multiplier=a.width, window_size_ms=a.window_ms, window_stride_ms=a.stride_ms, max_batch=n,
                        dropout_keep_prob=0.5, device=local_dev)
         sl, mv = torch.zeros_like(params), moving.clone()
         seed = 12345 * world + rank                                  # the same dropout draws in both handles
@@ -373,7 +375,9 @@ def run_ours(a):
         mean = torch.stack([q.double() for q in parts]).mean(0)
         err = float((g_avg.double() - mean).abs().max() / mean.abs().max().clamp_min(1e-30))
         out["dp_check"] = {"replicas_bit_identical": identical, "averaged_gradient_rel_err_vs_mean_of_local": err,
-                           "shard": f"{m} utterances per rank", "exchange": getattr(eng, "exchange", "nccl"), "ok": bool(identical and err < 1e-5)}
+                           "shard": f"{m} utterances per rank", "exchange": getattr(eng, "exchange", "nccl"), "ok": bool(identical and err < 1e-5),
+                           "note": "digest over trainables and momentum slots; BN moving statistics stay per-replica (no SyncBN, as in the "
+                                   "single-GPU reference)"}
         local.close()
         barrier()
 
@@ -694,12 +698,79 @@ def run_dscnn(a):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = n * a.steps / (ms * 1e-3)
+    # per-kernel durations (separate pass: the event brackets add overhead) and the roofline of the dominant kernel
+    lib = net.lib
+    lib.tcr_profile_enable(1)
+    for i in range(min(a.steps, 30)):
+        net.forward(feats[i % a.rotate], params)
+    torch.cuda.synchronize()
+    import ctypes as C
+    from tcresnet_b200 import _lib as L
+    stats_p, cnt = C.POINTER(L.TcrKernelStat)(), C.c_int32()
+    L.check(lib, lib.tcr_profile_read(C.byref(stats_p), C.byref(cnt)), "tcr_profile_read")
+    stats = {stats_p[i].name.decode(): (float(stats_p[i].total_ms), int(stats_p[i].launches)) for i in range(cnt.value)}
+    lib.tcr_profile_enable(0)
+    total_ms = sum(v[0] for v in stats.values())
+    # DS-CNN-S on 49x40 features: conv_1 (10x4, stride 2x2) -> 25x20x64, then four 3x3 separable blocks at 25x20x64
+    hout, wout, ch = (49 + 1) // 2, (40 + 1) // 2, 64
+    act = n * hout * wout * ch * 4
+    work = {"dscnn_dsblock_ws": (2 * act, n * hout * wout * (2 * 9 * ch + 2 * ch * ch)),
+            "dscnn_dsblock_tc": (2 * act, n * hout * wout * (2 * 9 * ch + 2 * ch * ch)),
+            "dscnn_dsblock": (2 * act, n * hout * wout * (2 * 9 * ch + 2 * ch * ch)),
+            "dscnn_conv_ws": (n * 49 * 40 * 4 + act, n * hout * wout * 2 * 40 * ch),
+            "dscnn_conv_tc": (n * 49 * 40 * 4 + act, n * hout * wout * 2 * 40 * ch),
+            "dscnn_conv": (n * 49 * 40 * 4 + act, n * hout * wout * 2 * 40 * ch),
+            "dscnn_head": (act, n * (hout * wout * ch + 2 * ch * 12))}
+    kernels = []
+    for name, (tms, c) in sorted(stats.items(), key=lambda kv: -kv[1][0]):
+        b, f = work.get(name, (0, 0))
+        dur = tms / c * 1e-3
+        kernels.append({"name": name, "us": dur * 1e6, "launches_per_step": c / min(a.steps, 30), "share": tms / total_ms,
+                        "GBps": b / dur / 1e9, "TFLOPs": f / dur / 1e12})
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = kernels[0]
+    alg_b, alg_f = work.get(dom["name"], (0, 0))
+    roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom["GBps"] / hbm_peak,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": None, "algorithmic_bytes_per_launch": alg_b, "algorithmic_flops_per_launch": alg_f,
+                "kernel_us": dom["us"], "kernel_share_of_step": dom["share"],
+                "note": "activations in + out once per block (fp32 NHWC); the 1x1 conv runs on tcgen05 as three TF32 passes "
+                        "(6.3 GFLOP/launch incl. the split, a ~6 us floor at the tf32 peak), so HBM is the roofline; ncu shows the "
+                        "L1/shared-memory data pipe as the busiest unit (profiles/r02_dscnn_*.txt)"}
+    # end to end through the public call with HOST features: pinned host -> H2D -> forward -> D2H probabilities, every step
+    h_feats = [f.cpu().pin_memory() for f in feats[:4]]
+    d_in = torch.empty(n, 49, 40, device=dev)
+    h_out = torch.empty(n, 12).pin_memory()
+    esteps = max(100, min(a.steps, 200))
+    for i in range(12):
+        d_in.copy_(h_feats[i % 4], non_blocking=True)
+        h_out.copy_(net.forward(d_in, params)[1], non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(esteps):
+        d_in.copy_(h_feats[i % 4], non_blocking=True)
+        h_out.copy_(net.forward(d_in, params)[1], non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_v = n * esteps / (time.perf_counter() - t0)
     emit({"metric": "utterances/sec (forward) DS-CNN-S", "value": value, "unit": "utterances/sec", "n_gpus": 1,
                       "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
                       "config": {"workload": f"DS-CNN-S forward (inference), MFCC 49x40 features resident in HBM, batch {n}",
-                                 "forward_flops_per_utt": net.forward_flops},
-                      "fp32_tflops": value * net.forward_flops / 1e12})
+                                 "global_batch": n, "l2": f"inputs rotate over {a.rotate} resident batches; every block streams "
+                                                          f"{2 * act / 1e6:.0f} MB of activations (> 126 MB L2 over a step)",
+                                 "exchange": "none (1 GPU)", "forward_flops_per_utt": net.forward_flops,
+                                 "pointwise": "fp32 FMA" if os.environ.get("TCR_DSCNN_TC", "2") == "0" else "tcgen05 3xTF32"},
+                      "fp32_tflops": value * net.forward_flops / 1e12, "roofline": roofline, "kernels": kernels,
+                      "gpu_launches": int(sum(k["launches_per_step"] for k in kernels) * a.steps),
+                      "e2e": {"value": e2e_v, "unit": "utterances/sec", "h2d_bytes_per_step": n * 49 * 40 * 4,
+                              "d2h_bytes_per_step": n * 12 * 4, "steps": esteps,
+                              "path": "DsCnn.forward on features copied from pinned host memory, probabilities copied back, every step"}})
 
 
 _JSON_FD = None

@@ -1343,12 +1343,14 @@ static ResidentState* resident_state(tcr_handle* h) {
   if ((h->n_train & 3) || (h->fc_off & 3) || (h->fc2_off & 3)) want = std::min(want, 1);
 #ifndef TCR_EMU
   if (S->smem_f > 227 * 1024) return S;
-  if (cudaFuncSetAttribute(resident_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem_f) != cudaSuccess) return S;
+  // the opt-in limit is a property of the FUNCTION, shared by every handle of the process: it is only ever raised
+  static SmemOptIn optin_f, optin_b;
+  if (optin_f.ensure(resident_fwd_kernel, S->smem_f) != cudaSuccess) return S;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_fwd_kernel, kResThreads, S->smem_f) != cudaSuccess || per_sm < 1) return S;
   if (want >= 2) {
     if (S->smem_b > 227 * 1024 ||
-        cudaFuncSetAttribute(resident_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem_b) != cudaSuccess ||
+        optin_b.ensure(resident_bwd_kernel, S->smem_b) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_bwd_kernel, kResThreads, S->smem_b) != cudaSuccess || per_sm < 1)
       want = 1;
   }

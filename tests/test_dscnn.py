@@ -85,3 +85,14 @@ def test_emulated_dscnn_matches_oracle():
 def test_cuda_dscnn_matches_oracle(size, h, w, n):
     from tcr_harness import TorchBackend
     assert _run(TorchBackend(), size, h, w, n) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["0", "1"], ids=["fp32-fma", "tcgen05-lockstep"])
+def test_cuda_dscnn_other_kernel_paths(mode, monkeypatch):
+    """TCR_DSCNN_TC picks the kernels when the net is created: 0 = register-tiled fp32 FMA, 1 = the lock-step tcgen05 kernels,
+    default = the warp-specialised tcgen05 kernels (TMA input tiles).  Every path meets the same bound."""
+    from tcr_harness import TorchBackend
+    monkeypatch.setenv("TCR_DSCNN_TC", mode)
+    assert _run(TorchBackend(), "S", 49, 40, 150) < 1e-5
+    assert _run(TorchBackend(), "S", 49, 10, 39) < 1e-5

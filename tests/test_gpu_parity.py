@@ -216,3 +216,22 @@ def test_silent_batch_and_full_scale(backend):
     assert np.isfinite(got).all()
     assert rel_err(got, ref) < 2e-5
     eng.close()
+
+
+def test_handles_of_different_size_share_the_resident_kernels(backend):
+    """The shared-memory opt-in of the resident kernels is a per-FUNCTION attribute: a second, smaller handle created later must
+    not lower it under the first handle (bench.py's dp_check does exactly this: a 16-utterance handle next to the 512 one)."""
+    import torch
+    from tcresnet_b200.engine import Engine
+    big = Engine(max_batch=512)
+    p, s, m = big.new_variables(seed=0)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    wav = torch.rand(512, 16000, device="cuda", generator=gen) * 2 - 1
+    hot = torch.nn.functional.one_hot(torch.randint(0, 12, (512,), device="cuda", generator=gen), 12).float()
+    l0 = float(big.train_step(wav, hot, p.clone(), s.clone(), m.clone(), 0.1)["losses"][0])
+    small = Engine(max_batch=16)
+    ps, ss, ms = small.new_variables(seed=0)
+    small.train_step(wav[:16], hot[:16], ps, ss, ms, 0.1)
+    l1 = float(big.train_step(wav, hot, p.clone(), s.clone(), m.clone(), 0.1)["losses"][0])             # launch still fits
+    assert l0 == l1
+    small.close(); big.close()

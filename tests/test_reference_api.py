@@ -187,7 +187,8 @@ def test_deployable_model_batch1_inference(tmp_path):
     rng = np.random.default_rng(0)
     clips = rng.uniform(-1, 1, (5, 16000)).astype(np.float32)
     import torch
-    ref = model.engine.forward(torch.from_numpy(clips).cuda(), model.params, model.moving)["probs"].cpu().numpy()
+    ref = np.concatenate([model.engine.forward(torch.from_numpy(c[None]).cuda(), model.params, model.moving)["probs"].cpu().numpy()
+                          for c in clips])                                 # the engine was sized for batch 1
     got = np.concatenate([deployed(c) for c in clips])                     # calls 3-5 replay the captured graph
     assert deployed._graph is not None
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)

@@ -21,6 +21,21 @@ print(run_case(b, model='TCResNet14', wm=1.5, window=480, stride=160, n=5, keep=
 print(run_case(b, model='TCResNet8', wm=1.0, n=9, keep=0.5))
 " > gpurun_out/sanitizer.txt 2>&1 ; echo "sanitizer rc=$?" | tee -a gpurun_out/sanitizer.txt
   tail -5 gpurun_out/sanitizer.txt
+  # shared-memory races and divergent barriers: one TC-ResNet step (default kernels), one with the resident backward kernel, and
+  # the DS-CNN forward (mbarrier / TMA / tcgen05 pipeline); racecheck serialises heavily, so the cases are tiny
+  for tool in racecheck synccheck; do
+    echo "== compute-sanitizer --tool $tool"
+    TCR_RESIDENT=2 timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 python -c "
+import sys; sys.path.insert(0,'tests'); sys.path.insert(0,'.')
+from tcr_harness import TorchBackend
+from parity_cases import run_case
+from test_dscnn import _run
+b = TorchBackend()
+print(run_case(b, model='TCResNet8', wm=1.0, n=5, keep=0.5))
+print(_run(b, 'S', 49, 40, 3))
+" > gpurun_out/$tool.txt 2>&1 ; echo "$tool rc=$?" | tee -a gpurun_out/$tool.txt
+    grep -E "RACECHECK SUMMARY|ERROR SUMMARY|hazard|Barrier error" gpurun_out/$tool.txt | head -8
+  done
 fi
 echo "== bench" ; timeout 900 python bench.py --steps 100 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?"
 cat gpurun_out/bench.json | cut -c1-3000 ; tail -5 gpurun_out/bench.err
