@@ -130,13 +130,18 @@ static int build_frontend_tables(tcr_handle* h) {
         last = k;
       }
     }
+    // packed for the kernel's 4-wide walk: the band starts on a multiple of four bins and covers whole groups of four, the
+    // extra leading / trailing weights are zero (start = first bin of the walk, len = groups of four, off = multiple of four)
     off[m] = (int)wts.size();
     if (first >= 0) {
-      start[m] = first;
-      len[m] = last - first + 1;
-      for (int k = first; k <= last; ++k) {
+      const int first4 = first & ~3;
+      const int groups = (last - first4) / 4 + 1;
+      start[m] = first4;
+      len[m] = groups;
+      for (int k = first4; k < first4 + 4 * groups; ++k) {
         const double fm = mel(nyq * k / (bins - 1));
-        wts.push_back((float)std::max(0.0, std::min((fm - lo) / (ce - lo), (up - fm) / (up - ce))));
+        const double w = (k >= first && k <= last) ? std::max(0.0, std::min((fm - lo) / (ce - lo), (up - fm) / (up - ce))) : 0.0;
+        wts.push_back((float)w);
       }
     }
   }

@@ -109,6 +109,24 @@ __device__ __forceinline__ float2 frame_sample(const void* x, const float2* __re
 template <int R, int MAXQ, bool PCM>
 __device__ __forceinline__ void fft_first_pass(const void* x, const float2* __restrict__ wtab, int half_w, float2* z, int N, int lane) {
   const int nb = N / R;
+  if (R == 8 && half_w == 5 * nb) {
+    // the window fills exactly five of the eight butterfly inputs (640-sample window in a 1024-point FFT): the last three are
+    // the zero padding, known at compile time, so their loads, bound checks and half of the first butterfly stage fold away
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const int j = lane + 32 * q;
+      if (j < nb) {
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = r < 5 ? frame_sample<PCM>(x, wtab, j + r * nb, 1 << 30) : make_float2(0.f, 0.f);
+        dft_small<R>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[zi(j * R + r)] = v[r];
+      }
+    }
+    __syncwarp();
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < MAXQ; ++q) {
     const int j = lane + 32 * q;
@@ -180,7 +198,7 @@ __global__ void __launch_bounds__(224, (NF2 <= 512) ? 4 : 2) mfcc_kernel(MfccArg
   const float2* g_tw2 = reinterpret_cast<const float2*>(a.consts + a.c_tw2);
   const float2* g_win = reinterpret_cast<const float2*>(a.consts + a.c_win);
   const int z_elems = NF2 + (NF2 >> 4);
-  const int pw_elems = ALIAS ? 0 : ((NF2 + 1 + 3) / 4) * 4;
+  const int pw_elems = ALIAS ? 0 : ((NF2 + 4 + 3) / 4) * 4;      // spectrum + 3 zero bins for the 4-wide band loop
   const int per_warp_floats = 2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3);
   float* s_warp = s_const + a.c_smem + (size_t)warp * per_warp_floats;
   float2* z = reinterpret_cast<float2*>(s_warp);
@@ -247,25 +265,28 @@ __global__ void __launch_bounds__(224, (NF2 <= 512) ? 4 : 2) mfcc_kernel(MfccArg
         pw[NF2 - k] = a.magnitude ? sqrtf(pb) : pb;
       }
     }
+    if (lane < 3) pw[NF2 + 1 + lane] = 0.f;                 // the 4-wide band loop may read up to three bins past the spectrum
     __syncwarp();
-    // banded mel + log; a lane takes bins i and mel_bins-1-i so short and long bands pair up
+    // banded mel + log; a lane takes bins i and mel_bins-1-i so short and long bands pair up.  A band starts on a multiple of four
+    // FFT bins (its packed weights carry leading / trailing zeros), so the walk is float4 loads and four independent chains.
 #pragma unroll 1
     for (int i = lane; 2 * i < a.mel_bins; i += 32) {
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int m = h ? a.mel_bins - 1 - i : i;
         if (h && m == i) break;
-        const int start = __ldg(&a.mel_start[m]), len = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
+        const int start = __ldg(&a.mel_start[m]), len4 = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
         const float* pp = pw + start;
         const float* ww = s_melw + off;
-        float a0 = 0.f, a1 = 0.f;                         // two chains: the band loop is latency-, not throughput-bound
-        int q = 0;
-        for (; q + 1 < len; q += 2) {
-          a0 = fmaf(pp[q], ww[q], a0);
-          a1 = fmaf(pp[q + 1], ww[q + 1], a1);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int q = 0; q < len4; ++q) {
+          const float4 p4 = ld4(pp + 4 * q), w4 = ld4(ww + 4 * q);
+          a0 = fmaf(p4.x, w4.x, a0);
+          a1 = fmaf(p4.y, w4.y, a1);
+          a2 = fmaf(p4.z, w4.z, a2);
+          a3 = fmaf(p4.w, w4.w, a3);
         }
-        if (q < len) a0 = fmaf(pp[q], ww[q], a0);
-        lm[m] = logf((a0 + a1) + 1e-6f);
+        lm[m] = logf(((a0 + a1) + (a2 + a3)) + 1e-6f);
       }
     }
     __syncwarp();
@@ -282,13 +303,23 @@ __global__ void __launch_bounds__(224, (NF2 <= 512) ? 4 : 2) mfcc_kernel(MfccArg
       // the two halves of the log-mel vector first and walks only M/2 rows (odd M: the middle row is added unfolded).
       const int M = a.mel_bins, half = M >> 1;
       const float sgn = (g & 1) ? -1.f : 1.f;
+      if (a.features == 40) {                               // the usual 40 coefficients: five per lane, no bound checks
 #pragma unroll 4
-      for (int m = q; m < half; m += 4) {
-        const float v = fmaf(sgn, lm[M - 1 - m], lm[m]);
-        const float* row = a.dct + m * a.features + g;
+        for (int m = q; m < half; m += 4) {
+          const float v = fmaf(sgn, lm[M - 1 - m], lm[m]);
+          const float* row = a.dct + m * 40 + g;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nj && g + 8 * j < a.features) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
+          for (int j = 0; j < 5; ++j) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
+        }
+      } else {
+#pragma unroll 4
+        for (int m = q; m < half; m += 4) {
+          const float v = fmaf(sgn, lm[M - 1 - m], lm[m]);
+          const float* row = a.dct + m * a.features + g;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < nj && g + 8 * j < a.features) acc[j] = fmaf(v, __ldg(row + 8 * j), acc[j]);
+        }
       }
       if ((M & 1) && q == 0) {
         const float v = lm[half];
@@ -315,7 +346,7 @@ __global__ void __launch_bounds__(224, (NF2 <= 512) ? 4 : 2) mfcc_kernel(MfccArg
 size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps) {
   const int span_max = (a.fpb - 1) * a.stride + a.window;
   const int z_elems = nf2 + (nf2 >> 4);
-  const int pw_elems = nf2 <= 512 ? 0 : ((nf2 + 1 + 3) / 4) * 4;      // fft <= 1024: the power spectrum aliases the FFT buffer
+  const int pw_elems = nf2 <= 512 ? 0 : ((nf2 + 4 + 3) / 4) * 4;      // fft <= 1024: the power spectrum aliases the FFT buffer
   const size_t per_warp = (size_t)(2 * z_elems + pw_elems + ((a.mel_bins + 3) & ~3)) * 4;
   return 16 + (size_t)span_max * 4 + (size_t)a.c_smem * 4 + per_warp * warps;
 }

@@ -16,9 +16,9 @@ struct MfccArgs {
   // one TMA bulk copy:  [0, 2*fft/2) tw exp(-2 pi i n / (fft/2)) | c_melw: packed mel weights | (c_smem) |
   //   c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_win: periodic Hann window [window]
   const float* consts; int c_tw2, c_melw, c_win, c_smem;
-  const int* mel_start;     // [mel_bins] first FFT bin with non-zero weight
-  const int* mel_len;       // [mel_bins]
-  const int* mel_off;       // [mel_bins] offset into mel_w
+  const int* mel_start;     // [mel_bins] first FFT bin of the band's walk (a multiple of four; leading weights may be zero)
+  const int* mel_len;       // [mel_bins] groups of four bins in the walk
+  const int* mel_off;       // [mel_bins] offset into mel_w (a multiple of four)
   const float* dct;         // [mel_bins, features]
 };
 

@@ -18,10 +18,10 @@ def backend():
 @pytest.mark.parametrize("kw", [
     dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=1),                      # config 1 (plumbing)
     dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=3, keep=0.5),            # eval-script batch size
-    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=39, keep=0.5, steps=2),  # test-script batch size
+    dict(model="TCResNet8", wm=1.0, window=640, stride=320, n=39, keep=0.5, steps=2, force_masks=True),  # test-script batch size
     dict(model="TCResNet8", wm=1.0, window=480, stride=160, n=37, keep=0.5, ls=0.1),   # script shape T=98, pad (3,4)
     dict(model="TCResNet14", wm=1.5, window=640, stride=320, n=21, keep=0.5),
-    dict(model="TCResNet14", wm=1.0, window=480, stride=160, n=16, use_wav=False, steps=3),
+    dict(model="TCResNet14", wm=1.0, window=480, stride=160, n=16, use_wav=False, steps=3, force_masks=True),
     dict(model="TCResNet8", wm=1.5, window=640, stride=320, n=150, check_f32_floor=True),
 ], ids=["r8-n1", "r8-n3", "r8-n39-2steps", "r8-T98-n37", "r14x1.5-n21", "r14-T98-3steps", "r8x1.5-n150"])
 def test_cuda_path_matches_oracle(backend, kw):
@@ -130,7 +130,7 @@ def test_host_feed_pipeline_matches_device_steps(backend):
 def test_without_thread_block_clusters(backend, monkeypatch):
     """TCR_CLUSTER=1: one statistics record per CTA instead of one per 8-CTA cluster; same results within tolerance."""
     monkeypatch.setenv("TCR_CLUSTER", "1")
-    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=70, keep=0.5, steps=2, check_f32_floor=True)
+    run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=70, keep=0.5, steps=2, force_masks=True)
     monkeypatch.setenv("TCR_CLUSTER", "4")
     run_case(backend, model="TCResNet14", wm=1.0, window=640, stride=320, n=19, keep=1.0)
 
