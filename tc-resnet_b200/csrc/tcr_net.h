@@ -23,9 +23,11 @@ int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_cli
 int eval_accumulate_launch(const float* scores, const float* onehot, int n, int classes, int topk, int64_t* counts, cudaStream_t s);
 int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
 // Resident forward (tcr_resident.cu): the training forward + head as one cooperative kernel with SM-resident activations.
-int resident_mode(tcr_handle* h);      // 0: per-layer kernels, 1: resident forward, 2: resident forward + backward
+int resident_mode(tcr_handle* h);      // 0: per-layer kernels, 1: resident forward, 2: resident forward + backward (dW inside), 3: resident forward + backward-data
 int resident_forward(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s);
 int resident_backward(tcr_handle* h, const float* feat, const tcr_step_args* a, float* grads, int* l2_records, cudaStream_t s);
+int resident_backward_data(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s);   // mode 3
+int net_weight_gradients(tcr_handle* h, const float* feat, int n, cudaStream_t s);                      // the grouped launch alone
 void resident_destroy(tcr_handle* h);
 int net_backward(tcr_handle* h, const float* feat, const float* params, int n, cudaStream_t s);
 

@@ -723,7 +723,11 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
       }
     }
   }
-  // weight gradients: every layer's inputs are final now -> one grouped launch over all layers
+  return net_weight_gradients(h, feat, n, s);
+}
+
+// weight gradients: every layer's inputs are final now -> one grouped launch over all layers
+int net_weight_gradients(tcr_handle* h, const float* feat, int n, cudaStream_t s) {
   {
     auto kfn = dw_grouped_kernel;
 #ifndef TCR_EMU

@@ -243,7 +243,7 @@ int net_update(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStr
   GradArgs ga{h->d_segs, h->n_segs, h->n_train, fc_segment(h), h->d_dwfc_part, h->fc_records, a->params, a->weight_decay,
               grads, h->d_l2part};
   int l2_records = blocks;
-  if (resident_mode(h) >= 2) {      // backward chain + weight gradients + this reduction in one cooperative kernel (tcr_resident.cu)
+  if (resident_mode(h) == 2) {      // backward chain + weight gradients + this reduction in one cooperative kernel (tcr_resident.cu)
     int rc = resident_backward(h, feat, a, grads, &l2_records, s);
     if (rc) return rc;
   } else {

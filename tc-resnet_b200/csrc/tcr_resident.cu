@@ -15,8 +15,11 @@
 //   * every CTA sums the records itself (float4 loads, all in flight at once, fixed order: bit-reproducible), CTA 0 publishes;
 //   * the phase bodies are non-inlined functions shared by all layers, so their code is fetched once and stays in the I-cache;
 //   * weight gradients never go through atomics: one partial per CTA, reduced in a fixed order by the kernel's last phase.
-// The forward kernel leaves exactly what the multi-kernel forward leaves and the backward kernel what net_backward +
-// grad_finalize leave, so either can be paired with the per-layer kernels (TCR_RESIDENT=0/1/2: off / forward only / both).
+// The forward kernel leaves exactly what the multi-kernel forward leaves (plus the transposed filter banks of the backward pass) and
+// the backward kernel what net_backward + grad_finalize leave, so either can be paired with the per-layer kernels.
+// TCR_RESIDENT = 0: per-layer kernels | 1: resident forward | 2: resident forward + backward with the weight gradients and the
+// gradient reduction inside | 3 (default): resident forward + resident backward-DATA chain; the weight gradients stay in the
+// grouped launch (two CTAs per SM), which reads the layer gradients the kernel stores.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -33,6 +36,7 @@ struct RConv {
   int cin, cout, k, stride, t_in, t_out, pad_left, pad_right;
   long long w_off, gamma_off, beta_off;
   float* y; float* bnf; float* var; float* bsum;
+  float* g;                                        // gradient after this layer's ReLU mask (what the grouped weight-gradient launch reads)
   float* frec; float* brec;                        // [G][2*cout] per-CTA records: (sum y, sum y^2) / (sum dz, sum dz*xhat)
   float* dwres;                                    // [G][k*cin*cout] per-CTA weight-gradient partials
   const float* wT;                                 // transposed bank [k][cout][cin]
@@ -40,7 +44,7 @@ struct RConv {
   int bks;                                         // backward-data k-slices
   int tbl, bs;                                     // float offsets of the [4][cout] table / [2][cout] sums in their smem regions
 };
-struct RBlock { int a, b, down, c, t; float* out; };
+struct RBlock { int a, b, down, c, t; float* out; float* gblk; };
 
 struct ResProgram {                  // static per handle
   int nconvs, nblocks, classes, umax;
@@ -67,6 +71,8 @@ struct ResCall {                     // per call
   float* logits; float* probs;
   int n; unsigned bar_base; float inv_n;
   float weight_decay; float* grads;  // backward kernel
+  int dw_inside;                     // backward kernel: 1 = weight gradients + reduction in the kernel, 0 = it stores the layer gradients
+                                     // for the grouped weight-gradient launch instead (mode 3)
   long long* tl;                     // debug timeline (TCR_DEBUG_TIMELINE=1): [cta][32] globaltimer stamps, else null
 };
 
@@ -503,6 +509,20 @@ __device__ __forceinline__ void res_run_conv(float* smem, const ResProgram& P, c
   }
 }
 
+// Transposed filter banks wT[k][co][ci] for the backward-data pass (what weight_transpose_kernel writes), spread over the CTAs and
+// run in the shadow of the first grid barrier: nobody waits for it before the kernel ends.
+__device__ __noinline__ void res_weight_transpose(const ResProgram& P, const float* __restrict__ params, int cta, int G) {
+  for (int l = 1; l < P.nconvs; ++l) {
+    const RConv& L = P.conv[l];
+    const int numel = L.k * L.cin * L.cout;
+    float* wT = const_cast<float*>(L.wT);
+    for (int i = cta * kResThreads + (int)threadIdx.x; i < numel; i += G * kResThreads) {
+      const int ci = i % L.cin, r = i / L.cin, co = r % L.cout, k = r / L.cout;
+      wT[i] = __ldg(params + L.w_off + ((long long)k * L.cin + ci) * L.cout + co);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kResThreads, 1) resident_fwd_kernel(const __grid_constant__ ResProgram P, const __grid_constant__ ResCall c) {
   TCR_DYNAMIC_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -561,6 +581,7 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_fwd_kernel(const __gr
     // nobody waits for these: the pre-BatchNorm outputs go to global memory for the backward pass
     res_store(L.y + (size_t)u0 * L.t_out * L.cout, ys, R * (L.cout >> 2));
     if (D) res_store(D->y + (size_t)u0 * L.t_out * D->cout, sh, R * (D->cout >> 2));
+    if (ph == 0) res_weight_transpose(P, c.params, cta, G);
     res_stamp(c, sl + 3);
     gbar_wait(P.bar, target);
     res_stamp(c, sl + 4);
@@ -719,7 +740,7 @@ __device__ __noinline__ void res_convT(float* smem, int dys_off, int dysd_off, i
 //   (identity shortcut) or recomputed as bn_b(yp) + relu(bn_d(ypd)).
 __device__ __noinline__ void res_bwd_epilogue(const float* dxs, int rcap, int KS, int Rin, int C, const float* gid, int kind,
                                               const float* yp, const float* tp, const float* outp, const float* ypd, const float* tpd,
-                                              float* gdst, float* red, int red_cap, float* recp, float* recpd) {
+                                              float* gdst, float* gglob, float* red, int red_cap, float* recp, float* recpd) {
   const int tid = threadIdx.x;
   const int NCIG = C >> 2;
   const int nseg = imax(1, imin(kResThreads / NCIG, red_cap / (4 * C)));   // red: [4][nseg][C]
@@ -742,6 +763,7 @@ __device__ __noinline__ void res_bwd_epilogue(const float* dxs, int rcap, int KS
       else if (ypd) g = rmask_pos4(v, add4(chan4_bn(kp, yv), relu4(zd)));      // the block output, recomputed exactly as the forward pass formed it
       else g = rmask_pos4(v, ld4(outp + o));
       st4(gdst + o, g);
+      if (gglob) st4(gglob + o, g);
       s1 = add4(s1, g);
       s2 = add4(s2, rmul4(g, chan4_xhat(kp, yv)));
       if (ypd) {
@@ -986,16 +1008,18 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
       res_convT(smem, P.b_dys, 0, P.b_w, 0, P.b_pl, rcap, Ue, C, C, 0, 1, B.t, B.t, Lb.pad_left, TPd, PLd, COS, 0, Lb.bks);
       __syncthreads();
       res_stamp(c, slot + 1);
-      res_bwd_epilogue(smem + P.b_pl, rcap, Lb.bks, R, C, nullptr, 1, ypr, tblr + La.tbl, nullptr, nullptr, nullptr, smem + P.b_g[gi_a], ysr,
-                       P.b_ys_cap, La.brec + (size_t)cta * 2 * C, nullptr);
+      res_bwd_epilogue(smem + P.b_pl, rcap, Lb.bks, R, C, nullptr, 1, ypr, tblr + La.tbl, nullptr, nullptr, nullptr, smem + P.b_g[gi_a],
+                       c.dw_inside ? nullptr : La.g + (size_t)u0 * B.t * C, ysr, P.b_ys_cap, La.brec + (size_t)cta * 2 * C, nullptr);
       res_stamp(c, slot + 2);
       gbar_arrive(P.bar);
       target += (unsigned)G;
       // ---- nobody waits for the rest of this phase ----
       // x_a = relu(bn_a(y_a)) as the padded input tile of conv_b (aliases the dx planes, which are dead)
       const int TPx = Lb.pad_left + B.t + Lb.pad_right;
-      res_stage(ypr, tblr + La.tbl, smem + P.b_pl, Ue, B.t, C, TPx, C, Lb.pad_left, Lb.pad_right);
-      __syncthreads();
+      if (c.dw_inside) {
+        res_stage(ypr, tblr + La.tbl, smem + P.b_pl, Ue, B.t, C, TPx, C, Lb.pad_left, Lb.pad_right);
+        __syncthreads();
+      }
       // next phase (conv_a): its tensors travel during this layer's weight gradient; the bank region doubles as the
       // weight-gradient scratch, so the TMA of the next bank(s) goes out after it
       const int Ca = La.cin, Rin = Ue * La.t_in;
@@ -1011,7 +1035,7 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
           res_fetch(ypr, P.conv[0].y + (size_t)u0 * La.t_in * Ca, n4);
         }
       }
-      res_dw<9>(smem, P.b_pl, TPx, C, P.b_dys, TPd, PLd, COS, Ue, C, C, 1, B.t, smem + P.b_w, Lb.dwres + (size_t)cta * 9 * C * C);
+      if (c.dw_inside) res_dw<9>(smem, P.b_pl, TPx, C, P.b_dys, TPd, PLd, COS, Ue, C, C, 1, B.t, smem + P.b_w, Lb.dwres + (size_t)cta * 9 * C * C);
       res_load_bank(smem + P.b_w, La.wT, (unsigned)(La.k * La.cin * La.cout), Dd ? Dd->wT : nullptr, Dd ? (unsigned)(Dd->cin * Dd->cout) : 0u, wbar);
       res_stamp(c, slot + 3);
       gbar_wait(P.bar, target);
@@ -1043,18 +1067,22 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
         const RConv& Lpb = P.conv[Bp.b];
         const RConv* Lpd = Bp.down >= 0 ? &P.conv[Bp.down] : nullptr;
         res_bwd_epilogue(smem + P.b_pl, rcap, La.bks, Rin, Ca, gid, 2, ypr, tblr + Lpb.tbl, Lpd ? nullptr : ypr + cap, Lpd ? ypr + cap : nullptr,
-                         Lpd ? tblr + Lpd->tbl : nullptr, smem + P.b_g[gi_n], ysr, P.b_ys_cap, Lpb.brec + (size_t)cta * 2 * Ca,
+                         Lpd ? tblr + Lpd->tbl : nullptr, smem + P.b_g[gi_n], c.dw_inside ? nullptr : Bp.gblk + (size_t)u0 * La.t_in * Ca, ysr,
+                         P.b_ys_cap, Lpb.brec + (size_t)cta * 2 * Ca,
                          Lpd ? Lpd->brec + (size_t)cta * 2 * Ca : nullptr);
       } else {
         res_bwd_epilogue(smem + P.b_pl, rcap, La.bks, Rin, Ca, gid, 1, ypr, tblr + P.conv[0].tbl, nullptr, nullptr, nullptr, smem + P.b_g[gi_n],
-                         ysr, P.b_ys_cap, P.conv[0].brec + (size_t)cta * 2 * Ca, nullptr);
+                         c.dw_inside ? nullptr : P.conv[0].g + (size_t)u0 * La.t_in * Ca, ysr, P.b_ys_cap, P.conv[0].brec + (size_t)cta * 2 * Ca,
+                         nullptr);
       }
       res_stamp(c, slot + 2);
       gbar_arrive(P.bar);
       target += (unsigned)G;
       // ---- weight gradients of conv_a and the shortcut conv: X = block input as conv_a's padded tile (aliases the planes) ----
       const int TPx = La.pad_left + La.t_in + La.pad_right;
-      if (bi > 0 && P.blk[bi - 1].down >= 0) {
+      if (!c.dw_inside) {
+        // mode 3: the grouped launch computes the weight gradients from the stored layer gradients
+      } else if (bi > 0 && P.blk[bi - 1].down >= 0) {
         const RBlock& Bp = P.blk[bi - 1];
         res_block_out(ypr, tblr + P.conv[Bp.b].tbl, ypr + cap, tblr + P.conv[Bp.down].tbl, nullptr, 0, 0, 0, smem + P.b_pl, Ue, La.t_in, Ca, TPx, Ca,
                       La.pad_left, La.pad_right, nullptr);
@@ -1069,13 +1097,13 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
         const RBlock& Bp = P.blk[bi - 1];
         res_fetch(ysr, P.conv[Bp.b].y + (size_t)u0 * Bp.t * Bp.c, Ue * Bp.t * (Bp.c >> 2));
         res_fetch(ypr, P.conv[Bp.a].y + (size_t)u0 * Bp.t * Bp.c, Ue * Bp.t * (Bp.c >> 2));
-      } else {                          // last phase: conv0's y and its input, the features
+      } else if (c.dw_inside) {         // last phase: conv0's y and its input, the features
         const RConv& L0 = P.conv[0];
         res_fetch(ysr, L0.y + (size_t)u0 * La.t_in * Ca, Rin * (Ca >> 2));
         res_fetch(ypr, c.feat + (size_t)u0 * L0.t_in * L0.cin, Ue * L0.t_in * (L0.cin >> 2));
       }
-      res_dw<9>(smem, P.b_pl, TPx, Ca, P.b_dys, TPd, PLd, COS, Ue, Ca, C, S, B.t, smem + P.b_w, La.dwres + (size_t)cta * 9 * Ca * C);
-      if (Dd)                           // 1x1 / stride 2, no padding: x row = pad_left + 2 t
+      if (c.dw_inside) res_dw<9>(smem, P.b_pl, TPx, Ca, P.b_dys, TPd, PLd, COS, Ue, Ca, C, S, B.t, smem + P.b_w, La.dwres + (size_t)cta * 9 * Ca * C);
+      if (Dd && c.dw_inside)            // 1x1 / stride 2, no padding: x row = pad_left + 2 t
         res_dw<1>(smem, P.b_pl + La.pad_left * Ca, TPx, Ca, P.b_dyd, B.t, 0, COS, Ue, Ca, C, 2, B.t, smem + P.b_w, Dd->dwres + (size_t)cta * Ca * C);
       if (bi > 0) {
         const RConv& Lpb = P.conv[P.blk[bi - 1].b];
@@ -1101,7 +1129,7 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
     }
   }
   // =============== conv0's weight gradient (no input gradient), then the gradient reduction ===============
-  {
+  if (c.dw_inside) {
     const RConv& L0 = P.conv[0];
     const int C = L0.cout, COS = chan_stride(C), TPx = L0.pad_left + L0.t_in + L0.pad_right;
     cp_async_wait_all();
@@ -1178,10 +1206,9 @@ static ResidentState* resident_state(tcr_handle* h) {
   if (h->resident) return (ResidentState*)h->resident;
   ResidentState* S = new ResidentState();
   h->resident = S;
-  // default: resident forward, per-layer backward kernels.  Measured on B200, TCResNet8-1.0, N=512: the
-  // resident backward (TCR_RESIDENT=2) is correct but its one-CTA-per-SM FMA loops run 16 warps where the per-layer kernels run
-  // two CTAs per SM with programmatic-launch overlap, and it loses ~25 us per step to them.
-  int want = 1;
+  // default 3.  Measured on B200, TCResNet8-1.0, N=512: mode 1 0.366 ms/step, mode 3 0.356 ms, mode 2 ~0.39 ms:
+  // the weight-gradient FMA loops of mode 2 run 16 warps per SM where the grouped launch runs two CTAs per SM and loses to it.
+  int want = 3;
   if (const char* e = getenv("TCR_RESIDENT")) want = atoi(e);
   if (want <= 0) return S;
   int sms = 3;                       // emulator: a few CTAs exercise ragged ownership
@@ -1209,18 +1236,18 @@ static ResidentState* resident_state(tcr_handle* h) {
     L.pad_left = cv.pad_left;
     L.pad_right = std::max((cv.t_out - 1) * cv.stride + cv.k - cv.pad_left - cv.t_in, 0);
     L.w_off = cv.w_off; L.gamma_off = cv.gamma_off; L.beta_off = cv.beta_off;
-    L.y = cv.y; L.bnf = cv.bnf; L.var = cv.var; L.bsum = cv.bsum; L.frec = cv.fpart; L.brec = cv.bpart; L.wT = cv.wT;
+    L.y = cv.y; L.bnf = cv.bnf; L.var = cv.var; L.bsum = cv.bsum; L.g = cv.g; L.frec = cv.fpart; L.brec = cv.bpart; L.wT = cv.wT;
     L.tbl = tbl; L.bs = bs;
     tbl += 4 * cv.cout;
     bs += 2 * cv.cout;
     if (cv.cout > kResThreads / 2) return S;                       // single-pass statistics need 2C <= blockDim
     if (cv.k != 9 && cv.k != 3 && cv.k != 1) return S;
-    if ((cv.cin / 4) * (cv.cout / 4) * (cv.k >= 3 ? cv.k / 3 : 1) > kResThreads) want = std::min(want, 1);   // weight-gradient tiles of one CTA
+    if ((cv.cin / 4) * (cv.cout / 4) * (cv.k >= 3 ? cv.k / 3 : 1) > kResThreads && want == 2) want = 3;   // weight-gradient tiles of one CTA: grouped launch instead
   }
   if (h->convs[0].k != 3) return S;
   for (int b = 0; b < P.nblocks; ++b) {
     const BlockPlan& bp = h->blocks[b];
-    P.blk[b] = RBlock{bp.a, bp.b, bp.down, bp.c, bp.t, bp.out};
+    P.blk[b] = RBlock{bp.a, bp.b, bp.down, bp.c, bp.t, bp.out, bp.gblk};
     if (h->convs[bp.a].k != 9 || h->convs[bp.b].k != 9) return S;
   }
   auto al = [](int v) { return (v + 3) & ~3; };
@@ -1355,7 +1382,7 @@ static ResidentState* resident_state(tcr_handle* h) {
       want = 1;
   }
 #endif
-  if (want >= 2) {                   // per-CTA weight-gradient partials
+  if (want == 2) {                   // per-CTA weight-gradient partials
     for (int l = 0; l < P.nconvs; ++l) {
       void* q = nullptr;
       const size_t bytes = (size_t)sms * h->convs[l].wnumel() * sizeof(float);
@@ -1366,7 +1393,7 @@ static ResidentState* resident_state(tcr_handle* h) {
     }
   }
   S->grid_max = sms;
-  S->mode = want >= 2 ? 2 : 1;
+  S->mode = want >= 3 ? 3 : (want == 2 ? 2 : 1);
   if (getenv("TCR_RESIDENT_VERBOSE")) {
     fprintf(stderr, "[tcr] resident mode %d, umax %d, smem fwd %zu B, bwd %zu B\n", S->mode, umax, S->smem_f, S->smem_b);
     for (int l = 0; l < P.nconvs; ++l)
@@ -1447,10 +1474,26 @@ int resident_backward(tcr_handle* h, const float* feat, const tcr_step_args* a, 
   ResCall c = res_call(h, feat, a);
   c.grads = grads;
   c.tl = h->d_timeline ? h->d_timeline + 148 * 32 : nullptr;
+  c.dw_inside = 1;
   c.bar_base = S->bar_next;
   S->bar_next += (unsigned)G * (unsigned)(2 * h->blocks.size() + 1);
   *l2_records = G;
   return res_launch(h, "resident_bwd", resident_bwd_kernel, G, S->smem_b, c, s);
+}
+
+// Mode 3: the backward-data chain alone as the resident kernel.  It leaves every layer's masked gradient (ConvPlan::g,
+// BlockPlan::gblk) and the published BatchNorm-backward sums, i.e. what the conv_bwd_data launches of net_backward leave.
+int resident_backward_data(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s) {
+  ResidentState* S = resident_state(h);
+  const int G = std::min(S->grid_max, a->n);
+  ResCall c = res_call(h, feat, a);
+  c.grads = nullptr;
+  c.dw_inside = 0;
+  c.tl = h->d_timeline ? h->d_timeline + 148 * 32 : nullptr;
+  c.bar_base = S->bar_next;
+  S->bar_next += (unsigned)G * (unsigned)(2 * h->blocks.size());
+  for (auto& cv : h->convs) cv.b_gc = 0;              // every layer's sums are published: nobody sums records afterwards
+  return res_launch(h, "resident_bwd_data", resident_bwd_kernel, G, S->smem_b, c, s);
 }
 
 }  // namespace tcr

@@ -28,7 +28,7 @@ def test_emulated_kernels_match_oracle(backend, kw):
     assert report["features"] < 1e-6
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
 def test_emulated_resident_kernels(backend, monkeypatch, mode):
     """TCR_RESIDENT = 0 / 1 / 2: per-layer kernels, resident forward kernel, resident forward + backward kernels
     (tcr_resident.cu; the emulator runs 3 co-resident CTAs, so ownership is ragged: 7 utterances = 3 + 2 + 2)."""

@@ -28,7 +28,7 @@ def test_cuda_path_matches_oracle(backend, kw):
     run_case(backend, **kw)
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
 def test_resident_kernels_match_oracle(backend, monkeypatch, mode):
     """TCR_RESIDENT = 0 / 1 / 2: per-layer kernels, resident forward kernel, resident forward + backward kernels
     (csrc/tcr_resident.cu): every combination meets the same bounds, including the headline shape (4 utterances per SM)."""
