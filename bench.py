@@ -45,6 +45,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of BASELINE.json configs 3 and 5 carried in `extra`")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--frontend", default="auto", choices=["auto", "ordered", "ahead"],
+                    help="ordered: the front-end is ordered on the step's stream; ahead: the timed inputs are resident and final, so it "
+                         "runs on the library's own stream (tcr_step_args::input_resident) and overlaps the previous step's tail; "
+                         "auto = ordered (measured on 1 and 2 GPUs: with resident inputs the early front-end only time-slices with the "
+                         "weight-gradient kernel, 0.363 vs 0.357 ms/step; the host-buffer path always runs it ahead, behind its copy)")
     ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer", "augment"],
                     help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point); "
                          "infer: evaluation-mode forward from wav (config 1 with --batch 1: latency); "
@@ -313,8 +318,11 @@ def run_ours(a):
     losses = torch.zeros(2, device=dev)
     lr, mom, wd = 0.1, 0.9, 1e-3
 
+    frontend_ahead = a.frontend == "ahead"
+
     def step(i):
-        eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i * world + rank, losses=losses)
+        eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i * world + rank, losses=losses,
+                       input_resident=frontend_ahead)
 
     def barrier():
         if world > 1:
@@ -348,6 +356,8 @@ def run_ours(a):
            "data": "synthetic", "impl": "ours",
            "config": make_config(a, world, "none (1 GPU)" if world == 1 else getattr(eng, "exchange", "nccl")),
            "parallelism": f"dp{world}", "final_total_loss": final_loss, "numa": numa,
+           "frontend": ("ordered on the step's stream" if not frontend_ahead else
+                        "runs ahead on the library's stream (tcr_step_args::input_resident: the timed inputs are resident and final)"),
            "gpu_launches": int(launches), "clocks": clocks}
 
     # ---- data-parallel self-check, outside the timed region (the driver's GPU-test box has one GPU and skips tests/test_dist.py):

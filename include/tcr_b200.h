@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TCR_ABI_VERSION 4
+#define TCR_ABI_VERSION 5
 
 enum {
   TCR_OK = 0,
@@ -133,6 +133,12 @@ typedef struct tcr_step_args {
   const struct tcr_augment_clip* clips;   /* [n]: device memory (tcr_train_step) / pinned host memory (tcr_train_step_host) */
   const float* background;   /* device: concatenated background recordings, may be NULL */
   int64_t      pcm_stride;   /* int16 samples per row of `input`; 0 = clip_samples; at most 2 * clip_samples */
+  /* 1: the caller promises that `input` (and `clips`) are final when the call is made, i.e. no work queued on `stream` writes
+   * them.  The front-end (input stage + MFCC) of this step then runs on the library's own low-priority stream into one of two
+   * feature buffers and overlaps the tail of the previous step (weight-gradient tail, update, the cross-GPU arrival barrier);
+   * the rest of the step waits for it on `stream`.  0: everything is ordered on `stream` (the default; zero-initialise).
+   * tcr_train_step_host sets it itself: its inputs arrive on the library's copy stream. */
+  int32_t      input_resident;
 } tcr_step_args;
 
 int         tcr_abi_version(void);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtcr_b200.so")
 
 TCR_MODEL_TCRESNET8 = 8
 TCR_MODEL_TCRESNET14 = 14
-ABI_VERSION = 4          # TCR_ABI_VERSION of include/tcr_b200.h this binding was written against
+ABI_VERSION = 5          # TCR_ABI_VERSION of include/tcr_b200.h this binding was written against
 TCR_INPUT_WAV_F32, TCR_INPUT_FEATURES, TCR_INPUT_WAV_PCM16 = 0, 1, 2
 TCR_FEATURE_MFCC = 0
 TCR_FEATURE_LOG_MEL = 1
@@ -68,7 +68,7 @@ class TcrStepArgs(C.Structure):
         ("learning_rate", C.c_float), ("momentum", C.c_float), ("weight_decay", C.c_float),
         ("dropout_seed", C.c_uint64), ("dropout_mask", C.c_void_p), ("losses", C.c_void_p),
         ("logits", C.c_void_p), ("probs", C.c_void_p), ("grads", C.c_void_p), ("apply_update", C.c_int32),
-        ("clips", C.c_void_p), ("background", C.c_void_p), ("pcm_stride", C.c_int64),
+        ("clips", C.c_void_p), ("background", C.c_void_p), ("pcm_stride", C.c_int64), ("input_resident", C.c_int32),
     ]
 
 

@@ -368,10 +368,12 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
 }
 
 static void hostfeed_destroy(tcr_handle* h);
+static void frontend_ahead_destroy(tcr_handle* h);
 
 extern "C" int tcr_destroy(tcr_handle* h) {
   if (!h) return TCR_OK;
   hostfeed_destroy(h);
+  frontend_ahead_destroy(h);
   resident_destroy(h);
   comm_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
@@ -490,6 +492,7 @@ extern "C" int tcr_forward(tcr_handle* h, const float* input, int32_t input_is_f
     if (input_is_features != TCR_INPUT_WAV_F32 && input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "unknown input kind %d", input_is_features);
     TCR_TRY(mfcc_run(h, input, input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, n, stream));
     feat = h->d_feat;
+    h->feat_last = h->d_feat;
   }
   int rc = net_forward(h, feat, params, moving, n, is_training != 0, dropout_seed, dropout_mask, onehot, weight_decay,
                        logits, probs, losses, /*backward=*/false, s);
@@ -509,30 +512,96 @@ extern "C" int tcr_eval_accumulate(tcr_handle* h, const float* scores, const flo
   return TCR_OK;
 }
 
-extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream stream) {
+// Front-end running ahead (tcr_step_args::input_resident): lazily created low-priority stream, second feature buffer, events.
+static int frontend_ahead_get(tcr_handle* h) {
+  if (h->fe_stream) return TCR_OK;
+#ifndef TCR_EMU
+  int lo = 0, hi = 0;
+  TCR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = numerically greatest = lowest priority
+  cudaStream_t st = nullptr;
+  TCR_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo));
+  for (int b = 0; b < 2; ++b) {      // its own two feature buffers: h->d_feat stays with the calls that are ordered on their stream
+    void* p = nullptr;
+    TCR_CUDA(cudaMalloc(&p, (size_t)h->cfg.max_batch * h->frames * h->features * sizeof(float)));
+    h->allocs.push_back(p);
+    h->workspace_bytes += (int64_t)h->cfg.max_batch * h->frames * h->features * (int64_t)sizeof(float);
+    h->fe_feat[b] = (float*)p;
+  }
+  for (int b = 0; b < 2; ++b) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TCR_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    TCR_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    h->fe_ready[b] = e0;
+    h->fe_free[b] = e1;
+  }
+  h->fe_stream = st;
+#endif
+  return TCR_OK;
+}
+static void frontend_ahead_destroy(tcr_handle* h) {
+#ifndef TCR_EMU
+  if (!h->fe_stream) return;
+  cudaStreamSynchronize((cudaStream_t)h->fe_stream);
+  for (int b = 0; b < 2; ++b) {
+    if (h->fe_ready[b]) cudaEventDestroy((cudaEvent_t)h->fe_ready[b]);
+    if (h->fe_free[b]) cudaEventDestroy((cudaEvent_t)h->fe_free[b]);
+  }
+  cudaStreamDestroy((cudaStream_t)h->fe_stream);
+  h->fe_stream = nullptr;
+#else
+  (void)h;
+#endif
+}
+
+// input_event: what the front-end has to wait for when it runs ahead (the host feed's H2D copy), or null
+static int train_step_impl(tcr_handle* h, const tcr_step_args* a, tcr_stream stream, void* input_event) {
   pdl_chain_reset();
   if (!h || !a || !a->input || !a->onehot || !a->params) return fail(TCR_ERR_INVALID, "NULL argument");
   if (a->apply_update && (!a->slots || !a->moving)) return fail(TCR_ERR_INVALID, "apply_update needs slots and moving");
   TCR_TRY(check_n(h, a->n));
   cudaStream_t s = (cudaStream_t)stream;
   const float* feat = a->input;
+  int fe_buf = -1;                   // feature buffer of a front-end that ran ahead
   if (a->input_is_features != TCR_INPUT_FEATURES) {
     if (a->input_is_features != TCR_INPUT_WAV_F32 && a->input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "unknown input kind %d", a->input_is_features);
+    tcr_stream fs = stream;          // stream of the front-end kernels
+    float* featbuf = h->d_feat;
+#ifndef TCR_EMU
+    if (a->input_resident) {
+      TCR_TRY(frontend_ahead_get(h));
+      fe_buf = (int)(h->fe_count++ & 1);
+      cudaStream_t f = (cudaStream_t)h->fe_stream;
+      if (input_event) TCR_CUDA(cudaStreamWaitEvent(f, (cudaEvent_t)input_event, 0));
+      if (h->fe_count > 2) TCR_CUDA(cudaStreamWaitEvent(f, (cudaEvent_t)h->fe_free[fe_buf], 0));   // the step two calls back has read it
+      fs = (tcr_stream)f;
+      featbuf = h->fe_feat[fe_buf];
+    }
+#endif
+    h->feat_last = featbuf;
     if (a->clips) {                  // device input stage first: int16 clips + per-clip draws -> fp32 wav (tcr_augment.cu)
       if (a->input_is_features != TCR_INPUT_WAV_PCM16) return fail(TCR_ERR_INVALID, "clips need TCR_INPUT_WAV_PCM16 input");
       const int64_t stride = a->pcm_stride > 0 ? a->pcm_stride : h->cfg.clip_samples;
-      if (!h->d_aug) {
+      float*& aug = fe_buf >= 0 ? h->fe_aug : h->d_aug;       // the ahead path decodes into its own buffer
+      if (!aug) {
         void* p = nullptr;
         TCR_CUDA(cudaMalloc(&p, (size_t)h->cfg.max_batch * h->cfg.clip_samples * sizeof(float)));
         h->allocs.push_back(p);
-        h->d_aug = (float*)p;
+        aug = (float*)p;
       }
-      augment_launch((const int16_t*)a->input, stride, a->clips, a->background, h->background_samples, h->d_aug, h->cfg.clip_samples, a->n, s);
-      TCR_TRY(mfcc_run(h, h->d_aug, 0, h->d_feat, a->n, stream));
+      augment_launch((const int16_t*)a->input, stride, a->clips, a->background, h->background_samples, aug, h->cfg.clip_samples, a->n,
+                     (cudaStream_t)fs);
+      TCR_TRY(mfcc_run(h, aug, 0, featbuf, a->n, fs));
     } else {
-      TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, h->d_feat, a->n, stream));
+      TCR_TRY(mfcc_run(h, a->input, a->input_is_features == TCR_INPUT_WAV_PCM16, featbuf, a->n, fs));
     }
-    feat = h->d_feat;
+    feat = featbuf;
+#ifndef TCR_EMU
+    if (fe_buf >= 0) {
+      TCR_CUDA(cudaEventRecord((cudaEvent_t)h->fe_ready[fe_buf], (cudaStream_t)h->fe_stream));
+      TCR_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)h->fe_ready[fe_buf], 0));
+      pdl_chain_reset();             // the next launch is the first one of this call on `stream`
+    }
+#endif
   }
   const int resident = resident_mode(h);
   if (resident < 1) net_weight_transpose(h, a->params, s);      // the resident forward kernel writes the transposed banks itself
@@ -551,9 +620,14 @@ extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream 
   rc = net_update(h, feat, a, s);
   if (rc) return fail(rc, "update launch failed: %s", g_err);
   TCR_CUDA(cudaGetLastError());
+#ifndef TCR_EMU
+  if (fe_buf >= 0) TCR_CUDA(cudaEventRecord((cudaEvent_t)h->fe_free[fe_buf], s));
+#endif
   h->last_n = a->n;
   return TCR_OK;
 }
+
+extern "C" int tcr_train_step(tcr_handle* h, const tcr_step_args* a, tcr_stream stream) { return train_step_impl(h, a, stream, nullptr); }
 
 // ------------------------------------------------------------------------------------------------
 // Host-buffer training step: the `feed_dict` / input-pipeline side of session.run(train_op)
@@ -650,13 +724,14 @@ extern "C" int tcr_train_step_host(tcr_handle* h, const tcr_step_args* a, int32_
   TCR_CUDA(cudaMemcpyAsync(sl.d_hot, a->onehot, (size_t)a->n * h->cfg.num_classes * 4, cudaMemcpyHostToDevice, f->copy));
   if (a->clips) TCR_CUDA(cudaMemcpyAsync(sl.d_clips, a->clips, (size_t)a->n * sizeof(tcr_augment_clip), cudaMemcpyHostToDevice, f->copy));
   TCR_CUDA(cudaEventRecord(sl.ready, f->copy));
-  TCR_CUDA(cudaStreamWaitEvent(s, sl.ready, 0));
+  TCR_CUDA(cudaStreamWaitEvent(s, sl.ready, 0));                   // labels (and features) for the step proper
   tcr_step_args d = *a;
   d.input = (const float*)sl.d_in;
   d.onehot = sl.d_hot;
   d.losses = sl.d_loss;
   if (a->clips) d.clips = sl.d_clips;          // the draws travel with the batch; the background bank is already on the device
-  TCR_TRY(tcr_train_step(h, &d, stream));
+  d.input_resident = 1;                        // the front-end waits for the copy only, not for the previous step on `stream`
+  TCR_TRY(train_step_impl(h, &d, stream, sl.ready));
   TCR_CUDA(cudaEventRecord(sl.consumed, s));
   TCR_CUDA(cudaMemcpyAsync(sl.h_loss, sl.d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   TCR_CUDA(cudaEventRecord(sl.done, s));
@@ -683,7 +758,7 @@ extern "C" int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr
     return TCR_OK;
   };
   if (s == "timeline" && h->d_timeline) return ret((float*)h->d_timeline, 2 * 16 * 8192);   // int64 viewed as float pairs
-  if (s == "features") return ret(h->d_feat, n * h->frames * h->features);
+  if (s == "features") return ret(h->feat_last ? h->feat_last : h->d_feat, n * h->frames * h->features);
   if (s == "grads") return ret(h->p2p.attached && h->world > 1 ? h->p2p.grads + (size_t)(h->p2p.step & 1u) * h->n_train : h->d_grads, h->n_train);
   if (s == "logits") return ret(h->d_logits, n * h->cfg.num_classes);
   if (s == "probs") return ret(h->d_probs, n * h->cfg.num_classes);

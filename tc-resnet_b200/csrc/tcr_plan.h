@@ -57,6 +57,12 @@ struct tcr_handle {
   float* d_dct = nullptr;
   // workspace
   float* d_feat = nullptr;
+  // front-end running ahead on its own stream (tcr_step_args::input_resident, tcr_train_step_host): two feature buffers, the
+  // events "features of buffer b are ready" / "the step that read buffer b has finished"
+  void* fe_stream = nullptr; float* fe_feat[2] = {nullptr, nullptr}; void* fe_ready[2] = {nullptr, nullptr};
+  void* fe_free[2] = {nullptr, nullptr}; long long fe_count = 0;
+  float* fe_aug = nullptr;           // the ahead path's own decoded-wav buffer (device input stage)
+  float* feat_last = nullptr;        // feature buffer the library filled last ("features" of tcr_workspace_tensor)
   float* d_logits = nullptr; float* d_probs = nullptr;
   float* d_loss_part = nullptr; float* d_loss = nullptr; float* d_dwfc_part = nullptr;
   float* d_grads = nullptr;

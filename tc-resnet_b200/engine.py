@@ -191,9 +191,11 @@ class Engine:
                    dropout_seed: int = 0, dropout_mask: Optional[torch.Tensor] = None, input_is_features: bool = False,
                    want_outputs: bool = False, want_grads: bool = False, apply_update: bool = True,
                    losses: Optional[torch.Tensor] = None, clips: Optional[torch.Tensor] = None,
-                   background: Optional[torch.Tensor] = None):
+                   background: Optional[torch.Tensor] = None, input_resident: bool = False):
         """clips (uint8 CUDA tensor of n packed tcr_augment_clip records) + int16 `inputs` [n, stride]: the step starts with
-        the device input stage (decode, shift, background mix, clip) instead of taking decoded fp32 samples."""
+        the device input stage (decode, shift, background mix, clip) instead of taking decoded fp32 samples.
+        input_resident=True: `inputs` is final when the call is made (nothing queued on the current stream writes it); the
+        front-end then runs ahead on the library's own stream and overlaps the previous step's tail (tcr_step_args::input_resident)."""
         n = inputs.shape[0]
         a = L.TcrStepArgs()
         if clips is not None:
@@ -216,6 +218,7 @@ class Engine:
             out["grads"] = self._f32(self.num_trainable)
             a.grads = self._ptr(out["grads"])
         a.apply_update = int(apply_update)
+        a.input_resident = int(bool(input_resident))
         L.check(self.lib, self.lib.tcr_train_step(self._h, C.byref(a), self._stream), "tcr_train_step")
         return out
 

@@ -235,3 +235,26 @@ def test_handles_of_different_size_share_the_resident_kernels(backend):
     l1 = float(big.train_step(wav, hot, p.clone(), s.clone(), m.clone(), 0.1)["losses"][0])             # launch still fits
     assert l0 == l1
     small.close(); big.close()
+
+
+def test_frontend_running_ahead_is_bitwise_equal(backend):
+    """tcr_step_args::input_resident lets the front-end of a step run on the library's own stream, ahead of the previous step's tail.
+    Same inputs, same seeds -> the same bits as the fully ordered steps, over rotating input buffers and both feature buffers."""
+    import torch
+    from tcresnet_b200.engine import Engine
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    wavs = [torch.rand(96, 16000, device="cuda", generator=gen) * 2 - 1 for _ in range(3)]
+    hots = [torch.nn.functional.one_hot(torch.randint(0, 12, (96,), device="cuda", generator=gen), 12).float() for _ in range(3)]
+    results = []
+    for ahead in (False, True):
+        eng = Engine(max_batch=96, dropout_keep_prob=0.5)
+        p, s, m = eng.new_variables(seed=0)
+        losses = []
+        for i in range(7):
+            out = eng.train_step(wavs[i % 3], hots[i % 3], p, s, m, 0.05, dropout_seed=i, input_resident=ahead)
+            losses.append(out["losses"].clone())
+        torch.cuda.synchronize()
+        results.append((p.clone(), s.clone(), m.clone(), torch.stack(losses)))
+        eng.close()
+    for x, y in zip(*results):
+        assert torch.equal(x, y)
