@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_fwd_kernel(const __gr
   const int u0 = cta * ubase + imin(cta, urem), Ue = ubase + (cta < urem ? 1 : 0);
   unsigned wpar = 0;
   unsigned target = c.bar_base;
-  if (tid == 0) mbar_init(wbar, 1);
+  uint64_t* fbar = wbar + 1;                                     // second half of the reserved 16 bytes: the feature tile's barrier
+  if (tid == 0) { mbar_init(wbar, 1); mbar_init(fbar, 1); }
   __syncthreads();
   float* tblr = smem + P.o_tbl;
   float* red = smem + P.o_red;
@@ -543,9 +544,15 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_fwd_kernel(const __gr
   const int nb = P.nblocks, nph = 1 + 2 * nb;
   res_stamp(c, 0);
   res_load_bank(smem + P.o_w, c.params + P.conv[0].w_off, (unsigned)(P.conv[0].k * P.conv[0].cin * P.conv[0].cout), nullptr, 0u, wbar);
-  {                                   // conv0's input: the raw features of this CTA's utterances
-    const RConv& L0 = P.conv[0];
-    res_stage(c.feat + (size_t)u0 * L0.t_in * L0.cin, nullptr, smem + bufo[0], Ue, L0.t_in, L0.cin, L0.pad_left + L0.t_in + L0.pad_right,
+  {                                   // conv0's input: the T x F feature tiles of this CTA's utterances are one contiguous span:
+    const RConv& L0 = P.conv[0];      // one TMA bulk copy into the (still idle) output-plane region, then the padded tile is formed from it
+    const unsigned fbytes = (unsigned)(Ue * L0.t_in * L0.cin) * 4u;
+    if (tid == 0) {
+      mbar_expect_tx(fbar, fbytes);
+      tma_load_1d(ys, c.feat + (size_t)u0 * L0.t_in * L0.cin, fbytes, fbar);
+    }
+    mbar_wait(fbar, 0u);
+    res_stage(ys, nullptr, smem + bufo[0], Ue, L0.t_in, L0.cin, L0.pad_left + L0.t_in + L0.pad_right,
               chan_stride(L0.cin), L0.pad_left, L0.pad_right);
   }
   __syncthreads();
@@ -1273,6 +1280,7 @@ static ResidentState* resident_state(tcr_handle* h) {
     plane_max = std::max(plane_max, P.conv[l].ks * umax * cv.t_out * cv.cout);
     if (dn) sh_max = std::max(sh_max, umax * dn->t_out * dn->cout);
   }
+  plane_max = std::max(plane_max, umax * h->convs[0].t_in * h->convs[0].cin);      // the raw feature tiles land there first (TMA)
   // ping-pong of the two tile buffers (see the kernel): conv0's input in buf0, block input X in buf[p], x_a and the block
   // output in buf[1 - p], p flips per block
   int bufsz[2] = {tile_floats(h->convs[0]), 0};
