@@ -188,6 +188,7 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.features = h->features;
   a.mel_bins = h->cfg.num_mel_bins;
   a.fpb = h->fpb;
+  a.warps = h->fwarps;
   a.magnitude = h->cfg.feature_kind == TCR_FEATURE_LOG_MEL;
   a.use_dct = h->cfg.feature_kind == TCR_FEATURE_MFCC;
   a.consts = h->d_fe_consts;
@@ -356,6 +357,13 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
       }
     }
     h->fpb = std::min(best, h->frames);
+  }
+  h->fwarps = std::min(h->fpb, 7);
+  if (const char* e = getenv("TCR_MFCC_FPB")) {                  // tuning knob: frames per CTA[,warps per CTA]
+    int f = 0, w = 0;
+    const int got = sscanf(e, "%d,%d", &f, &w);
+    if (got >= 1 && f >= 1) { h->fpb = std::min(f, h->frames); h->fwarps = std::min(h->fpb, 7); }
+    if (got >= 2 && w >= 1) h->fwarps = std::min(std::min(w, 7), h->fpb);
   }
   int rc = build_frontend_tables(h);
   if (rc) return bail(rc);

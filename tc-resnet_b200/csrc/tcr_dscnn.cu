@@ -1312,7 +1312,7 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
     cur ^= 1;
   }
   const DsLayerDev& last = d->net.layer[d->net.nlayers - 1];
-  if (last.cout > 256) { set_error("DS-CNN head supports up to 256 channels"); return TCR_ERR_UNSUPPORTED; }
+  if (last.cout > 320) { set_error("DS-CNN head supports up to 320 channels"); return TCR_ERR_UNSUPPORTED; }
   TCR_LAUNCH("dscnn_head", dscnn_head_kernel, dim3(n), dim3(256), 0, s, last.hout * last.wout, last.cout, d->net.classes, d->net.fcw,
              d->net.fcb, params, in, logits, probs);
   if (cudaGetLastError() != cudaSuccess) { set_error("DS-CNN launch failed"); return TCR_ERR_CUDA; }

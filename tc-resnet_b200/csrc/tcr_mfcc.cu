@@ -353,7 +353,7 @@ size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps) {
 
 int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream) {
   const int nf2 = fft_length / 2;
-  const int warps = a.fpb;
+  const int warps = a.warps;
   dim3 grid((a.frames + a.fpb - 1) / a.fpb, n, 1);
   dim3 block(32 * warps, 1, 1);
   const size_t smem = mfcc_smem_bytes(a, nf2, warps);

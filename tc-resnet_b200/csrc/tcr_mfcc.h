@@ -9,7 +9,8 @@ struct MfccArgs {
   int pcm16;
   float* feat;              // [N, frames, features]
   int clip, window, stride, frames, features, mel_bins;
-  int fpb;                  // frames per CTA (== warps per CTA)
+  int fpb;                  // frames per CTA
+  int warps;                // warps per CTA (<= 7): a warp takes frames warp, warp + warps, ... of the CTA's chunk
   int magnitude;            // 0: power spectrogram (MFCC path), 1: magnitude (log-mel path)
   int use_dct;              // 1: MFCC, 0: log-mel output
   // constant block (offsets in floats, each section 16-byte aligned); the first c_smem floats are staged in shared memory by

@@ -42,7 +42,7 @@ struct BlockPlan {
 
 struct tcr_handle {
   tcr_config cfg;
-  int frames = 0, features = 0, fft = 0, fpb = 1;
+  int frames = 0, features = 0, fft = 0, fpb = 1, fwarps = 1;
   std::string scope;
   std::vector<tcr::ConvPlan> convs;
   std::vector<tcr::BlockPlan> blocks;
