@@ -512,14 +512,24 @@ __device__ __forceinline__ void res_run_conv(float* smem, const ResProgram& P, c
 // Transposed filter banks wT[k][co][ci] for the backward-data pass (what weight_transpose_kernel writes), spread over the CTAs and
 // run in the shadow of the first grid barrier: nobody waits for it before the kernel ends.
 __device__ __noinline__ void res_weight_transpose(const ResProgram& P, const float* __restrict__ params, int cta, int G) {
-  for (int l = 1; l < P.nconvs; ++l) {
-    const RConv& L = P.conv[l];
-    const int numel = L.k * L.cin * L.cout;
-    float* wT = const_cast<float*>(L.wT);
-    for (int i = cta * kResThreads + (int)threadIdx.x; i < numel; i += G * kResThreads) {
-      const int ci = i % L.cin, r = i / L.cin, co = r % L.cout, k = r / L.cout;
-      wT[i] = __ldg(params + L.w_off + ((long long)k * L.cin + ci) * L.cout + co);
+  // one flat index space over all banks, an equal slice per CTA (a per-layer split left the low CTAs with nine dependent
+  // round trips and made them the stragglers of the next barrier)
+  int total = 0;
+  for (int l = 1; l < P.nconvs; ++l) total += P.conv[l].k * P.conv[l].cin * P.conv[l].cout;
+  const int per = (total + G - 1) / G;
+  const int lo = cta * per, hi = imin(total, lo + per);
+  for (int p = lo + (int)threadIdx.x; p < hi; p += kResThreads) {
+    int l = 1, base = 0;
+    for (;;) {
+      const int numel = P.conv[l].k * P.conv[l].cin * P.conv[l].cout;
+      if (p < base + numel) break;
+      base += numel;
+      ++l;
     }
+    const RConv& L = P.conv[l];
+    const int i = p - base;
+    const int ci = i % L.cin, r = i / L.cin, co = r % L.cout, k = r / L.cout;
+    const_cast<float*>(L.wT)[i] = __ldg(params + L.w_off + ((long long)k * L.cin + ci) * L.cout + co);
   }
 }
 
@@ -973,8 +983,15 @@ __global__ void __launch_bounds__(kResThreads, 1) resident_bwd_kernel(const __gr
   int gi_b = 0, gi_a = 1, gi_n = 2;  // regions holding gblk (block-level gradient), g_a, and the gradient being produced
   res_stamp(c, 0);
   // every layer's BN table (published by the forward pass) stays in shared memory for the whole kernel
-  for (int l = 0; l < P.nconvs; ++l)
-    for (int i = tid; i < 4 * P.conv[l].cout; i += kResThreads) tblr[P.conv[l].tbl + i] = __ldcg(P.conv[l].bnf + i);
+  {                                   // one flat pass over all layers' entries (tbl offsets are cumulative): a single round trip
+    const RConv& Ll = P.conv[P.nconvs - 1];
+    const int total = Ll.tbl + 4 * Ll.cout;
+    for (int i = tid; i < total; i += kResThreads) {
+      int l = 0;
+      while (l + 1 < P.nconvs && i >= P.conv[l + 1].tbl) ++l;
+      tblr[i] = __ldcg(P.conv[l].bnf + (i - P.conv[l].tbl));
+    }
+  }
   // inputs of the first phase (conv_b of the last block): bank, gradient at the block output, y_b, y_a
   {
     const RBlock& B = P.blk[nb - 1];
