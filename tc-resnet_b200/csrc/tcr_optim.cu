@@ -42,14 +42,23 @@ __device__ __forceinline__ void grad_finalize_body(const GradArgs& a, const int 
     const float* part = si == fc_seg ? fc_part : sg.part;
     const int R = si == fc_seg ? fc_R : sg.R;
     float g = 0.f;
-    if (part) {                      // 8 independent loads in flight, fixed summation order (deterministic)
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int r = 0;
-      for (; r + 8 <= R; r += 8) {
+    if (part) {                      // fixed summation order (deterministic); many loads in flight: the fc partials come one per
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // CTA of the resident forward kernel (148 records), and a
+      int r = 0;                                                    // dependent round trip per 8 records made them the kernel's tail
+      for (; r + 32 <= R; r += 32) {
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += part[(size_t)(r + j) * sg.numel + i];
+        for (int j = 0; j < 32; ++j) v[j] = part[(size_t)(r + j) * sg.numel + i];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j & 7] += v[j];
       }
-      for (; r < R; ++r) acc[0] += part[(size_t)r * sg.numel + i];
+      for (; r < R; r += 8) {        // last (partial) batches: predicated, still independent loads
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = r + j < R ? part[(size_t)(r + j) * sg.numel + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
       g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     }
     if (sg.decay) {
