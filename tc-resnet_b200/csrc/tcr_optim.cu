@@ -171,19 +171,25 @@ __global__ void __launch_bounds__(kOptThreads) update_kernel(UpdateArgs a) {
       }
     }
   } else if (extra == a.nmsegs && a.losses) {
-    __shared__ double s_l2[kOptThreads];
-    double l2 = 0.0;
+    // every record is loaded by its own thread (one round trip), the two fixed-order sums run on two warps side by side
+    __shared__ double s_l2[kOptThreads], s_ce[kOptThreads], s_tot[2];
+    double l2 = 0.0, cs = 0.0;
     for (int i = threadIdx.x; i < a.l2blocks; i += kOptThreads) l2 += (double)a.l2part[i];
+    for (int i = threadIdx.x; i < a.ce_count; i += kOptThreads) cs += (double)a.ce_sum[i];   // records of the head, <= 256: one per thread
     s_l2[threadIdx.x] = l2;
+    s_ce[threadIdx.x] = cs;
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+      const double* src = threadIdx.x == 0 ? s_l2 : s_ce;
+      double tot = 0.0;
+      for (int i = 0; i < kOptThreads; ++i) tot += src[i];
+      s_tot[threadIdx.x >> 5] = tot;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int i = 0; i < kOptThreads; ++i) tot += s_l2[i];
-      double ce = 0.0;
-      for (int i = 0; i < a.ce_count; ++i) ce += (double)a.ce_sum[i];      // per-cluster records of the head launch, fixed order
-      const float model = (float)ce * a.inv_n;
+      const float model = (float)s_tot[1] * a.inv_n;
       a.losses[1] = model;
-      a.losses[0] = model + a.weight_decay * (float)(0.5 * tot);
+      a.losses[0] = model + a.weight_decay * (float)(0.5 * s_tot[0]);
     }
   }
 }
