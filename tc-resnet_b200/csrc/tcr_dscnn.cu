@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) dscnn_conv_kernel(DsLayerDev L, const flo
 
 // ---- depthwise-separable block, one CTA per (utterance, chunk of RH output rows) ----
 constexpr int kDsTM = 4;
-__global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH, const float* __restrict__ params,
+__global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH, int COT, const float* __restrict__ params,
                                                             const float* __restrict__ in, float* __restrict__ out, float eps) {
   pdl_wait();
   TCR_DYNAMIC_SMEM(smem_raw);
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH
   const int wp = (L.wout - 1) * L.sw + L.kw;                     // padded width
   float* xs = smem;                                              // [hin_t][wp][C]
   float* ds = xs + (size_t)hin_t * wp * C;                       // [RH*wout][C]  depthwise output
-  float* pws = ds + (size_t)RH * L.wout * C;                     // [C][CO]       pointwise weights
-  float* dws = pws + (size_t)C * CO;                             // [kh*kw][C]    depthwise weights
+  float* pws = ds + (size_t)RH * L.wout * C;                     // [C][COT]      pointwise weights, a tile of COT output channels
+  float* dws = pws + (size_t)C * COT;                            // [kh*kw][C]    depthwise weights   (COT = CO unless the bank exceeds shared memory: DS-CNN-L)
   float* sc1 = dws + L.kh * L.kw * C;                            // folded BN of the depthwise stage
   float* sf1 = sc1 + C;
   float* sc2 = sf1 + C;                                          // folded BN of the pointwise stage
@@ -117,7 +117,14 @@ __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH
       }
     }
   }
-  for (int i = tid; i < C * CO / 4; i += blockDim.x) st4(pws + 4 * i, ldg4(params + L.pw + 4 * i));
+  auto load_slice = [&](int co0, int cot) {                      // pw[ci][co0 .. co0 + cot) -> pws[ci][COT]
+    const int q4 = cot >> 2;
+    for (int i = tid; i < C * q4; i += blockDim.x) {
+      const int ci = i / q4, q = i - ci * q4;
+      st4(pws + (size_t)ci * COT + 4 * q, ldg4(params + L.pw + (size_t)ci * CO + co0 + 4 * q));
+    }
+  };
+  load_slice(0, imin(COT, CO));
   for (int i = tid; i < L.kh * L.kw * C / 4; i += blockDim.x) st4(dws + 4 * i, ldg4(params + L.w + 4 * i));
   for (int c = tid; c < C; c += blockDim.x) fold_bn(params, L.b, L.beta, L.mm, L.mv, c, eps, sc1, sf1);
   for (int c = tid; c < CO; c += blockDim.x) fold_bn(params, L.pb, L.pbeta, L.pmm, L.pmv, c, eps, sc2, sf2);
@@ -147,38 +154,46 @@ __global__ void __launch_bounds__(256) dscnn_dsblock_kernel(DsLayerDev L, int RH
     }
   }
   __syncthreads();
-  // pointwise: tasks of kDsTM positions x 4 output channels, positions of a task are NRT apart
-  const int ncg = CO >> 2, NRT = (npos + kDsTM - 1) / kDsTM;
+  // pointwise: tasks of kDsTM positions x 4 output channels, positions of a task are NRT apart; one pass per tile of COT channels
+  const int NRT = (npos + kDsTM - 1) / kDsTM;
   const size_t gbase = ((size_t)n * L.hout + h0) * L.wout;
-  for (int task = tid; task < NRT * ncg; task += blockDim.x) {
-    const int cg = task % ncg, rt = task / ncg;
-    const float* xr[kDsTM];
+  for (int co0 = 0; co0 < CO; co0 += COT) {
+    const int cot = imin(COT, CO - co0), ncg = cot >> 2;
+    if (co0 > 0) {
+      __syncthreads();                                           // everybody is done with the previous slice
+      load_slice(co0, cot);
+      __syncthreads();
+    }
+    for (int task = tid; task < NRT * ncg; task += blockDim.x) {
+      const int cg = task % ncg, rt = task / ncg;
+      const float* xr[kDsTM];
 #pragma unroll
-    for (int i = 0; i < kDsTM; ++i) xr[i] = ds + (size_t)imin(rt + i * NRT, npos - 1) * C;
-    float4 acc[kDsTM];
+      for (int i = 0; i < kDsTM; ++i) xr[i] = ds + (size_t)imin(rt + i * NRT, npos - 1) * C;
+      float4 acc[kDsTM];
 #pragma unroll
-    for (int i = 0; i < kDsTM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* wk = pws + 4 * cg;
+      for (int i = 0; i < kDsTM; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* wk = pws + 4 * cg;
 #pragma unroll 2
-    for (int ci = 0; ci < C; ci += 4) {
-      const float4 w0 = ld4(wk + (ci + 0) * CO), w1 = ld4(wk + (ci + 1) * CO), w2 = ld4(wk + (ci + 2) * CO), w3 = ld4(wk + (ci + 3) * CO);
+      for (int ci = 0; ci < C; ci += 4) {
+        const float4 w0 = ld4(wk + (ci + 0) * COT), w1 = ld4(wk + (ci + 1) * COT), w2 = ld4(wk + (ci + 2) * COT), w3 = ld4(wk + (ci + 3) * COT);
+#pragma unroll
+        for (int i = 0; i < kDsTM; ++i) {
+          const float4 x = ld4(xr[i] + ci);
+          acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y); acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
+          acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y); acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
+          acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y); acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
+          acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y); acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+        }
+      }
+      const float4 s = ld4(sc2 + co0 + 4 * cg), t = ld4(sf2 + co0 + 4 * cg);
 #pragma unroll
       for (int i = 0; i < kDsTM; ++i) {
-        const float4 x = ld4(xr[i] + ci);
-        acc[i].x = fmaf(x.x, w0.x, acc[i].x); acc[i].y = fmaf(x.x, w0.y, acc[i].y); acc[i].z = fmaf(x.x, w0.z, acc[i].z); acc[i].w = fmaf(x.x, w0.w, acc[i].w);
-        acc[i].x = fmaf(x.y, w1.x, acc[i].x); acc[i].y = fmaf(x.y, w1.y, acc[i].y); acc[i].z = fmaf(x.y, w1.z, acc[i].z); acc[i].w = fmaf(x.y, w1.w, acc[i].w);
-        acc[i].x = fmaf(x.z, w2.x, acc[i].x); acc[i].y = fmaf(x.z, w2.y, acc[i].y); acc[i].z = fmaf(x.z, w2.z, acc[i].z); acc[i].w = fmaf(x.z, w2.w, acc[i].w);
-        acc[i].x = fmaf(x.w, w3.x, acc[i].x); acc[i].y = fmaf(x.w, w3.y, acc[i].y); acc[i].z = fmaf(x.w, w3.z, acc[i].z); acc[i].w = fmaf(x.w, w3.w, acc[i].w);
+        const int pos = rt + i * NRT;
+        if (pos < npos)
+          st4(out + (gbase + pos) * CO + co0 + 4 * cg,
+              make_float4(fmaxf(fmaf(acc[i].x, s.x, t.x), 0.f), fmaxf(fmaf(acc[i].y, s.y, t.y), 0.f),
+                          fmaxf(fmaf(acc[i].z, s.z, t.z), 0.f), fmaxf(fmaf(acc[i].w, s.w, t.w), 0.f)));
       }
-    }
-    const float4 s = ld4(sc2 + 4 * cg), t = ld4(sf2 + 4 * cg);
-#pragma unroll
-    for (int i = 0; i < kDsTM; ++i) {
-      const int pos = rt + i * NRT;
-      if (pos < npos)
-        st4(out + (gbase + pos) * CO + 4 * cg,
-            make_float4(fmaxf(fmaf(acc[i].x, s.x, t.x), 0.f), fmaxf(fmaf(acc[i].y, s.y, t.y), 0.f),
-                        fmaxf(fmaf(acc[i].z, s.z, t.z), 0.f), fmaxf(fmaf(acc[i].w, s.w, t.w), 0.f)));
     }
   }
 }
@@ -1009,10 +1024,10 @@ __global__ void __launch_bounds__(256) dscnn_head_kernel(int npos, int C, int cl
     }
   }
   __syncthreads();
-  if (tid < C) {
+  for (int c = tid; c < C; c += blockDim.x) {
     float tot = 0.f;
-    for (int q = 0; q < nseg; ++q) tot += s_red[q * C + tid];
-    s_pool[tid] = tot / (float)npos;
+    for (int q = 0; q < nseg; ++q) tot += s_red[q * C + c];
+    s_pool[c] = tot / (float)npos;
   }
   __syncthreads();
   if (tid < classes) {
@@ -1250,9 +1265,9 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
 #endif
       TCR_LAUNCH("dscnn_conv", kfn, dim3(n), dim3(256), smem, s, L, params, in, out, eps);
     } else {
-      auto smem_for = [&](int RH) {
+      auto smem_for = [&](int RH, int COT) {
         const int hin_t = (RH - 1) * L.sh + L.kh, wp = (L.wout - 1) * L.sw + L.kw;
-        return (size_t)((size_t)hin_t * wp * L.cin + (size_t)RH * L.wout * L.cin + (size_t)L.cin * L.cout + L.kh * L.kw * L.cin +
+        return (size_t)((size_t)hin_t * wp * L.cin + (size_t)RH * L.wout * L.cin + (size_t)L.cin * COT + L.kh * L.kw * L.cin +
                         2 * L.cin + 2 * L.cout) * 4;
       };
 #ifndef TCR_EMU
@@ -1297,16 +1312,20 @@ extern "C" int tcr_dscnn_forward(tcr_dscnn* d, const float* features, const floa
         }
       }
 #endif
+      // the whole pointwise bank in shared memory when it fits next to a useful tile; else (DS-CNN-L: 276 x 276 fp32 = 305 KB) output-
+      // channel tiles of COT, the depthwise output of the tile being reused for every slice
+      int COT = L.cout;
+      while (COT > 32 && smem_for(1, COT) > 96 * 1024) COT = ((COT / 2) + 3) & ~3;
       int RH = std::min(L.hout, 8);
-      while (RH > 1 && smem_for(RH) > 100 * 1024) --RH;
-      const size_t smem = smem_for(RH);
+      while (RH > 1 && smem_for(RH, COT) > 100 * 1024) --RH;
+      const size_t smem = smem_for(RH, COT);
       if (smem > 200 * 1024) { set_error("DS-CNN layer does not fit in shared memory"); return TCR_ERR_UNSUPPORTED; }
       auto kfn = dscnn_dsblock_kernel;
 #ifndef TCR_EMU
       static SmemOptIn optin;
       if (optin.ensure(kfn, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
-      TCR_LAUNCH("dscnn_dsblock", kfn, dim3((L.hout + RH - 1) / RH, n), dim3(256), smem, s, L, RH, params, in, out, eps);
+      TCR_LAUNCH("dscnn_dsblock", kfn, dim3((L.hout + RH - 1) / RH, n), dim3(256), smem, s, L, RH, COT, params, in, out, eps);
     }
     in = out;
     cur ^= 1;

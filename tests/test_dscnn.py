@@ -78,10 +78,11 @@ def test_emulated_dscnn_matches_oracle():
     assert _run(b, "S", 49, 40, 2) < 1e-5
     assert _run(b, "S", 49, 10, 1) < 1e-5                 # the reference's DS-CNN recipes use 10 MFCCs
     assert _run(b, "M", 49, 10, 1) < 1e-5                 # 172 channels, strided depthwise
+    assert _run(b, "L", 49, 10, 1) < 1e-5                 # 276 channels: the pointwise bank is walked in output-channel tiles
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("size,h,w,n", [("S", 49, 40, 512), ("S", 49, 10, 39), ("M", 49, 10, 33)])
+@pytest.mark.parametrize("size,h,w,n", [("S", 49, 40, 512), ("S", 49, 10, 39), ("M", 49, 10, 33), ("L", 49, 10, 17)])
 def test_cuda_dscnn_matches_oracle(size, h, w, n):
     from tcr_harness import TorchBackend
     assert _run(TorchBackend(), size, h, w, n) < 1e-5
