@@ -236,6 +236,12 @@ int tcr_workspace_tensor(tcr_handle* h, const char* name, float** ptr, int64_t* 
  * (128 bytes, ncclUniqueId) is created on rank 0 and distributed by the host (torch.distributed). */
 int tcr_comm_unique_id(void* id128);
 int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int32_t world_size);
+/* Parity-test flag: BatchNorm batch statistics (forward) and BatchNorm-backward sums over the GLOBAL batch of all
+ * ranks = the reference's single-device batch of world * n.  One NCCL all-reduce of 2*C floats per BN layer, forward and backward;
+ * the step then runs on the per-layer kernels.  Not a production path: the default is local (per-replica) statistics.  No
+ * reference counterpart (single device: const.py:7). */
+int tcr_comm_set_sync_bn(tcr_handle* h, int32_t enable);
+
 /* Peer-memory gradient exchange over NVLink / NVSwitch (optional, same node, world_size <= 8): every rank exports two CUDA IPC
  * handles (128 bytes: its double-buffered flat gradient and its arrival flags), the host gathers all ranks' handles (rank-major,
  * world_size x 128 bytes) and every rank attaches them.  From then on the update kernel of tcr_train_step announces its gradient

@@ -801,6 +801,23 @@ extern "C" int tcr_comm_init(tcr_handle* h, const void* id128, int32_t rank, int
   int rc = comm_init(h, id128, rank, world_size);
   return rc ? fail(rc, "ncclCommInitRank failed: %s", comm_error()) : TCR_OK;
 }
+extern "C" int tcr_comm_set_sync_bn(tcr_handle* h, int32_t enable) {
+  if (!h) return fail(TCR_ERR_INVALID, "NULL argument");
+  if (enable && (!h->comm || h->world < 2)) return fail(TCR_ERR_INVALID, "SyncBN needs an initialised communicator (tcr_comm_init, world > 1)");
+  if (enable) {
+    for (auto& cv : h->convs) {
+      if (cv.fsync) continue;
+      void* p = nullptr;
+      TCR_CUDA(cudaMalloc(&p, (size_t)4 * cv.cout * sizeof(float)));
+      h->allocs.push_back(p);
+      cv.fsync = (float*)p;
+      cv.bsync = cv.fsync + 2 * cv.cout;
+    }
+  }
+  h->sync_bn = enable ? 1 : 0;
+  resident_destroy(h);               // the mode is decided again on the next step (SyncBN: per-layer kernels)
+  return TCR_OK;
+}
 extern "C" int tcr_comm_p2p_export(tcr_handle* h, void* handles128) {
   if (!h || !handles128) return fail(TCR_ERR_INVALID, "NULL argument");
   int rc = comm_p2p_export(h, handles128);

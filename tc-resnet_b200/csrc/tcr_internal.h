@@ -158,6 +158,7 @@ struct MovingSegment {      // one BN layer
 struct GradArgs {           // gradient finalisation (sum of partials + weight decay -> flat gradient)
   const OptSegment* segs; int nsegs; int64_t total; int fc_seg; const float* fc_part; int fc_R;
   const float* params; float weight_decay; float* grads; float* l2part;
+  float bn_grad_scale;      // 1, or 1/world with SyncBN: every rank then holds the GLOBAL sums for the gamma / beta gradients
 };
 struct WtLayer { int64_t w_off; float* wT; int k, cin, cout; int64_t begin; };
 struct WtArgs { WtLayer layer[kMaxConvs]; int nlayers; int64_t total; const float* params; };

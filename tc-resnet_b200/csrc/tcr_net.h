@@ -23,6 +23,9 @@ int augment_launch(const int16_t* pcm, int64_t pcm_stride, const tcr_augment_cli
 int eval_accumulate_launch(const float* scores, const float* onehot, int n, int classes, int topk, int64_t* counts, cudaStream_t s);
 int net_weight_transpose(tcr_handle* h, const float* params, cudaStream_t s);
 // Resident forward (tcr_resident.cu): the training forward + head as one cooperative kernel with SM-resident activations.
+int sync_records(tcr_handle* h, const float* part, int gc, int cols, float* out, cudaStream_t s);   // SyncBN: sum records, all-reduce
+inline bool sync_bn_on(const tcr_handle* h) { return h->sync_bn && h->world > 1 && h->comm; }
+inline float bn_inv(const tcr_handle* h, int n, int t) { return 1.0f / ((float)n * (float)t * (sync_bn_on(h) ? (float)h->world : 1.0f)); }
 int resident_mode(tcr_handle* h);      // 0: per-layer kernels, 1: resident forward, 2: resident forward + backward (dW inside), 3: resident forward + backward-data
 int resident_forward(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStream_t s);
 int resident_backward(tcr_handle* h, const float* feat, const tcr_step_args* a, float* grads, int* l2_records, cudaStream_t s);

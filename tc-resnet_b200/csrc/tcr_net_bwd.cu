@@ -429,7 +429,7 @@ __device__ __forceinline__ void dw_body(const BwdWeightArgs& a, int bx, int by, 
 // All layers' weight gradients in ONE launch: virtual CTA -> (layer, output-channel tile, row chunk) through a
 // static table, so ~600 CTAs of 256 threads keep every SM busy instead of ten serial 64-CTA launches.
 __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ layers, int nlayers, int n, const float* __restrict__ feat,
-                                                long long* tl, const int vb, unsigned char* smem_raw, const BsumSrc& bs0) {
+                                                long long* tl, const int vb, unsigned char* smem_raw, const BsumSrc& bs0, float inv_scale) {
   float* smem = reinterpret_cast<float*>(smem_raw);
   tl_stamp(tl, 4096 + vb, 0);
   int l = 0;
@@ -440,7 +440,7 @@ __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ laye
   BwdWeightArgs a;
   a.n = n;
   a.x = ActSrc{L.x_data ? L.x_data : feat, L.x_bnf, L.x_kind, StatSrc{}};     // tables were published during the forward pass
-  a.dy = DySrc{L.dz, L.y, L.bnf, L.bsum, L.mask_relu, 1.0f / ((float)n * (float)L.t_out), l == 0 ? bs0 : BsumSrc{nullptr, 0, nullptr}};
+  a.dy = DySrc{L.dz, L.y, L.bnf, L.bsum, L.mask_relu, 1.0f / ((float)n * (float)L.t_out) * inv_scale, l == 0 ? bs0 : BsumSrc{nullptr, 0, nullptr}};
   a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.stride = L.stride; a.t_in = L.t_in; a.t_out = L.t_out;
   a.pad_left = L.pad_left; a.cot = L.cot; a.RG = L.RG; a.R = L.R; a.UB = L.UB; a.dwpart = L.dwpart;
   const int bx = local % ncot, by = local / ncot;
@@ -452,10 +452,10 @@ __device__ __forceinline__ void dw_grouped_body(const DwLayer* __restrict__ laye
   if (tl && threadIdx.x == 0) { tl[(size_t)(4096 + vb) * 8 + 3] = l; tl[(size_t)(4096 + vb) * 8 + 4] = (long long)by; }
 }
 __global__ void __launch_bounds__(kDwThreads, 2) dw_grouped_kernel(const DwLayer* __restrict__ layers, int nlayers, int n,
-                                                                const float* __restrict__ feat, long long* tl, BsumSrc bs0) {
+                                                                const float* __restrict__ feat, long long* tl, BsumSrc bs0, float inv_scale) {
   TCR_DYNAMIC_SMEM(smem_raw);
   pdl_wait();
-  dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw, bs0);
+  dw_grouped_body(layers, nlayers, n, feat, tl, (int)blockIdx.x, smem_raw, bs0, inv_scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,9 +624,12 @@ static int launch_bwd_data(const char* name, const BwdDataArgs& a, int groups, s
   return 0;
 }
 
-static DySrc make_dy(const ConvPlan& cv, const float* dz, int mask, int n) {
-  return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, 1.0f / ((float)n * (float)cv.t_out),
-               BsumSrc{cv.b_gc ? cv.bpart : nullptr, cv.b_gc, cv.bsum}};
+static BsumSrc bsum_src(const tcr_handle* h, const ConvPlan& cv) {
+  if (sync_bn_on(h) && cv.b_gc) return BsumSrc{cv.bsync, 1, cv.bsum};          // SyncBN: the sums over all ranks as one record
+  return BsumSrc{cv.b_gc ? cv.bpart : nullptr, cv.b_gc, cv.bsum};
+}
+static DySrc make_dy(const tcr_handle* h, const ConvPlan& cv, const float* dz, int mask, int n) {
+  return DySrc{dz, cv.y, cv.bnf, cv.bsum, mask, bn_inv(h, n, cv.t_out), bsum_src(h, cv)};
 }
 
 // *gc_out: per-cluster records of BatchNorm-backward sums this launch leaves for the layer(s) below (0 when recording)
@@ -680,20 +683,21 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
     {
       BwdDataArgs a;
       memset(&a, 0, sizeof(a));
-      a.dy = make_dy(cb, b.gblk, 0, n);
+      a.dy = make_dy(h, cb, b.gblk, 0, n);
       a.epi_kind = 1;
       a.yp = ca.y; a.bnfp = ca.bnf; a.bpartp = ca.bpart; a.gprev = ca.g;
       int gc = 0;
       int rc = bwd_data(h, cb, nullptr, a, params, n, s, &gc);
       if (rc) return rc;
       ca.b_gc = gc;
+      if (sync_bn_on(h) && (rc = sync_records(h, ca.bpart, gc, 2 * ca.cout, ca.bsync, s))) return rc;
     }
     // (2) conv_a (+ down conv | identity): dx is the gradient at the block input
     {
       BwdDataArgs a;
       memset(&a, 0, sizeof(a));
-      a.dy = make_dy(ca, ca.g, 0, n);
-      if (dn) a.dyd = make_dy(*dn, b.gblk, 1, n);
+      a.dy = make_dy(h, ca, ca.g, 0, n);
+      if (dn) a.dyd = make_dy(h, *dn, b.gblk, 1, n);
       else a.gid = b.gblk;
       if (i > 0) {
         BlockPlan& pb = h->blocks[i - 1];
@@ -718,8 +722,17 @@ int net_backward(tcr_handle* h, const float* feat, const float* params, int n, c
         BlockPlan& pb = h->blocks[i - 1];
         h->convs[pb.b].b_gc = gc;
         if (pb.down >= 0) h->convs[pb.down].b_gc = gc;
+        if (sync_bn_on(h)) {
+          ConvPlan& q = h->convs[pb.b];
+          if ((rc = sync_records(h, q.bpart, gc, 2 * q.cout, q.bsync, s))) return rc;
+          if (pb.down >= 0) {
+            ConvPlan& qd = h->convs[pb.down];
+            if ((rc = sync_records(h, qd.bpart, gc, 2 * qd.cout, qd.bsync, s))) return rc;
+          }
+        }
       } else {
         h->convs[0].b_gc = gc;
+        if (sync_bn_on(h) && (rc = sync_records(h, h->convs[0].bpart, gc, 2 * h->convs[0].cout, h->convs[0].bsync, s))) return rc;
       }
     }
   }
@@ -736,8 +749,10 @@ int net_weight_gradients(tcr_handle* h, const float* feat, int n, cudaStream_t s
 #endif
     // conv0's BatchNorm-backward sums have no backward-data consumer: its weight-gradient CTAs add the records themselves
     const ConvPlan& c0 = h->convs[0];
-    const BsumSrc bs0{c0.b_gc ? c0.bpart : nullptr, c0.b_gc, c0.bsum};
-    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat, h->d_timeline, bs0);
+    const BsumSrc bs0 = bsum_src(h, c0);
+    const float inv_scale = sync_bn_on(h) ? 1.0f / (float)h->world : 1.0f;         // SyncBN: BatchNorm-backward means over the global rows
+    TCR_LAUNCH("dw_grouped", kfn, dim3(h->dw_ctas), dim3(kDwThreads), h->dw_smem, s, h->d_dw_layers, h->n_dw_layers, n, feat, h->d_timeline, bs0,
+               inv_scale);
   }
   return 0;
 }

@@ -634,8 +634,24 @@ int cluster_size(tcr_handle* h) {
   return h->cluster;
 }
 StatSrc stat_src(const tcr_handle* h, const ConvPlan& cv, const float* params, int n) {
+  if (sync_bn_on(h) && cv.f_gc)     // SyncBN: one "record" holding the sums over all ranks, count = global rows
+    return StatSrc{cv.fsync, 1, params + cv.gamma_off, params + cv.beta_off, cv.bnf, cv.var, bn_inv(h, n, cv.t_out), h->cfg.bn_epsilon};
   return StatSrc{cv.f_gc ? cv.fpart : nullptr, cv.f_gc, params + cv.gamma_off, params + cv.beta_off, cv.bnf, cv.var,
                  1.0f / ((float)n * (float)cv.t_out), h->cfg.bn_epsilon};
+}
+
+// SyncBN (parity tests only): out[c] = sum over this rank's records, then summed over the ranks by NCCL.
+__global__ void __launch_bounds__(256) records_sum_kernel(const float* __restrict__ part, int gc, int cols, float* __restrict__ out) {
+  pdl_wait();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < gc; ++g) s += part[(size_t)g * cols + c];
+    out[c] = s;
+  }
+}
+int sync_records(tcr_handle* h, const float* part, int gc, int cols, float* out, cudaStream_t s) {
+  TCR_LAUNCH("records_sum", records_sum_kernel, dim3(1), dim3(256), 0, s, part, gc, cols, out);
+  return comm_allreduce_sum(h, out, cols, s);
 }
 static ActSrc act_of(const tcr_handle* h, const ConvPlan& cv, int kind, const float* params, int n) {
   return ActSrc{cv.y, cv.bnf, kind, stat_src(h, cv, params, n)};
@@ -678,13 +694,21 @@ static int conv_fwd(tcr_handle* h, ConvPlan& cv, ConvPlan* dn, FwdArgs a, const 
     cv.f_gc = grid / CL;
     if (dn) dn->f_gc = grid / CL;
   }
+  int rc;
   switch (cv.k) {
-    case 3: return wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
-                       : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
-    case 9: return wsm ? launch_conv_fwd<9, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
-                       : launch_conv_fwd<9, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
+    case 3: rc = wsm ? launch_conv_fwd<3, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
+                     : launch_conv_fwd<3, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
+      break;
+    case 9: rc = wsm ? launch_conv_fwd<9, true>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL)
+                     : launch_conv_fwd<9, false>(("fwd:" + cv.name).c_str(), a, grid, smem, s, CL);
+      break;
     default: set_error("unsupported kernel width"); return TCR_ERR_UNSUPPORTED;
   }
+  if (!rc && training && sync_bn_on(h)) {
+    rc = sync_records(h, cv.fpart, cv.f_gc, 2 * cv.cout, cv.fsync, s);
+    if (!rc && dn) rc = sync_records(h, dn->fpart, dn->f_gc, 2 * dn->cout, dn->fsync, s);
+  }
+  return rc;
 }
 
 int net_forward(tcr_handle* h, const float* feat, const float* params, const float* moving, int n, bool training,
@@ -778,6 +802,11 @@ int net_forward(tcr_handle* h, const float* feat, const float* params, const flo
         if (optin.ensure(head_kernel, smem) != cudaSuccess) return TCR_ERR_CUDA;
 #endif
         TCR_LAUNCH_CLUSTER("head", head_kernel, dim3(grid), dim3(kHeadThreads), smem, s, CL, ha);
+      }
+      if (backward && sync_bn_on(h)) {
+        int rcs = sync_records(h, cb.bpart, cb.b_gc, 2 * cb.cout, cb.bsync, s);
+        if (!rcs && dn) rcs = sync_records(h, dn->bpart, dn->b_gc, 2 * dn->cout, dn->bsync, s);
+        if (rcs) return rcs;
       }
     }
     // the identity shortcut of the NEXT block is this block's materialised output; it is written by the next

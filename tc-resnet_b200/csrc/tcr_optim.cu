@@ -65,6 +65,8 @@ __device__ __forceinline__ void grad_finalize_body(const GradArgs& a, const int 
       const float w = params[p];
       g = fmaf(weight_decay, w, g);
       w2 = w * w;
+    } else {
+      g *= a.bn_grad_scale;          // gamma / beta (the only segments without decay)
     }
     grads[p] = g;
   }
@@ -256,7 +258,7 @@ int net_update(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStr
   if (p2p) ++h->p2p.step;
   float* grads = p2p ? h->p2p.grads + (size_t)(h->p2p.step & 1u) * h->n_train : h->d_grads;
   GradArgs ga{h->d_segs, h->n_segs, h->n_train, fc_segment(h), h->d_dwfc_part, h->fc_records, a->params, a->weight_decay,
-              grads, h->d_l2part};
+              grads, h->d_l2part, sync_bn_on(h) ? 1.0f / (float)h->world : 1.0f};
   int l2_records = blocks;
   if (resident_mode(h) == 2) {      // backward chain + weight gradients + this reduction in one cooperative kernel (tcr_resident.cu)
     int rc = resident_backward(h, feat, a, grads, &l2_records, s);
@@ -279,7 +281,7 @@ int net_update(tcr_handle* h, const float* feat, const tcr_step_args* a, cudaStr
   u.lr = a->learning_rate; u.momentum = a->momentum; u.weight_decay = a->weight_decay;
   u.one_minus_decay = (float)(1.0 - (double)h->cfg.bn_decay);
   u.grad_scale = 1.0f / (float)h->world;
-  u.msegs = h->d_msegs; u.nmsegs = h->n_msegs; u.n = a->n;
+  u.msegs = h->d_msegs; u.nmsegs = h->n_msegs; u.n = sync_bn_on(h) ? a->n * h->world : a->n;   // rows behind the batch variance
   u.l2part = h->d_l2part; u.l2blocks = l2_records;
   u.ce_sum = h->d_loss_part; u.ce_count = h->loss_gc; u.inv_n = 1.0f / (float)a->n;
   u.losses = a->losses; u.grads_out = a->grads; u.apply = a->apply_update ? 1 : 0;

@@ -28,6 +28,7 @@ struct ConvPlan {
   // per call: how many per-cluster records the producer launch of this step left in fpart / bpart (0: the global table /
   // sums are final: persistent kernel, evaluation tables)
   int f_gc = 0, b_gc = 0;
+  float* fsync = nullptr; float* bsync = nullptr;   // [2*cout] sums over ALL ranks (tcr_comm_set_sync_bn, parity tests only)
   int64_t wnumel() const { return (int64_t)k * cin * cout; }
 };
 
@@ -62,7 +63,8 @@ struct tcr_handle {
   void* fe_stream = nullptr; float* fe_feat[2] = {nullptr, nullptr}; void* fe_ready[2] = {nullptr, nullptr};
   void* fe_free[2] = {nullptr, nullptr}; long long fe_count = 0;
   float* fe_aug = nullptr;           // the ahead path's own decoded-wav buffer (device input stage)
-  float* feat_last = nullptr;        // feature buffer the library filled last ("features" of tcr_workspace_tensor)
+  float* feat_last = nullptr;
+  int sync_bn = 0;                   // BatchNorm statistics over the global batch (per-layer kernels + NCCL; tcr_comm_set_sync_bn)        // feature buffer the library filled last ("features" of tcr_workspace_tensor)
   float* d_logits = nullptr; float* d_probs = nullptr;
   float* d_loss_part = nullptr; float* d_loss = nullptr; float* d_dwfc_part = nullptr;
   float* d_grads = nullptr;

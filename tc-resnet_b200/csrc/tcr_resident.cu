@@ -1234,6 +1234,7 @@ static ResidentState* resident_state(tcr_handle* h) {
   // the weight-gradient FMA loops of mode 2 run 16 warps per SM where the grouped launch runs two CTAs per SM and loses to it.
   int want = 3;
   if (const char* e = getenv("TCR_RESIDENT")) want = atoi(e);
+  if (h->sync_bn) want = 0;          // SyncBN lives in the per-layer kernels' launch sequence (NCCL between launches)
   if (want <= 0) return S;
   int sms = 3;                       // emulator: a few CTAs exercise ragged ownership
 #ifndef TCR_EMU

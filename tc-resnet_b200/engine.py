@@ -234,6 +234,12 @@ class Engine:
         return counts
 
     # ------------------------------------------------------------------ data parallel
+    def set_sync_bn(self, enable: bool = True):
+        """Parity-test flag: BatchNorm statistics over the global batch of all ranks (= one device with batch
+        world * n).  Needs attach_process_group() first; the step then runs on the per-layer kernels with one small NCCL all-reduce
+        per BN layer, forward and backward.  The default (local statistics) is what production runs use."""
+        L.check(self.lib, self.lib.tcr_comm_set_sync_bn(self._h, int(bool(enable))), "tcr_comm_set_sync_bn")
+
     def attach_process_group(self):
         """One NCCL communicator per handle; the 128-byte unique id travels through torch.distributed."""
         import torch.distributed as dist

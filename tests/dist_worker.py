@@ -4,6 +4,8 @@ mode gloo : CPU, world 2.  Host-side DP logic: shard bounds, unique-id style byt
             GPU path relies on — mean over ranks of per-shard gradients (local BN statistics) == oracle computed
             shard-wise and averaged; a data-parallel SGD-momentum step on the averaged gradient keeps replicas identical.
 mode nccl : GPU, one rank per GPU.  The CUDA path with its NCCL all-reduce vs the same oracle average.
+mode syncbn : GPU, one rank per GPU.  tcr_comm_set_sync_bn: every rank's step must equal the oracle's SINGLE-device step on the
+            global batch (gradient, updated parameters, momentum slots, BatchNorm moving statistics).
 """
 import os
 import sys
@@ -94,5 +96,59 @@ def main():
     dist.destroy_process_group()
 
 
+def syncbn_main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    per = 12
+    n_global = per * world
+    spec = O.build_spec("TCResNet8", 1.0, 49)
+    params, moving = perturbed_variables(spec)
+    rng = np.random.RandomState(3)
+    slots = {k: 0.01 * rng.randn(*v.shape) for k, v in params.items()}
+    wav, onehot = O.synthetic_batch(n_global)
+    feat = O.mfcc(wav, 640, 320)
+    wd, lr, mom = 1e-3, 0.1, 0.9
+    # the reference's single device with the whole batch: global BatchNorm statistics, mean loss over world * per utterances
+    p1, mv1, sl1, ref = O.train_step(spec, params, moving, slots, feat, onehot, lr, mom, wd, 1.0, None, 0.0)
+    from tcresnet_b200.engine import Engine
+    eng = Engine(max_batch=per, dropout_keep_prob=1.0)
+    eng.attach_process_group()
+    eng.set_sync_bn(True)
+    dev = eng.device
+    p = torch.from_numpy(O.flatten_vars(spec, params)).to(dev)
+    mv = torch.from_numpy(O.flatten_moving(spec, moving)).to(dev)
+    sl = torch.from_numpy(O.flatten_vars(spec, slots)).to(dev)
+    lo, hi = rank * per, (rank + 1) * per
+    out = eng.train_step(torch.from_numpy(wav[lo:hi]).to(dev), torch.from_numpy(onehot[lo:hi]).to(dev), p, sl, mv, lr, mom, wd,
+                         want_grads=True)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        b = np.asarray(b, np.float64)
+        return float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())
+    errs = {"grads": rel(out["grads"].cpu().numpy(), O.flatten_vars(spec, ref["grads"], np.float64)),
+            "params": rel(p.cpu().numpy(), O.flatten_vars(spec, p1, np.float64)),
+            "slots": rel(sl.cpu().numpy(), O.flatten_vars(spec, sl1, np.float64)),
+            "moving": rel(mv.cpu().numpy(), O.flatten_moving(spec, mv1, np.float64))}
+    assert all(v < 1e-4 for v in errs.values()), f"rank {rank}: {errs}"
+    # and it differs from local statistics: the flag is not a no-op
+    eng.set_sync_bn(False)
+    p2 = torch.from_numpy(O.flatten_vars(spec, params)).to(dev)
+    out2 = eng.train_step(torch.from_numpy(wav[lo:hi]).to(dev), torch.from_numpy(onehot[lo:hi]).to(dev), p2, torch.zeros_like(p2),
+                          torch.from_numpy(O.flatten_moving(spec, moving)).to(dev), lr, mom, wd, want_grads=True)
+    local_err = rel(out2["grads"].cpu().numpy(), O.flatten_vars(spec, ref["grads"], np.float64))
+    assert local_err > 10 * errs["grads"], (local_err, errs)
+    if rank == 0:
+        print(f"syncbn world={world}: vs the oracle's single-device batch of {n_global}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()) +
+              f"; local-statistics gradient differs by {local_err:.2e}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1] == "syncbn":
+        syncbn_main()
+    else:
+        main()

@@ -30,3 +30,15 @@ def test_gradient_exchange_matches_oracle(exchange, env):
     r = _torchrun("nccl", min(torch.cuda.device_count(), 8), 29612 if exchange == "nccl" else 29613, env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "replicas bit-identical" in r.stdout and f"exchange={exchange}" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.gpu
+def test_sync_bn_flag_equals_single_device_global_batch():
+    """tcr_comm_set_sync_bn (parity-test flag): with BatchNorm statistics all-reduced over the ranks, every rank's
+    step equals the oracle's single-device step on the concatenated global batch."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun("syncbn", 2, 29614)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "syncbn world=2" in r.stdout, r.stdout[-500:]
