@@ -10,7 +10,7 @@ timeout 300 python bench.py --workload dscnn --steps 100 --warmup 10 > $O/bench_
 TCR_DSCNN_TC=0 timeout 300 python bench.py --workload dscnn --steps 100 --warmup 10 > $O/bench_dscnn_fma.json 2> $O/bench_dscnn_fma.err; echo "dscnn fma rc=$?"; cut -c1-300 $O/bench_dscnn_fma.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"; cut -c1-300 $O/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > $O/under_ncu.log 2>&1; echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:tcr:: -s 60 -c 20 -o $O/full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:tcr:: -s 12 -c 14 -o $O/full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:dscnn -s 12 -c 6 -o $O/dscnn python bench.py --workload dscnn --steps 3 --warmup 3 > $O/ncu_dscnn.log 2>&1; echo "ncu dscnn rc=$?"
 TCR_DSCNN_TC=0 timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active --clock-control none --kernel-name-base demangled -k regex:dscnn -s 12 -c 6 --csv --log-file $O/dscnn_fma.csv python bench.py --workload dscnn --steps 3 --warmup 3 > $O/ncu_dscnn_fma.log 2>&1; echo "ncu dscnn fma rc=$?"
 for tool in memcheck racecheck synccheck; do
