@@ -280,6 +280,9 @@ def kernel_work(plan, name, n):
     if name == "resident_fwd":        # all forward convs + head in one cooperative launch: reads the features, writes every pre-BN output
         b = n * (4 * plan.frames * plan.features + sum(4 * c.t_out * c.cout for c in plan.convs())) + 4 * sum(c.weights for c in plan.convs())
         return b, fwd_flops
+    if name == "resident_bwd_data":   # the backward-data chain alone: reads every layer's pre-BN output, writes every layer's gradient
+        b = n * sum(8 * c.t_out * c.cout for c in plan.convs()) + 4 * sum(c.weights for c in plan.convs()[1:])
+        return b, fwd_flops - 2.0 * n * plan.convs()[0].macs
     if name == "resident_bwd":        # backward-data chain + all weight gradients + gradient reduction
         b = n * (4 * plan.frames * plan.features + sum(4 * c.t_out * c.cout for c in plan.convs())) + 12 * sum(c.weights for c in plan.convs())
         return b, 2 * fwd_flops - 2.0 * n * plan.convs()[0].macs
@@ -532,7 +535,8 @@ def run_ours(a):
                 traffic_src = f"stale capture ignored ({tj.get('source')}: kernels_sha {tj.get('kernels_sha')} != {sources_sha()})"
             elif a.model == "TCResNet8" and a.width == 1.0 and n == 512:
                 ncu_name = {"mfcc": "mfcc_kernel", "dw_grouped": "dw_grouped_kernel", "head": "head_kernel",
-                            "resident_fwd": "resident_fwd_kernel", "resident_bwd": "resident_bwd_kernel"}.get(dom["name"])
+                            "resident_fwd": "resident_fwd_kernel", "resident_bwd": "resident_bwd_kernel",
+                            "resident_bwd_data": "resident_bwd_kernel"}.get(dom["name"])
                 for k, v in tj["bytes_per_launch"].items():
                     if ncu_name and k.startswith(ncu_name):
                         traffic, traffic_src = v, f"profiles/ncu_traffic_tcresnet8_b512.json ({tj['source']})"
