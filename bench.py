@@ -46,10 +46,10 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of BASELINE.json configs 3 and 5 carried in `extra`")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--frontend", default="auto", choices=["auto", "ordered", "ahead"],
-                    help="ordered: the front-end is ordered on the step's stream; ahead: the timed inputs are resident and final, so it "
-                         "runs on the library's own stream (tcr_step_args::input_resident) and overlaps the previous step's tail; "
-                         "auto = ordered (measured on 1 and 2 GPUs: with resident inputs the early front-end only time-slices with the "
-                         "weight-gradient kernel, 0.363 vs 0.357 ms/step; the host-buffer path always runs it ahead, behind its copy)")
+                    help="ordered: the front-end is ordered on the step's stream; ahead (= auto): the timed inputs are resident and final, so "
+                         "the call sets tcr_step_args::input_resident and the next step's front-end runs on the library's own stream behind "
+                         "the previous step's weight-gradient launch, i.e. next to grad_finalize / update and the cross-GPU arrival wait "
+                         "(measured: 0.348 -> 0.339 ms/step on 1 GPU, 0.359 -> 0.344 on 2)")
     ap.add_argument("--workload", default="train", choices=["train", "dscnn", "infer", "augment"],
                     help="train: the headline training step; dscnn: DS-CNN-S forward (BASELINE.json config 5, comparison point); "
                          "infer: evaluation-mode forward from wav (config 1 with --batch 1: latency); "
@@ -321,7 +321,7 @@ def run_ours(a):
     losses = torch.zeros(2, device=dev)
     lr, mom, wd = 0.1, 0.9, 1e-3
 
-    frontend_ahead = a.frontend == "ahead"
+    frontend_ahead = a.frontend != "ordered"
 
     def step(i):
         eng.train_step(wavs[i % rot], onehots[i % rot], params, slots, moving, lr, mom, wd, dropout_seed=i * world + rank, losses=losses,

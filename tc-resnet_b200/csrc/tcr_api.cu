@@ -542,6 +542,11 @@ static int frontend_ahead_get(tcr_handle* h) {
     h->fe_ready[b] = e0;
     h->fe_free[b] = e1;
   }
+  {
+    cudaEvent_t g = nullptr;
+    TCR_CUDA(cudaEventCreateWithFlags(&g, cudaEventDisableTiming));
+    h->fe_gate = g;
+  }
   h->fe_stream = st;
 #endif
   return TCR_OK;
@@ -554,6 +559,7 @@ static void frontend_ahead_destroy(tcr_handle* h) {
     if (h->fe_ready[b]) cudaEventDestroy((cudaEvent_t)h->fe_ready[b]);
     if (h->fe_free[b]) cudaEventDestroy((cudaEvent_t)h->fe_free[b]);
   }
+  if (h->fe_gate) cudaEventDestroy((cudaEvent_t)h->fe_gate);
   cudaStreamDestroy((cudaStream_t)h->fe_stream);
   h->fe_stream = nullptr;
 #else
@@ -581,6 +587,9 @@ static int train_step_impl(tcr_handle* h, const tcr_step_args* a, tcr_stream str
       cudaStream_t f = (cudaStream_t)h->fe_stream;
       if (input_event) TCR_CUDA(cudaStreamWaitEvent(f, (cudaEvent_t)input_event, 0));
       if (h->fe_count > 2) TCR_CUDA(cudaStreamWaitEvent(f, (cudaEvent_t)h->fe_free[fe_buf], 0));   // the step two calls back has read it
+      // not before the previous step's weight gradients are launched-and-done: the front-end then shares the GPU with the small,
+      // latency-bound tail kernels (grad_finalize, update and its cross-GPU arrival wait) instead of time-slicing with the FMA-bound ones
+      if (h->fe_gate_valid) TCR_CUDA(cudaStreamWaitEvent(f, (cudaEvent_t)h->fe_gate, 0));
       fs = (tcr_stream)f;
       featbuf = h->fe_feat[fe_buf];
     }
@@ -625,6 +634,12 @@ static int train_step_impl(tcr_handle* h, const tcr_step_args* a, tcr_stream str
     if (!rc) rc = net_weight_gradients(h, feat, a->n, s);
     if (rc) return fail(rc, "backward launch failed: %s", g_err);
   }
+#ifndef TCR_EMU
+  if (h->fe_gate) {                   // the gate of the NEXT step's front-end (see above)
+    TCR_CUDA(cudaEventRecord((cudaEvent_t)h->fe_gate, s));
+    h->fe_gate_valid = 1;
+  }
+#endif
   rc = net_update(h, feat, a, s);
   if (rc) return fail(rc, "update launch failed: %s", g_err);
   TCR_CUDA(cudaGetLastError());

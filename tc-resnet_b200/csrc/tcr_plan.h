@@ -63,6 +63,8 @@ struct tcr_handle {
   void* fe_stream = nullptr; float* fe_feat[2] = {nullptr, nullptr}; void* fe_ready[2] = {nullptr, nullptr};
   void* fe_free[2] = {nullptr, nullptr}; long long fe_count = 0;
   float* fe_aug = nullptr;           // the ahead path's own decoded-wav buffer (device input stage)
+  void* fe_gate = nullptr; int fe_gate_valid = 0;   // recorded on the step's stream once the weight gradients are launched: the next
+                                     // step's front-end starts behind it, i.e. next to grad_finalize / update, not next to the FMA-bound kernels
   float* feat_last = nullptr;
   int sync_bn = 0;                   // BatchNorm statistics over the global batch (per-layer kernels + NCCL; tcr_comm_set_sync_bn)        // feature buffer the library filled last ("features" of tcr_workspace_tensor)
   float* d_logits = nullptr; float* d_probs = nullptr;
