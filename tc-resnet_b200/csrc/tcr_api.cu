@@ -167,6 +167,15 @@ static int build_frontend_tables(tcr_handle* h) {
     h->c_win = (int)blk.size();
     blk.insert(blk.end(), win.begin(), win.end());
     pad4();
+    if (fft == 1024) {                             // frame-pair kernel: W_512^(n2 k1), k1 < 16 rows of n2 < 32
+      h->c_twa = (int)blk.size();
+      for (int k1 = 0; k1 < 16; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const double a = -2.0 * M_PI * (double)(n2 * k1) / 512.0;
+          blk.push_back((float)cos(a));
+          blk.push_back((float)sin(a));
+        }
+    }
     TCR_TRY(dev_upload(h, &h->d_fe_consts, blk));
   }
   TCR_TRY(dev_upload(h, &h->d_mel_start, start));
@@ -193,6 +202,7 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.use_dct = h->cfg.feature_kind == TCR_FEATURE_MFCC;
   a.consts = h->d_fe_consts;
   a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_smem = h->c_smem;
+  a.c_twa = h->c_twa;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;
@@ -365,6 +375,13 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
     if (got >= 1 && f >= 1) { h->fpb = std::min(f, h->frames); h->fwarps = std::min(h->fpb, 7); }
     if (got >= 2 && w >= 1) h->fwarps = std::min(std::min(w, 7), h->fpb);
   }
+  if (const char* e = getenv("TCR_MFCC_PAIR")) {                 // frame-pair kernel: 0 | 1 | frames per CTA (even)[,warps per CTA <= 5]
+    int f = 0, w = 0;
+    const int got = sscanf(e, "%d,%d", &f, &w);
+    h->mfcc_pair = got >= 1 && f >= 1;
+    if (got >= 1 && f >= 2) { h->pair_fpb = f & ~1; h->pair_warps = std::min(5, h->pair_fpb / 2); }
+    if (got >= 2 && w >= 1) h->pair_warps = std::min(std::min(w, 5), h->pair_fpb / 2);
+  }
   int rc = build_frontend_tables(h);
   if (rc) return bail(rc);
   rc = build_plan(h);
@@ -455,7 +472,17 @@ static int mfcc_run(tcr_handle* h, const void* wav, int pcm16, float* features, 
   if (pcm16 && (h->cfg.window_size_samples % 8 || h->cfg.window_stride_samples % 8 || h->cfg.clip_samples % 8))
     return fail(TCR_ERR_UNSUPPORTED, "int16 input needs window, stride and clip lengths that are multiples of 8 samples");
   MfccArgs a = mfcc_args(h, wav, pcm16, features);
-  if (mfcc_launch(a, n, h->fft, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc launch configuration failed");
+  bool launched = false;
+  if (h->mfcc_pair) {                                             // two frames per warp (tcr_mfcc_pair.cu) where the shape allows
+    MfccArgs b = a;
+    b.fpb = h->pair_fpb;
+    b.warps = h->pair_warps;
+    if (mfcc_pair_supported(b, h->fft)) {
+      if (mfcc_pair_launch(b, n, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc (frame pairs) launch configuration failed");
+      launched = true;
+    }
+  }
+  if (!launched && mfcc_launch(a, n, h->fft, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc launch configuration failed");
   TCR_CUDA(cudaGetLastError());
   return TCR_OK;
 }

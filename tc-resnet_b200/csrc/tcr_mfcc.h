@@ -17,6 +17,7 @@ struct MfccArgs {
   // one TMA bulk copy:  [0, 2*fft/2) tw exp(-2 pi i n / (fft/2)) | c_melw: packed mel weights | (c_smem) |
   //   c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_win: periodic Hann window [window]
   const float* consts; int c_tw2, c_melw, c_win, c_smem;
+  int c_twa;                // frame-pair kernel (tcr_mfcc_pair.cu): W_512^(n2 k1) as [16][32] float2, or -1 when not built
   const int* mel_start;     // [mel_bins] first FFT bin of the band's walk (a multiple of four; leading weights may be zero)
   const int* mel_len;       // [mel_bins] groups of four bins in the walk
   const int* mel_off;       // [mel_bins] offset into mel_w (a multiple of four)
@@ -25,5 +26,11 @@ struct MfccArgs {
 
 size_t mfcc_smem_bytes(const MfccArgs& a, int nf2, int warps);
 int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream);
+
+// tcr_mfcc_pair.cu: two frames per warp, register-resident 16 x 32 FFT; only the 640 / 320 / 1024 front-end shape, an even
+// number of frames per CTA and at most five warps
+bool mfcc_pair_supported(const MfccArgs& a, int fft_length);
+size_t mfcc_pair_smem_bytes(const MfccArgs& a, int warps);
+int mfcc_pair_launch(const MfccArgs& a, int n, cudaStream_t stream);
 
 }  // namespace tcr
