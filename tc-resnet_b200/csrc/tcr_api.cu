@@ -203,6 +203,8 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.consts = h->d_fe_consts;
   a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_smem = h->c_smem;
   a.c_twa = h->c_twa;
+  a.n_utts = 0;
+  a.variant = h->pair_variant;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;
@@ -350,6 +352,9 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
     return rc;
   };
   if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(TCR_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device));
+#ifndef TCR_EMU
+  if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || h->sms < 1) h->sms = 1;
+#endif
   h->frames = 1 + (cfg->clip_samples - cfg->window_size_samples) / cfg->window_stride_samples;
   h->features = cfg->feature_kind == TCR_FEATURE_MFCC ? cfg->num_mfccs : cfg->num_mel_bins;
   h->fft = next_pow2(cfg->window_size_samples);
@@ -375,13 +380,14 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
     if (got >= 1 && f >= 1) { h->fpb = std::min(f, h->frames); h->fwarps = std::min(h->fpb, 7); }
     if (got >= 2 && w >= 1) h->fwarps = std::min(std::min(w, 7), h->fpb);
   }
-  if (const char* e = getenv("TCR_MFCC_PAIR")) {                 // frame-pair kernel: 0 | 1 | frames per CTA (even)[,warps per CTA <= 5]
+  if (const char* e = getenv("TCR_MFCC_PAIR")) {                 // frame-pair kernel: 0 | 1 | frames per work item (even, <= 10)
     int f = 0, w = 0;
     const int got = sscanf(e, "%d,%d", &f, &w);
     h->mfcc_pair = got >= 1 && f >= 1;
-    if (got >= 1 && f >= 2) { h->pair_fpb = f & ~1; h->pair_warps = std::min(5, h->pair_fpb / 2); }
-    if (got >= 2 && w >= 1) h->pair_warps = std::min(std::min(w, 5), h->pair_fpb / 2);
+    if (got >= 1 && f >= 2) { h->pair_fpb = std::min(f & ~1, 10); h->pair_warps = h->pair_fpb / 2; }   // one warp per frame pair
+    (void)w;
   }
+  if (const char* e = getenv("TCR_MFCC_PAIR_VARIANT")) h->pair_variant = atoi(e);
   int rc = build_frontend_tables(h);
   if (rc) return bail(rc);
   rc = build_plan(h);
@@ -478,7 +484,7 @@ static int mfcc_run(tcr_handle* h, const void* wav, int pcm16, float* features, 
     b.fpb = h->pair_fpb;
     b.warps = h->pair_warps;
     if (mfcc_pair_supported(b, h->fft)) {
-      if (mfcc_pair_launch(b, n, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc (frame pairs) launch configuration failed");
+      if (mfcc_pair_launch(b, n, 3 * h->sms, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc (frame pairs) launch configuration failed");
       launched = true;
     }
   }

@@ -17,6 +17,8 @@ struct MfccArgs {
   // one TMA bulk copy:  [0, 2*fft/2) tw exp(-2 pi i n / (fft/2)) | c_melw: packed mel weights | (c_smem) |
   //   c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_win: periodic Hann window [window]
   const float* consts; int c_tw2, c_melw, c_win, c_smem;
+  int variant;              // frame-pair kernel: bit 0 = window loads requested ahead of the sample wait (TCR_MFCC_PAIR_VARIANT)
+  int n_utts;               // frame-pair kernel: utterances of the launch (set by mfcc_pair_launch)
   int c_twa;                // frame-pair kernel (tcr_mfcc_pair.cu): W_512^(n2 k1) as [16][32] float2, or -1 when not built
   const int* mel_start;     // [mel_bins] first FFT bin of the band's walk (a multiple of four; leading weights may be zero)
   const int* mel_len;       // [mel_bins] groups of four bins in the walk
@@ -31,6 +33,6 @@ int mfcc_launch(const MfccArgs& a, int n, int fft_length, cudaStream_t stream);
 // number of frames per CTA and at most five warps
 bool mfcc_pair_supported(const MfccArgs& a, int fft_length);
 size_t mfcc_pair_smem_bytes(const MfccArgs& a, int warps);
-int mfcc_pair_launch(const MfccArgs& a, int n, cudaStream_t stream);
+int mfcc_pair_launch(const MfccArgs& a, int n, int ctas, cudaStream_t stream);   // ctas: persistent grid (3 per SM)
 
 }  // namespace tcr

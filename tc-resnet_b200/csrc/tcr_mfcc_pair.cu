@@ -65,15 +65,14 @@ __device__ __forceinline__ void real_fft_bins(float2 zk, float2 zr, float2 tw, f
 
 // Dynamic shared memory (bytes): [0,16) mbarrier | staged samples (span_max x 4) | W_512^(n2 k1) table [16][32] float2 |
 // packed mel weights | per warp: exchange buffer (aliased by the two power spectra) + log-mel vectors of the two frames.
-template <bool PCM, bool MAG>
+// Persistent CTAs: a CTA walks work items (utterance, chunk of fpb = 2 x warps frames) with stride gridDim.x; one warp per
+// frame pair.  As soon as every warp has read its samples into registers (pass A), the TMA copy of the NEXT item's samples
+// is issued into the same buffer, so only the first item of a CTA waits for HBM.
+template <bool PCM, bool MAG, bool WINPRE>
 __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
   TCR_DYNAMIC_SMEM(smem);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  const int utt = blockIdx.y;
-  const int f0 = blockIdx.x * a.fpb;
-  const int nf = min(a.fpb, a.frames - f0);
   constexpr int SB = PCM ? 2 : 4;
 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -87,28 +86,48 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
   const float2* g_tw2 = reinterpret_cast<const float2*>(a.consts + a.c_tw2);
   const float2* g_win = reinterpret_cast<const float2*>(a.consts + a.c_win);
 
-  const int span = (nf - 1) * a.stride + a.window;
+  const int chunks = (a.frames + a.fpb - 1) / a.fpb;
+  const int items = a.n_utts * chunks;
+  // this lane's two mel bands (the usual <= 64 bins: one trip of the band loop), packed start/4 | len4 << 8 | off/4 << 16:
+  // constant tables, loaded ahead of the dependency wait
+  int band_lo = 0, band_hi = 0;
+  if (2 * lane < a.mel_bins) {
+    const int m0 = lane, m1 = a.mel_bins - 1 - lane;
+    band_lo = (__ldg(&a.mel_start[m0]) >> 2) | (__ldg(&a.mel_len[m0]) << 8) | ((__ldg(&a.mel_off[m0]) >> 2) << 16);
+    band_hi = (__ldg(&a.mel_start[m1]) >> 2) | (__ldg(&a.mel_len[m1]) << 8) | ((__ldg(&a.mel_off[m1]) >> 2) << 16);
+  }
+  auto issue = [&](int item, bool with_consts) {         // thread 0: stage the samples of a work item
+    const int utt = item / chunks, f0 = (item - utt * chunks) * a.fpb;
+    const int nf = min(a.fpb, a.frames - f0);
+    const uint32_t bytes = (uint32_t)((nf - 1) * a.stride + a.window) * SB;
+    mbar_expect_tx(bar, bytes + (with_consts ? 4096u + (uint32_t)melw_len * 4u : 0u));
+    tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB, bytes, bar);
+    if (with_consts) {
+      tma_load_1d(s_twa, a.consts + a.c_twa, 4096u, bar);
+      tma_load_1d(s_melw, a.consts + a.c_melw, (uint32_t)melw_len * 4u, bar);
+    }
+  };
   if (threadIdx.x == 0) mbar_init(bar, 1);
   pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)span * SB + 4096u + (uint32_t)melw_len * 4u);
-    tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB,
-                (uint32_t)span * SB, bar);
-    tma_load_1d(s_twa, a.consts + a.c_twa, 4096u, bar);
-    tma_load_1d(s_melw, a.consts + a.c_melw, (uint32_t)melw_len * 4u, bar);
-  }
-  mbar_wait(bar, 0);
-  __syncthreads();
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, true);
 
   const int k1 = lane & 15;
   const int partner = (lane & 16) | ((16 - k1) & 15);
-  const int npairs = (nf + 1) >> 1;
-  for (int p = warp; p < npairs; p += nwarps) {
-    const int fa = 2 * p;
-    const bool has_b = fa + 1 < nf;
+  uint32_t phase = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, phase ^= 1u) {
+    const int utt = item / chunks, f0 = (item - utt * chunks) * a.fpb;
+    const int nf = min(a.fpb, a.frames - f0);
+    const int fa = 2 * warp;                                 // this warp's frame pair (fa, fa + 1) of the chunk
+    const bool has_a = fa < nf, has_b = fa + 1 < nf;
     float2* xb = reinterpret_cast<float2*>(s_warp);
-    {
+    float2 win[kRowsIn];                                     // WINPRE: requested ahead of the wait for the samples
+    if (WINPRE) {
+#pragma unroll
+      for (int r = 0; r < kRowsIn; ++r) win[r] = __ldg(g_win + lane + 32 * r);
+    }
+    mbar_wait(bar, phase);
+    if (has_a) {
       // ---- pass A: framing + window + 16-point DFT over n1 for both frames, twiddle, exchange
       const unsigned char* x = s_wav + (size_t)fa * a.stride * SB;
       float2 raw[kRowsIn + kRowShift];
@@ -118,7 +137,7 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       float2 ina[kRowsIn], inb[kRowsIn];
 #pragma unroll
       for (int r = 0; r < kRowsIn; ++r) {
-        const float2 w = __ldg(g_win + lane + 32 * r);
+        const float2 w = WINPRE ? win[r] : __ldg(g_win + lane + 32 * r);
         ina[r] = make_float2(raw[r].x * w.x, raw[r].y * w.y);
         inb[r] = make_float2(raw[r + kRowShift].x * w.x, raw[r + kRowShift].y * w.y);
       }
@@ -135,7 +154,9 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
         xb[(16 + k) * kXRow + lane] = cmul2(yb[k], t);
       }
     }
-    __syncwarp();
+    __syncthreads();                                         // every warp holds its samples in registers / the exchange buffer
+    if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x, false);
+    if (!has_a) continue;
     float* pw = s_warp + (lane >> 4) * kPwStride;            // this lane's frame; aliases the exchange buffer
     {
       // ---- pass B: 32-point DFT over n2; lane (f, k1) ends up with X[k1 + 16 k2] in X[k2]
@@ -171,6 +192,17 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       if (k1 < 3) pw[kNF2 + 1 + k1] = 0.f;                   // the 4-wide band walk may read three bins past the spectrum
     }
     __syncwarp();
+    // DCT table entries of this lane (q, g) = (lane / 8, lane % 8): rows m = q + 4 i, coefficients g + 8 j.  Requested here so
+    // the loads fly during the band walk (the 40-coefficient fast path only; 40 registers that the walk does not need)
+    const bool dct40 = a.use_dct && a.features == 40 && a.mel_bins == 64;
+    float dtab[8][5];
+    if (dct40) {
+      const float* row = a.dct + (lane >> 3) * 40 + (lane & 7);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) dtab[i][j] = __ldg(row + i * 160 + 8 * j);
+    }
     // ---- banded mel + log for both frames: one weight load serves two spectra; a lane takes bands i and mel_bins-1-i
     float* lm = s_warp + kXbufFloats;
     {
@@ -182,11 +214,22 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
         for (int h = 0; h < 2; ++h) {
           const int m = h ? a.mel_bins - 1 - i : i;
           if (h && m == i) break;
-          const int start = __ldg(&a.mel_start[m]), len4 = __ldg(&a.mel_len[m]), off = __ldg(&a.mel_off[m]);
+          int start, len4, off;
+          if (i == lane) {
+            const int pk = h ? band_hi : band_lo;
+            start = (pk & 255) << 2;
+            len4 = (pk >> 8) & 255;
+            off = (pk >> 16) << 2;
+          } else {
+            start = __ldg(&a.mel_start[m]);
+            len4 = __ldg(&a.mel_len[m]);
+            off = __ldg(&a.mel_off[m]);
+          }
           const float* pa = pwa + start;
           const float* pb = pwb + start;
           const float* ww = s_melw + off;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 4
           for (int q = 0; q < len4; ++q) {
             const float4 w4 = ld4(ww + 4 * q), p4 = ld4(pa + 4 * q), r4 = ld4(pb + 4 * q);
             a0 = fmaf(p4.x, w4.x, a0);
@@ -207,8 +250,8 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
     float* outa = a.feat + ((size_t)utt * a.frames + (f0 + fa)) * a.features;
     float* outb = outa + a.features;
     if (a.use_dct) {
-      // DCT-II for both frames: lane (q, g) = (lane / 8, lane % 8) sums mel rows m = q, q + 4, ... for coefficients
-      // c = g, g + 8, ...; rows are folded by D[M-1-m][c] = (-1)^c D[m][c] (c = g + 8 j has the parity of g)
+      // DCT-II for both frames: lane (q, g) sums mel rows m = q, q + 4, ... for coefficients c = g, g + 8, ...; rows are
+      // folded by D[M-1-m][c] = (-1)^c D[m][c] (c = g + 8 j has the parity of g)
       const int q = lane >> 3, g = lane & 7;
       float acca[8], accb[8];
 #pragma unroll
@@ -216,17 +259,16 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       const int nj = (a.features + 7) >> 3;
       const int M = a.mel_bins, half = M >> 1;
       const float sgn = (g & 1) ? -1.f : 1.f;
-      if (a.features == 40) {                               // the usual 40 coefficients: five per lane, no bound checks
-#pragma unroll 4
-        for (int m = q; m < half; m += 4) {
-          const float va = fmaf(sgn, lm[M - 1 - m], lm[m]);
-          const float vb = fmaf(sgn, lm[lms + M - 1 - m], lm[lms + m]);
-          const float* row = a.dct + m * 40 + g;
+      if (dct40) {                                          // the usual 40 coefficients of 64 bins: table entries in registers
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = q + 4 * i;
+          const float va = fmaf(sgn, lm[63 - m], lm[m]);
+          const float vb = fmaf(sgn, lm[lms + 63 - m], lm[lms + m]);
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
-            const float d = __ldg(row + 8 * j);
-            acca[j] = fmaf(va, d, acca[j]);
-            accb[j] = fmaf(vb, d, accb[j]);
+            acca[j] = fmaf(va, dtab[i][j], acca[j]);
+            accb[j] = fmaf(vb, dtab[i][j], accb[j]);
           }
         }
       } else {
@@ -243,17 +285,17 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
               accb[j] = fmaf(vb, d, accb[j]);
             }
         }
-      }
-      if ((M & 1) && q == 0) {
-        const float va = lm[half], vb = lm[lms + half];
-        const float* row = a.dct + half * a.features + g;
+        if ((M & 1) && q == 0) {
+          const float va = lm[half], vb = lm[lms + half];
+          const float* row = a.dct + half * a.features + g;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nj && g + 8 * j < a.features) {
-            const float d = __ldg(row + 8 * j);
-            acca[j] = fmaf(va, d, acca[j]);
-            accb[j] = fmaf(vb, d, accb[j]);
-          }
+          for (int j = 0; j < 8; ++j)
+            if (j < nj && g + 8 * j < a.features) {
+              const float d = __ldg(row + 8 * j);
+              acca[j] = fmaf(va, d, acca[j]);
+              accb[j] = fmaf(vb, d, accb[j]);
+            }
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -279,7 +321,8 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
 }
 
 bool mfcc_pair_supported(const MfccArgs& a, int fft_length) {
-  return fft_length == 2 * kNF2 && a.window == 64 * kRowsIn && a.stride == 64 * kRowShift && a.c_twa >= 0 && (a.fpb % 2) == 0;
+  return fft_length == 2 * kNF2 && a.window == 64 * kRowsIn && a.stride == 64 * kRowShift && a.c_twa >= 0 && (a.fpb % 2) == 0 &&
+         a.fpb == 2 * a.warps && a.warps <= 5 && a.mel_bins <= 128;
 }
 
 size_t mfcc_pair_smem_bytes(const MfccArgs& a, int warps) {
@@ -288,15 +331,28 @@ size_t mfcc_pair_smem_bytes(const MfccArgs& a, int warps) {
   return 16 + (size_t)span_max * 4 + 4096 + (size_t)(a.c_smem - a.c_melw) * 4 + (size_t)warps * (kXbufFloats + 2 * lms) * 4;
 }
 
-int mfcc_pair_launch(const MfccArgs& a, int n, cudaStream_t stream) {
-  dim3 grid((a.frames + a.fpb - 1) / a.fpb, n, 1);
+int mfcc_pair_launch(const MfccArgs& a0, int n, int ctas, cudaStream_t stream) {
+  MfccArgs a = a0;
+  a.n_utts = n;
+  const int items = n * ((a.frames + a.fpb - 1) / a.fpb);
+  dim3 grid(ctas < items ? ctas : items, 1, 1);           // persistent: three CTAs per SM walk the work items
   dim3 block(32 * a.warps, 1, 1);
   const size_t smem = mfcc_pair_smem_bytes(a, a.warps);
-  auto k = a.pcm16 ? (a.magnitude ? mfcc_pair_kernel<true, true> : mfcc_pair_kernel<true, false>)
-                   : (a.magnitude ? mfcc_pair_kernel<false, true> : mfcc_pair_kernel<false, false>);
+  void (*k)(MfccArgs);
+  const int sel = (a.pcm16 ? 4 : 0) + (a.magnitude ? 2 : 0) + (a.variant & 1);
+  switch (sel) {
+    case 0: k = mfcc_pair_kernel<false, false, false>; break;
+    case 1: k = mfcc_pair_kernel<false, false, true>; break;
+    case 2: k = mfcc_pair_kernel<false, true, false>; break;
+    case 3: k = mfcc_pair_kernel<false, true, true>; break;
+    case 4: k = mfcc_pair_kernel<true, false, false>; break;
+    case 5: k = mfcc_pair_kernel<true, false, true>; break;
+    case 6: k = mfcc_pair_kernel<true, true, false>; break;
+    default: k = mfcc_pair_kernel<true, true, true>; break;
+  }
 #ifndef TCR_EMU
-  static SmemOptIn optin[4];
-  if (optin[(a.pcm16 ? 2 : 0) + (a.magnitude ? 1 : 0)].ensure(k, smem) != cudaSuccess) return 1;
+  static SmemOptIn optin[8];
+  if (optin[sel].ensure(k, smem) != cudaSuccess) return 1;
 #endif
   TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);
   return 0;
