@@ -167,7 +167,9 @@ static int build_frontend_tables(tcr_handle* h) {
     h->c_win = (int)blk.size();
     blk.insert(blk.end(), win.begin(), win.end());
     pad4();
-    if (fft == 1024) {                             // frame-pair kernel: W_512^(n2 k1), k1 < 16 rows of n2 < 32
+    if (fft == 1024 && M == 64) {
+      // frame-pair kernel (tcr_mfcc_pair.cu), one contiguous section staged by a single TMA copy:
+      //   W_512^(n2 k1), k1 < 16 rows of n2 < 32 | segment weights | DCT entries in lane order
       h->c_twa = (int)blk.size();
       for (int k1 = 0; k1 < 16; ++k1)
         for (int n2 = 0; n2 < 32; ++n2) {
@@ -175,6 +177,48 @@ static int build_frontend_tables(tcr_handle* h) {
           blk.push_back((float)cos(a));
           blk.push_back((float)sin(a));
         }
+      // Mel by SEGMENTS: the band edges cut the bins into M + 1 runs; a bin of run j rises in band j with weight
+      // u = (mel - edge_j) / (edge_j+1 - edge_j) and falls in band j - 1 with 1 - u, so with R_j = sum u P and S_j = sum P over
+      // the run, band_m = R_m + (S_m+1 - R_m+1): every bin and one weight are read once (167 groups of four instead of 282).
+      // A run is walked in aligned groups of four; bins of the groups that belong to a neighbouring run carry the marker -1.
+      std::vector<int> seg_of(bins, -1);
+      std::vector<double> up(bins, 0.0);
+      for (int k = 1; k < bins; ++k) {
+        const double fm = mel(nyq * k / (bins - 1));
+        for (int j = 0; j <= M; ++j)
+          if (fm >= edges[j] && fm < edges[j + 1]) {
+            seg_of[k] = j;
+            up[k] = (fm - edges[j]) / (edges[j + 1] - edges[j]);
+            break;
+          }
+      }
+      const int segw0 = (int)blk.size();
+      std::vector<int> seg_meta(3 * 32, 0);           // [pass][lane]: start/4 | groups << 8 | (offset/4 from the section start) << 16
+      for (int j = 0; j <= M; ++j) {
+        int first = -1, last = -1;
+        for (int k = 1; k < bins; ++k)
+          if (seg_of[k] == j) {
+            if (first < 0) first = k;
+            last = k;
+          }
+        if (first < 0) continue;
+        const int first4 = first & ~3, groups = (last - first4) / 4 + 1;
+        const int off4 = ((int)blk.size() - segw0) / 4;
+        for (int k = first4; k < first4 + 4 * groups; ++k) blk.push_back((k < bins && seg_of[k] == j) ? (float)up[k] : -1.0f);
+        // pass 0: lane i walks run i (i < 32); pass 1: lane i walks run 64 - i; pass 2: lane 0 walks run 32
+        const int slot = j < 32 ? j : (j > 32 ? 32 + (64 - j) : 64);
+        seg_meta[slot] = (first4 >> 2) | (groups << 8) | (off4 << 16);
+      }
+      h->pair_segw_len = (int)blk.size() - segw0;
+      // DCT entries in the order the kernel's lanes use them: lane (q, g) = (lane / 8, lane % 8), rows q + 4 i, columns g + 8 j
+      if (F == 40) {
+        for (int i = 0; i < 8; ++i)
+          for (int j = 0; j < 5; ++j)
+            for (int lane = 0; lane < 32; ++lane) blk.push_back(dct[(size_t)((lane >> 3) + 4 * i) * F + (lane & 7) + 8 * j]);
+        h->pair_dct_len = 8 * 5 * 32;
+      }
+      pad4();
+      TCR_TRY(dev_upload(h, &h->d_seg_meta, seg_meta));
     }
     TCR_TRY(dev_upload(h, &h->d_fe_consts, blk));
   }
@@ -203,6 +247,7 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.consts = h->d_fe_consts;
   a.c_tw2 = h->c_tw2; a.c_melw = h->c_melw; a.c_win = h->c_win; a.c_smem = h->c_smem;
   a.c_twa = h->c_twa;
+  a.seg_meta = h->d_seg_meta; a.segw_len = h->pair_segw_len; a.dct_len = h->pair_dct_len;
   a.n_utts = 0;
   a.variant = h->pair_variant;
   a.mel_start = h->d_mel_start;

@@ -19,7 +19,8 @@ struct MfccArgs {
   const float* consts; int c_tw2, c_melw, c_win, c_smem;
   int variant;              // frame-pair kernel: bit 0 = window loads requested ahead of the sample wait (TCR_MFCC_PAIR_VARIANT)
   int n_utts;               // frame-pair kernel: utterances of the launch (set by mfcc_pair_launch)
-  int c_twa;                // frame-pair kernel (tcr_mfcc_pair.cu): W_512^(n2 k1) as [16][32] float2, or -1 when not built
+  const int* seg_meta; int segw_len, dct_len;   // frame-pair kernel: runs of bins per (pass, lane), section lengths (floats)
+  int c_twa;                // frame-pair kernel (tcr_mfcc_pair.cu): section W_512^(n2 k1) [16][32] float2 | segment weights | DCT entries in lane order; -1 when not built
   const int* mel_start;     // [mel_bins] first FFT bin of the band's walk (a multiple of four; leading weights may be zero)
   const int* mel_len;       // [mel_bins] groups of four bins in the walk
   const int* mel_off;       // [mel_bins] offset into mel_w (a multiple of four)

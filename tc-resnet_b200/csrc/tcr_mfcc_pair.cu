@@ -79,33 +79,28 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
   unsigned char* s_wav = smem + 16;
   const int span_max = (a.fpb - 1) * a.stride + a.window;
   float* s_twa = reinterpret_cast<float*>(s_wav + (size_t)span_max * 4);
-  float* s_melw = s_twa + 2 * 16 * 32;
-  const int melw_len = a.c_smem - a.c_melw;
-  const int lms = (a.mel_bins + 3) & ~3;
-  float* s_warp = s_melw + melw_len + (size_t)warp * (kXbufFloats + 2 * lms);
+  const float* s_segw = s_twa + 2 * 16 * 32;                 // segment weights (see build_frontend_tables)
+  const float* s_dct = s_segw + a.segw_len;                  // DCT entries in lane order [8][5][32]
+  const int pair_len = 2 * 16 * 32 + a.segw_len + a.dct_len; // floats staged by one TMA copy
+  constexpr int lms = 64;                                    // mel bins (mfcc_pair_supported)
+  float* s_warp = s_twa + pair_len + (size_t)warp * (kXbufFloats + 2 * lms);
   const float2* g_tw2 = reinterpret_cast<const float2*>(a.consts + a.c_tw2);
   const float2* g_win = reinterpret_cast<const float2*>(a.consts + a.c_win);
 
   const int chunks = (a.frames + a.fpb - 1) / a.fpb;
   const int items = a.n_utts * chunks;
-  // this lane's two mel bands (the usual <= 64 bins: one trip of the band loop), packed start/4 | len4 << 8 | off/4 << 16:
-  // constant tables, loaded ahead of the dependency wait
-  int band_lo = 0, band_hi = 0;
-  if (2 * lane < a.mel_bins) {
-    const int m0 = lane, m1 = a.mel_bins - 1 - lane;
-    band_lo = (__ldg(&a.mel_start[m0]) >> 2) | (__ldg(&a.mel_len[m0]) << 8) | ((__ldg(&a.mel_off[m0]) >> 2) << 16);
-    band_hi = (__ldg(&a.mel_start[m1]) >> 2) | (__ldg(&a.mel_len[m1]) << 8) | ((__ldg(&a.mel_off[m1]) >> 2) << 16);
-  }
+  // the runs of bins this lane walks in the three mel passes (constant table, loaded ahead of the dependency wait):
+  // start/4 | groups << 8 | (weight offset / 4) << 16
+  int run[3];
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) run[ps] = __ldg(&a.seg_meta[32 * ps + lane]);
   auto issue = [&](int item, bool with_consts) {         // thread 0: stage the samples of a work item
     const int utt = item / chunks, f0 = (item - utt * chunks) * a.fpb;
     const int nf = min(a.fpb, a.frames - f0);
     const uint32_t bytes = (uint32_t)((nf - 1) * a.stride + a.window) * SB;
-    mbar_expect_tx(bar, bytes + (with_consts ? 4096u + (uint32_t)melw_len * 4u : 0u));
+    mbar_expect_tx(bar, bytes + (with_consts ? (uint32_t)pair_len * 4u : 0u));
     tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB, bytes, bar);
-    if (with_consts) {
-      tma_load_1d(s_twa, a.consts + a.c_twa, 4096u, bar);
-      tma_load_1d(s_melw, a.consts + a.c_melw, (uint32_t)melw_len * 4u, bar);
-    }
+    if (with_consts) tma_load_1d(s_twa, a.consts + a.c_twa, (uint32_t)pair_len * 4u, bar);
   };
   if (threadIdx.x == 0) mbar_init(bar, 1);
   pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
@@ -192,122 +187,86 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       if (k1 < 3) pw[kNF2 + 1 + k1] = 0.f;                   // the 4-wide band walk may read three bins past the spectrum
     }
     __syncwarp();
-    // DCT table entries of this lane (q, g) = (lane / 8, lane % 8): rows m = q + 4 i, coefficients g + 8 j.  Requested here so
-    // the loads fly during the band walk (the 40-coefficient fast path only; 40 registers that the walk does not need)
-    const bool dct40 = a.use_dct && a.features == 40 && a.mel_bins == 64;
-    float dtab[8][5];
-    if (dct40) {
-      const float* row = a.dct + (lane >> 3) * 40 + (lane & 7);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) dtab[i][j] = __ldg(row + i * 160 + 8 * j);
-    }
-    // ---- banded mel + log for both frames: one weight load serves two spectra; a lane takes bands i and mel_bins-1-i
+    // ---- mel by runs of bins + log, both frames: lane walks run `lane` (pass 0), run 64 - lane (pass 1) and lane 0 run 32
+    // (pass 2); per run R = sum u P (rising part of band j) and S - R = sum (1 - u) P (falling part of band j - 1)
     float* lm = s_warp + kXbufFloats;
     {
       const float* pwa = s_warp;
       const float* pwb = s_warp + kPwStride;
-#pragma unroll 1
-      for (int i = lane; 2 * i < a.mel_bins; i += 32) {
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int m = h ? a.mel_bins - 1 - i : i;
-          if (h && m == i) break;
-          int start, len4, off;
-          if (i == lane) {
-            const int pk = h ? band_hi : band_lo;
-            start = (pk & 255) << 2;
-            len4 = (pk >> 8) & 255;
-            off = (pk >> 16) << 2;
-          } else {
-            start = __ldg(&a.mel_start[m]);
-            len4 = __ldg(&a.mel_len[m]);
-            off = __ldg(&a.mel_off[m]);
-          }
-          const float* pa = pwa + start;
-          const float* pb = pwb + start;
-          const float* ww = s_melw + off;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-#pragma unroll 4
-          for (int q = 0; q < len4; ++q) {
-            const float4 w4 = ld4(ww + 4 * q), p4 = ld4(pa + 4 * q), r4 = ld4(pb + 4 * q);
-            a0 = fmaf(p4.x, w4.x, a0);
-            a1 = fmaf(p4.y, w4.y, a1);
-            a2 = fmaf(p4.z, w4.z, a2);
-            a3 = fmaf(p4.w, w4.w, a3);
-            b0 = fmaf(r4.x, w4.x, b0);
-            b1 = fmaf(r4.y, w4.y, b1);
-            b2 = fmaf(r4.z, w4.z, b2);
-            b3 = fmaf(r4.w, w4.w, b3);
-          }
-          lm[m] = logf(((a0 + a1) + (a2 + a3)) + 1e-6f);
-          lm[lms + m] = logf(((b0 + b1) + (b2 + b3)) + 1e-6f);
+      float ua[3], va[3], ub[3], vb[3];
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const int groups = (run[ps] >> 8) & 255;
+        const float* pa = pwa + ((run[ps] & 255) << 2);
+        const float* pb = pwb + ((run[ps] & 255) << 2);
+        const float* tw = s_segw + ((run[ps] >> 16) << 2);
+        float ra0 = 0.f, ra1 = 0.f, ra2 = 0.f, ra3 = 0.f, sa0 = 0.f, sa1 = 0.f, sa2 = 0.f, sa3 = 0.f;
+        float rb0 = 0.f, rb1 = 0.f, rb2 = 0.f, rb3 = 0.f, sb0 = 0.f, sb1 = 0.f, sb2 = 0.f, sb3 = 0.f;
+#pragma unroll 2
+        for (int q = 0; q < groups; ++q) {
+          const float4 t4 = ld4(tw + 4 * q), p4 = ld4(pa + 4 * q), r4 = ld4(pb + 4 * q);
+          // marker -1: the bin belongs to a neighbouring run (weight 0, not counted in S)
+          const float t0 = fmaxf(t4.x, 0.f), t1 = fmaxf(t4.y, 0.f), t2 = fmaxf(t4.z, 0.f), t3 = fmaxf(t4.w, 0.f);
+          const float m0 = t4.x >= 0.f ? 1.f : 0.f, m1 = t4.y >= 0.f ? 1.f : 0.f, m2 = t4.z >= 0.f ? 1.f : 0.f, m3 = t4.w >= 0.f ? 1.f : 0.f;
+          ra0 = fmaf(p4.x, t0, ra0); ra1 = fmaf(p4.y, t1, ra1); ra2 = fmaf(p4.z, t2, ra2); ra3 = fmaf(p4.w, t3, ra3);
+          sa0 = fmaf(p4.x, m0, sa0); sa1 = fmaf(p4.y, m1, sa1); sa2 = fmaf(p4.z, m2, sa2); sa3 = fmaf(p4.w, m3, sa3);
+          rb0 = fmaf(r4.x, t0, rb0); rb1 = fmaf(r4.y, t1, rb1); rb2 = fmaf(r4.z, t2, rb2); rb3 = fmaf(r4.w, t3, rb3);
+          sb0 = fmaf(r4.x, m0, sb0); sb1 = fmaf(r4.y, m1, sb1); sb2 = fmaf(r4.z, m2, sb2); sb3 = fmaf(r4.w, m3, sb3);
         }
+        ua[ps] = (ra0 + ra1) + (ra2 + ra3);
+        va[ps] = ((sa0 + sa1) + (sa2 + sa3)) - ua[ps];
+        ub[ps] = (rb0 + rb1) + (rb2 + rb3);
+        vb[ps] = ((sb0 + sb1) + (sb2 + sb3)) - ub[ps];
       }
+      // band m = R_m + (S - R)_m+1.  Band `lane`: own R of pass 0 + the falling part of run lane + 1 (next lane's pass 0; run 32
+      // is lane 0's pass 2).  Band 63 - lane: R of run 63 - lane (next lane's pass 1; run 32 again) + own falling part of pass 1.
+      const float va_next = __shfl_down_sync(0xffffffffu, va[0], 1), vb_next = __shfl_down_sync(0xffffffffu, vb[0], 1);
+      const float ua_next = __shfl_down_sync(0xffffffffu, ua[1], 1), ub_next = __shfl_down_sync(0xffffffffu, ub[1], 1);
+      const float va_32 = __shfl_sync(0xffffffffu, va[2], 0), vb_32 = __shfl_sync(0xffffffffu, vb[2], 0);
+      const float ua_32 = __shfl_sync(0xffffffffu, ua[2], 0), ub_32 = __shfl_sync(0xffffffffu, ub[2], 0);
+      const bool last = lane == 31;
+      // the falling part is a difference: clamp the (rounding-sized) negative values it can take next to a strong line
+      const float lo_a = fmaxf(ua[0] + (last ? va_32 : va_next), 0.f), lo_b = fmaxf(ub[0] + (last ? vb_32 : vb_next), 0.f);
+      const float hi_a = fmaxf((last ? ua_32 : ua_next) + va[1], 0.f), hi_b = fmaxf((last ? ub_32 : ub_next) + vb[1], 0.f);
+      lm[lane] = logf(lo_a + 1e-6f);
+      lm[63 - lane] = logf(hi_a + 1e-6f);
+      lm[lms + lane] = logf(lo_b + 1e-6f);
+      lm[lms + 63 - lane] = logf(hi_b + 1e-6f);
     }
     __syncwarp();
     float* outa = a.feat + ((size_t)utt * a.frames + (f0 + fa)) * a.features;
     float* outb = outa + a.features;
     if (a.use_dct) {
-      // DCT-II for both frames: lane (q, g) sums mel rows m = q, q + 4, ... for coefficients c = g, g + 8, ...; rows are
-      // folded by D[M-1-m][c] = (-1)^c D[m][c] (c = g + 8 j has the parity of g)
+      // DCT-II (40 of 64) for both frames: lane (q, g) = (lane / 8, lane % 8) sums mel rows m = q + 4 i for coefficients
+      // c = g + 8 j; rows are folded by D[63-m][c] = (-1)^c D[m][c] (c has the parity of g); the table sits in shared memory
+      // in lane order, so each entry is one conflict-free 4-byte load that serves both frames
       const int q = lane >> 3, g = lane & 7;
-      float acca[8], accb[8];
+      float acca[5], accb[5];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acca[j] = accb[j] = 0.f;
-      const int nj = (a.features + 7) >> 3;
-      const int M = a.mel_bins, half = M >> 1;
+      for (int j = 0; j < 5; ++j) acca[j] = accb[j] = 0.f;
       const float sgn = (g & 1) ? -1.f : 1.f;
-      if (dct40) {                                          // the usual 40 coefficients of 64 bins: table entries in registers
+      const float* tab = s_dct + lane;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = q + 4 * i;
-          const float va = fmaf(sgn, lm[63 - m], lm[m]);
-          const float vb = fmaf(sgn, lm[lms + 63 - m], lm[lms + m]);
+      for (int i = 0; i < 8; ++i) {
+        const int m = q + 4 * i;
+        const float va = fmaf(sgn, lm[63 - m], lm[m]);
+        const float vb = fmaf(sgn, lm[lms + 63 - m], lm[lms + m]);
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            acca[j] = fmaf(va, dtab[i][j], acca[j]);
-            accb[j] = fmaf(vb, dtab[i][j], accb[j]);
-          }
-        }
-      } else {
-#pragma unroll 2
-        for (int m = q; m < half; m += 4) {
-          const float va = fmaf(sgn, lm[M - 1 - m], lm[m]);
-          const float vb = fmaf(sgn, lm[lms + M - 1 - m], lm[lms + m]);
-          const float* row = a.dct + m * a.features + g;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nj && g + 8 * j < a.features) {
-              const float d = __ldg(row + 8 * j);
-              acca[j] = fmaf(va, d, acca[j]);
-              accb[j] = fmaf(vb, d, accb[j]);
-            }
-        }
-        if ((M & 1) && q == 0) {
-          const float va = lm[half], vb = lm[lms + half];
-          const float* row = a.dct + half * a.features + g;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nj && g + 8 * j < a.features) {
-              const float d = __ldg(row + 8 * j);
-              acca[j] = fmaf(va, d, acca[j]);
-              accb[j] = fmaf(vb, d, accb[j]);
-            }
+        for (int j = 0; j < 5; ++j) {
+          const float d = tab[(i * 5 + j) * 32];
+          acca[j] = fmaf(va, d, acca[j]);
+          accb[j] = fmaf(vb, d, accb[j]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < nj) {
-          acca[j] += __shfl_xor_sync(0xffffffffu, acca[j], 8);
-          accb[j] += __shfl_xor_sync(0xffffffffu, accb[j], 8);
-          acca[j] += __shfl_xor_sync(0xffffffffu, acca[j], 16);
-          accb[j] += __shfl_xor_sync(0xffffffffu, accb[j], 16);
-          if (q == 0 && g + 8 * j < a.features) {
-            outa[g + 8 * j] = acca[j];
-            if (has_b) outb[g + 8 * j] = accb[j];
-          }
+      for (int j = 0; j < 5; ++j) {
+        acca[j] += __shfl_xor_sync(0xffffffffu, acca[j], 8);
+        accb[j] += __shfl_xor_sync(0xffffffffu, accb[j], 8);
+        acca[j] += __shfl_xor_sync(0xffffffffu, acca[j], 16);
+        accb[j] += __shfl_xor_sync(0xffffffffu, accb[j], 16);
+        if (q == 0) {
+          outa[g + 8 * j] = acca[j];
+          if (has_b) outb[g + 8 * j] = accb[j];
         }
       }
     } else {
@@ -322,13 +281,13 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
 
 bool mfcc_pair_supported(const MfccArgs& a, int fft_length) {
   return fft_length == 2 * kNF2 && a.window == 64 * kRowsIn && a.stride == 64 * kRowShift && a.c_twa >= 0 && (a.fpb % 2) == 0 &&
-         a.fpb == 2 * a.warps && a.warps <= 5 && a.mel_bins <= 128;
+         a.fpb == 2 * a.warps && a.warps <= 5 && a.mel_bins == 64 && a.seg_meta != nullptr &&
+         (a.use_dct ? (a.features == 40 && a.dct_len == 8 * 5 * 32) : a.features == 64);
 }
 
 size_t mfcc_pair_smem_bytes(const MfccArgs& a, int warps) {
   const int span_max = (a.fpb - 1) * a.stride + a.window;
-  const int lms = (a.mel_bins + 3) & ~3;
-  return 16 + (size_t)span_max * 4 + 4096 + (size_t)(a.c_smem - a.c_melw) * 4 + (size_t)warps * (kXbufFloats + 2 * lms) * 4;
+  return 16 + (size_t)span_max * 4 + (size_t)(2 * 16 * 32 + a.segw_len + a.dct_len) * 4 + (size_t)warps * (kXbufFloats + 2 * 64) * 4;
 }
 
 int mfcc_pair_launch(const MfccArgs& a0, int n, int ctas, cudaStream_t stream) {
