@@ -219,7 +219,6 @@ static int build_frontend_tables(tcr_handle* h) {
       }
       pad4();
       TCR_TRY(dev_upload(h, &h->d_seg_meta, seg_meta));
-      TCR_TRY(dev_upload(h, &h->d_pair_ctr, std::vector<int>(16, 0)));
     }
     TCR_TRY(dev_upload(h, &h->d_fe_consts, blk));
   }
@@ -250,7 +249,7 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.c_twa = h->c_twa;
   a.seg_meta = h->d_seg_meta; a.segw_len = h->pair_segw_len; a.dct_len = h->pair_dct_len;
   a.n_utts = 0;
-  a.work_ctr = nullptr;
+  a.variant = h->pair_variant;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;
@@ -433,6 +432,7 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
     if (got >= 1 && f >= 2) { h->pair_fpb = std::min(f & ~1, 10); h->pair_warps = h->pair_fpb / 2; }   // one warp per frame pair
     (void)w;
   }
+  if (const char* e = getenv("TCR_MFCC_PAIR_VARIANT")) h->pair_variant = atoi(e);
   int rc = build_frontend_tables(h);
   if (rc) return bail(rc);
   rc = build_plan(h);
@@ -528,7 +528,6 @@ static int mfcc_run(tcr_handle* h, const void* wav, int pcm16, float* features, 
     MfccArgs b = a;
     b.fpb = h->pair_fpb;
     b.warps = h->pair_warps;
-    b.work_ctr = h->d_pair_ctr ? h->d_pair_ctr + 2 * (h->pair_launches++ & 7u) : nullptr;   // launches in flight never share counters
     if (mfcc_pair_supported(b, h->fft)) {
       if (mfcc_pair_launch(b, n, 3 * h->sms, (cudaStream_t)stream) != 0) return fail(TCR_ERR_CUDA, "mfcc (frame pairs) launch configuration failed");
       launched = true;

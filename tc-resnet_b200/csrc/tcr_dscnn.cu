@@ -449,6 +449,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) dscnn_dsblock_tc_kernel(DsLayer
 // tmem_empty (epilogue warps).  A rows are packed to the tile's own row count (rounded to 8): the M = 128 MMA then reads a few
 // rows of the next K chunk as rows >= npos, whose accumulator rows are never stored.
 constexpr int kWsProducerWarps = 10, kWsProducers = 32 * kWsProducerWarps, kWsFetchers = 128;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {       // arrives when this thread's earlier cp.asyncs have landed
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void real_fft_bins(float2 zk, float2 zr, float2 tw, f
 // Persistent CTAs: a CTA walks work items (utterance, chunk of fpb = 2 x warps frames) with stride gridDim.x; one warp per
 // frame pair.  As soon as every warp has read its samples into registers (pass A), the TMA copy of the NEXT item's samples
 // is issued into the same buffer, so only the first item of a CTA waits for HBM.
-template <bool PCM, bool MAG>
+template <bool PCM, bool MAG, bool WINPRE>
 __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
   TCR_DYNAMIC_SMEM(smem);
   const int lane = threadIdx.x & 31;
@@ -102,29 +102,26 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
     tma_load_1d(s_wav, reinterpret_cast<const unsigned char*>(a.wav) + ((size_t)utt * a.clip + (size_t)f0 * a.stride) * SB, bytes, bar);
     if (with_consts) tma_load_1d(s_twa, a.consts + a.c_twa, (uint32_t)pair_len * 4u, bar);
   };
-  int* s_cnt = reinterpret_cast<int*>(smem + 8);            // warps that have read the current item's samples
-  volatile int* s_next = reinterpret_cast<volatile int*>(smem + 12);   // next work item of this CTA (-1: none left)
-  const int nwarps = blockDim.x >> 5;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    *s_cnt = 0;
-    *s_next = -1;
-  }
+  if (threadIdx.x == 0) mbar_init(bar, 1);
   pdl_wait();                       // the wav buffer and the feature buffer belong to the caller / the previous step
   __syncthreads();
-  if (threadIdx.x == 0) issue(blockIdx.x, true);             // the grid never exceeds the number of items
+  if (threadIdx.x == 0 && (int)blockIdx.x < items) issue(blockIdx.x, true);
 
   const int k1 = lane & 15;
   const int partner = (lane & 16) | ((16 - k1) & 15);
   uint32_t phase = 0;
-  mbar_wait(bar, phase);
-  for (int item = blockIdx.x;;) {
-    phase ^= 1u;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, phase ^= 1u) {
     const int utt = item / chunks, f0 = (item - utt * chunks) * a.fpb;
     const int nf = min(a.fpb, a.frames - f0);
     const int fa = 2 * warp;                                 // this warp's frame pair (fa, fa + 1) of the chunk
     const bool has_a = fa < nf, has_b = fa + 1 < nf;
     float2* xb = reinterpret_cast<float2*>(s_warp);
+    float2 win[kRowsIn];                                     // WINPRE: requested ahead of the wait for the samples
+    if (WINPRE) {
+#pragma unroll
+      for (int r = 0; r < kRowsIn; ++r) win[r] = __ldg(g_win + lane + 32 * r);
+    }
+    mbar_wait(bar, phase);
     if (has_a) {
       // ---- pass A: framing + window + 16-point DFT over n1 for both frames, twiddle, exchange
       const unsigned char* x = s_wav + (size_t)fa * a.stride * SB;
@@ -135,7 +132,7 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       float2 ina[kRowsIn], inb[kRowsIn];
 #pragma unroll
       for (int r = 0; r < kRowsIn; ++r) {
-        const float2 w = __ldg(g_win + lane + 32 * r);
+        const float2 w = WINPRE ? win[r] : __ldg(g_win + lane + 32 * r);
         ina[r] = make_float2(raw[r].x * w.x, raw[r].y * w.y);
         inb[r] = make_float2(raw[r + kRowShift].x * w.x, raw[r + kRowShift].y * w.y);
       }
@@ -152,28 +149,9 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
         xb[(16 + k) * kXRow + lane] = cmul2(yb[k], t);
       }
     }
-    // This warp no longer needs the staged samples (they sit in registers / the exchange buffer).  The LAST warp of the CTA to
-    // get here takes the next work item from the launch's counter and starts its TMA copy into the same buffer; nobody waits.
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      if (atomicAdd(s_cnt, 1) == nwarps - 1) {
-        atomicExch(s_cnt, 0);
-        const int nxt = (int)gridDim.x + atomicAdd(a.work_ctr, 1);
-        if (nxt < items) {
-          *s_next = nxt;
-          issue(nxt, false);                                 // the arrive of expect_tx publishes s_next with the phase
-        } else {
-          *s_next = -1;
-          mbar_arrive(bar);                                  // complete the phase the other warps wait for: they see -1 and leave
-          if (atomicAdd(a.work_ctr + 1, 1) == (int)gridDim.x - 1) {   // last CTA to run dry: reset the counters for the next launch
-            a.work_ctr[0] = 0;
-            a.work_ctr[1] = 0;
-          }
-        }
-      }
-    }
-    if (has_a) {
+    __syncthreads();                                         // every warp holds its samples in registers / the exchange buffer
+    if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x, false);
+    if (!has_a) continue;
     float* pw = s_warp + (lane >> 4) * kPwStride;            // this lane's frame; aliases the exchange buffer
     {
       // ---- pass B: 32-point DFT over n2; lane (f, k1) ends up with X[k1 + 16 k2] in X[k2]
@@ -298,16 +276,12 @@ __global__ void __launch_bounds__(160, 3) mfcc_pair_kernel(MfccArgs a) {
       }
     }
     __syncwarp();
-    }                                                        // has_a
-    mbar_wait(bar, phase);                                   // the next item's samples have landed (or there is none)
-    item = *s_next;
-    if (item < 0) break;
   }
 }
 
 bool mfcc_pair_supported(const MfccArgs& a, int fft_length) {
   return fft_length == 2 * kNF2 && a.window == 64 * kRowsIn && a.stride == 64 * kRowShift && a.c_twa >= 0 && (a.fpb % 2) == 0 &&
-         a.fpb == 2 * a.warps && a.warps <= 5 && a.mel_bins == 64 && a.seg_meta != nullptr && a.work_ctr != nullptr &&
+         a.fpb == 2 * a.warps && a.warps <= 5 && a.mel_bins == 64 && a.seg_meta != nullptr &&
          (a.use_dct ? (a.features == 40 && a.dct_len == 8 * 5 * 32) : a.features == 64);
 }
 
@@ -323,11 +297,20 @@ int mfcc_pair_launch(const MfccArgs& a0, int n, int ctas, cudaStream_t stream) {
   dim3 grid(ctas < items ? ctas : items, 1, 1);           // persistent: three CTAs per SM walk the work items
   dim3 block(32 * a.warps, 1, 1);
   const size_t smem = mfcc_pair_smem_bytes(a, a.warps);
-  auto k = a.pcm16 ? (a.magnitude ? mfcc_pair_kernel<true, true> : mfcc_pair_kernel<true, false>)
-                   : (a.magnitude ? mfcc_pair_kernel<false, true> : mfcc_pair_kernel<false, false>);
-  const int sel = (a.pcm16 ? 2 : 0) + (a.magnitude ? 1 : 0);
+  void (*k)(MfccArgs);
+  const int sel = (a.pcm16 ? 4 : 0) + (a.magnitude ? 2 : 0) + (a.variant & 1);
+  switch (sel) {
+    case 0: k = mfcc_pair_kernel<false, false, false>; break;
+    case 1: k = mfcc_pair_kernel<false, false, true>; break;
+    case 2: k = mfcc_pair_kernel<false, true, false>; break;
+    case 3: k = mfcc_pair_kernel<false, true, true>; break;
+    case 4: k = mfcc_pair_kernel<true, false, false>; break;
+    case 5: k = mfcc_pair_kernel<true, false, true>; break;
+    case 6: k = mfcc_pair_kernel<true, true, false>; break;
+    default: k = mfcc_pair_kernel<true, true, true>; break;
+  }
 #ifndef TCR_EMU
-  static SmemOptIn optin[4];
+  static SmemOptIn optin[8];
   if (optin[sel].ensure(k, smem) != cudaSuccess) return 1;
 #endif
   TCR_LAUNCH("mfcc", k, grid, block, smem, stream, a);

@@ -20,12 +20,13 @@ run() {  # label frontend env...
   env "$@" timeout 200 python bench.py --steps 100 --warmup 10 --frontend $fe --no-cpu-baseline --no-e2e --no-extra > $O/b_$label.json 2> $O/b_$label.err
   show "$label" $O/b_$label.json
 }
+run old_ordered ordered TCR_MFCC_PAIR=0
 run new_ordered ordered TCR_MFCC_PAIR=1
 run new_ahead ahead TCR_MFCC_PAIR=1
-PREV=$(ls tools/ab/*.so 2>/dev/null | head -1)
-if [ -n "$PREV" ]; then
-  cp tc-resnet_b200/libtcr_b200.so $O/new.so; cp $PREV tc-resnet_b200/libtcr_b200.so
+if [ -f tools/ab/libtcr_pair_v2.so ]; then
+  cp tc-resnet_b200/libtcr_b200.so $O/new.so; cp tools/ab/libtcr_pair_v2.so tc-resnet_b200/libtcr_b200.so
   run prev_ordered ordered TCR_MFCC_PAIR=1
+  run prev_ahead ahead TCR_MFCC_PAIR=1
   cp $O/new.so tc-resnet_b200/libtcr_b200.so; rm -f $O/new.so
 fi
 run new_ordered2 ordered TCR_MFCC_PAIR=1
