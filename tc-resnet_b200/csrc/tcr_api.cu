@@ -249,7 +249,6 @@ static MfccArgs mfcc_args(const tcr_handle* h, const void* wav, int pcm16, float
   a.c_twa = h->c_twa;
   a.seg_meta = h->d_seg_meta; a.segw_len = h->pair_segw_len; a.dct_len = h->pair_dct_len;
   a.n_utts = 0;
-  a.variant = h->pair_variant;
   a.mel_start = h->d_mel_start;
   a.mel_len = h->d_mel_len;
   a.mel_off = h->d_mel_off;
@@ -432,7 +431,6 @@ extern "C" int tcr_create(const tcr_config* cfg, tcr_handle** out) {
     if (got >= 1 && f >= 2) { h->pair_fpb = std::min(f & ~1, 10); h->pair_warps = h->pair_fpb / 2; }   // one warp per frame pair
     (void)w;
   }
-  if (const char* e = getenv("TCR_MFCC_PAIR_VARIANT")) h->pair_variant = atoi(e);
   int rc = build_frontend_tables(h);
   if (rc) return bail(rc);
   rc = build_plan(h);

@@ -17,7 +17,6 @@ struct MfccArgs {
   // one TMA bulk copy:  [0, 2*fft/2) tw exp(-2 pi i n / (fft/2)) | c_melw: packed mel weights | (c_smem) |
   //   c_tw2: tw2 exp(-2 pi i k / fft), k <= fft/2 | c_win: periodic Hann window [window]
   const float* consts; int c_tw2, c_melw, c_win, c_smem;
-  int variant;              // frame-pair kernel: bit 0 = window loads requested ahead of the sample wait (TCR_MFCC_PAIR_VARIANT)
   int n_utts;               // frame-pair kernel: utterances of the launch (set by mfcc_pair_launch)
   const int* seg_meta; int segw_len, dct_len;   // frame-pair kernel: runs of bins per (pass, lane), section lengths (floats)
   int c_twa;                // frame-pair kernel (tcr_mfcc_pair.cu): section W_512^(n2 k1) [16][32] float2 | segment weights | DCT entries in lane order; -1 when not built

@@ -44,7 +44,7 @@ struct BlockPlan {
 struct tcr_handle {
   tcr_config cfg;
   int frames = 0, features = 0, fft = 0, fpb = 1, fwarps = 1;
-  int mfcc_pair = 1, pair_fpb = 10, pair_warps = 5, c_twa = -1, sms = 1, pair_variant = 0, pair_segw_len = 0, pair_dct_len = 0;
+  int mfcc_pair = 1, pair_fpb = 10, pair_warps = 5, c_twa = -1, sms = 1, pair_segw_len = 0, pair_dct_len = 0;
   int* d_seg_meta = nullptr;   // frame-pair front-end kernel (tcr_mfcc_pair.cu)
   std::string scope;
   std::vector<tcr::ConvPlan> convs;

@@ -129,3 +129,12 @@ def run_case(backend, model="TCResNet8", wm=1.0, window=640, stride=320, n=4, ke
         return report
     finally:
         eng.close()
+
+
+def spectral_lines():
+    """Seven full-scale sines (on and between bin centres; 2296.875 Hz = bin 147 has the smallest falling mel weight) over a
+    -60 dB noise floor: the worst case of the frame-pair front-end kernel's run-based mel stage."""
+    t = np.arange(16000) / 16000.0
+    rng = np.random.default_rng(3)
+    return np.stack([np.sin(2 * np.pi * f * t) for f in (100.0, 437.3, 2296.875, 2345.6, 3999.0, 6999.9, 7590.0)]) \
+        + 1e-3 * rng.uniform(-1, 1, (7, 16000))

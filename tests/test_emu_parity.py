@@ -127,3 +127,37 @@ def test_batch_larger_than_workspace_is_an_error(backend):
     with pytest.raises(Exception, match="max_batch"):
         eng.mfcc(wav)
     eng.close()
+
+
+@pytest.mark.parametrize("pair", ["1", "4", "0"], ids=["pairs-10-per-item", "pairs-4-per-item", "one-frame-per-warp"])
+def test_both_front_end_kernels_match_the_oracle(backend, monkeypatch, pair):
+    """TCR_MFCC_PAIR: the frame-pair kernel (tcr_mfcc_pair.cu, default for the 640 / 320 / 1024 shape; 49 frames = an odd count, so
+    the last work item of an utterance ends on half a pair) and the one-frame-per-warp kernel (tcr_mfcc.cu), MFCC and log-mel,
+    fp32 and int16 input, silence and a full-scale square wave among the clips."""
+    monkeypatch.setenv("TCR_MFCC_PAIR", pair)
+    wav, _ = O.synthetic_batch(5, adversarial=True)
+    for kind, ref in ((0, O.mfcc(wav, 640, 320)), (1, O.log_mel_spectrogram(wav, 640, 320, magnitude_squared=False))):
+        eng = Engine(backend, feature_kind=kind, max_batch=8)
+        got = eng.mfcc(wav)
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) < (1e-6 if kind == 0 else 2e-5)
+        pcm = np.clip(np.round(wav * 32768.0), -32768, 32767).astype(np.int16)
+        assert np.array_equal(eng.mfcc(pcm), eng.mfcc(pcm.astype(np.float32) / 32768.0))
+        eng.close()
+
+
+def test_single_spectral_lines_through_the_run_based_mel_stage(backend, monkeypatch):
+    """The frame-pair kernel forms the falling half of a band as a difference (sum P - sum u P over a run of bins), worst on a
+    band that one spectral line dominates (bin 147 = 2296.875 Hz has the smallest 1 - u).  Strong lines over a -60 dB floor:
+    the error is the fp32 FFT's round-off floor under the line in BOTH kernels; the run-based stage must not add to it."""
+    from parity_cases import spectral_lines
+    tones = spectral_lines()
+    err = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("TCR_MFCC_PAIR", pair)
+        for kind, ref in ((0, O.mfcc(tones, 640, 320)), (1, O.log_mel_spectrogram(tones, 640, 320, magnitude_squared=False))):
+            eng = Engine(backend, feature_kind=kind, max_batch=8)
+            err[pair, kind] = rel_err(eng.mfcc(tones), ref)
+            eng.close()
+    assert err["1", 0] < 2e-5 and err["1", 0] < 1.5 * err["0", 0] + 1e-7
+    assert err["1", 1] < 1e-3 and err["1", 1] < 1.5 * err["0", 1] + 1e-7

@@ -258,3 +258,35 @@ def test_frontend_running_ahead_is_bitwise_equal(backend):
         eng.close()
     for x, y in zip(*results):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("pair", ["1", "6", "0"], ids=["pairs-10-per-item", "pairs-6-per-item", "one-frame-per-warp"])
+def test_both_front_end_kernels_on_sm100a(backend, monkeypatch, pair):
+    """TCR_MFCC_PAIR on the GPU: frame-pair kernel (default) and one-frame-per-warp kernel against the fp64 oracle, MFCC and
+    log-mel, noise + silence + full-scale square wave, n not a multiple of anything; int16 input bit-identical to the decoded
+    samples."""
+    monkeypatch.setenv("TCR_MFCC_PAIR", pair)
+    wav, _ = O.synthetic_batch(37, adversarial=True)
+    for kind, ref in ((0, O.mfcc(wav, 640, 320)), (1, O.log_mel_spectrogram(wav, 640, 320, magnitude_squared=False))):
+        eng = Engine(backend, feature_kind=kind, max_batch=64)
+        got = eng.mfcc(wav)
+        assert rel_err(got, ref) < (2e-6 if kind == 0 else 2e-5)
+        pcm = np.clip(np.round(wav * 32768.0), -32768, 32767).astype(np.int16)
+        assert np.array_equal(eng.mfcc(pcm), eng.mfcc(pcm.astype(np.float32) / 32768.0))
+        eng.close()
+
+
+def test_spectral_lines_through_the_run_based_mel_stage_on_sm100a(backend, monkeypatch):
+    """Strong spectral lines over a -60 dB floor (see tests/test_emu_parity.py): the frame-pair kernel's run-based mel stage must
+    not add to the fp32 FFT round-off that both kernels show under a line."""
+    from parity_cases import spectral_lines
+    tones = spectral_lines()
+    err = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("TCR_MFCC_PAIR", pair)
+        for kind, ref in ((0, O.mfcc(tones, 640, 320)), (1, O.log_mel_spectrogram(tones, 640, 320, magnitude_squared=False))):
+            eng = Engine(backend, feature_kind=kind, max_batch=8)
+            err[pair, kind] = rel_err(eng.mfcc(tones), ref)
+            eng.close()
+    assert err["1", 0] < 2e-5 and err["1", 0] < 2.0 * err["0", 0] + 1e-6
+    assert err["1", 1] < 1e-3 and err["1", 1] < 2.0 * err["0", 1] + 1e-6
