@@ -534,9 +534,9 @@ def run_ours(a):
             if tj.get("kernels_sha") != sources_sha():           # a capture of OTHER kernels is not evidence for these
                 traffic_src = f"stale capture ignored ({tj.get('source')}: kernels_sha {tj.get('kernels_sha')} != {sources_sha()})"
             elif a.model == "TCResNet8" and a.width == 1.0 and n == 512:
-                ncu_name = {"mfcc": "mfcc_kernel", "dw_grouped": "dw_grouped_kernel", "head": "head_kernel",
-                            "resident_fwd": "resident_fwd_kernel", "resident_bwd": "resident_bwd_kernel",
-                            "resident_bwd_data": "resident_bwd_kernel"}.get(dom["name"])
+                ncu_name = {"mfcc": ("mfcc_pair_kernel", "mfcc_kernel"), "dw_grouped": ("dw_grouped_kernel",), "head": ("head_kernel",),
+                            "resident_fwd": ("resident_fwd_kernel",), "resident_bwd": ("resident_bwd_kernel",),
+                            "resident_bwd_data": ("resident_bwd_kernel",)}.get(dom["name"])
                 for k, v in tj["bytes_per_launch"].items():
                     if ncu_name and k.startswith(ncu_name):
                         traffic, traffic_src = v, f"profiles/ncu_traffic_tcresnet8_b512.json ({tj['source']})"
