@@ -84,3 +84,11 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.replace("tcr_oracle_free", ""), f"{f} mentions the oracle"
                 assert "cuda_emu" not in src or f == "tcr_device.cuh", f"{f} references the test emulator"
+
+
+def test_generated_register_dft_header_is_current():
+    """csrc/tcr_fft_reg.cuh is generated (tools/gen_fft_reg.py): the committed file is what the generator emits today."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_fft_reg.py")], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "tc-resnet_b200", "csrc", "tcr_fft_reg.cuh")).read()
